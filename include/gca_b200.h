@@ -1,0 +1,182 @@
+/* gca_b200.h -- C ABI of libgca_b200.so, the B200 (sm_100a) implementation of GCA's contrastive hot path.
+ *
+ * The reference (ACMMM2021-Anonymous/video-graph-ssl) is pure Python/PyTorch and has no FFI of its own;
+ * the boundary it offers is a set of nn.Module call conventions.  Each entry point
+ * below states the reference code it replaces (paths relative to the reference repo).  The Python mirror of
+ * those module interfaces lives in video-graph-ssl_b200/gca_b200/ and binds this header with ctypes
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller, contiguous, 16-byte aligned; row-major.
+ *   - the library allocates no persistent device memory, frees nothing, never synchronises the device;
+ *     scratch space is caller-provided (`gca_*_workspace_bytes`).  Every call only enqueues work on
+ *     `stream` (a cudaStream_t passed as void*) and returns.
+ *   - return value: GCA_OK or a negative GCA_ERR_*; `gca_last_error()` gives a thread-local message.
+ *     No exceptions, no abort, and NO CPU FALLBACK: without a CUDA device every compute call fails.
+ *   - thread-safety: re-entrant; the only global state is a per-thread cache of TMA descriptors.
+ *   - `dtype_queue`: GCA_F32 = queue rows stored fp32 (parity mode), GCA_BF16 = stored bf16 (fast mode).
+ *   - temperature is passed as inv_T = 1/T.
+ */
+#ifndef GCA_B200_H
+#define GCA_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCA_ABI_VERSION 1
+
+#define GCA_OK               0
+#define GCA_ERR_BAD_ARG     (-1)
+#define GCA_ERR_UNSUPPORTED (-2)
+#define GCA_ERR_CUDA        (-3)
+#define GCA_ERR_WORKSPACE   (-4)
+
+#define GCA_F32  0
+#define GCA_BF16 1
+
+/* kernel family for the InfoNCE stream */
+#define GCA_ALGO_AUTO    0   /* tcgen05 when (bf16 queue, d == 128), else ffma */
+#define GCA_ALGO_FFMA    1   /* CUDA-core fp32 FMA, exact fp32 arithmetic (parity mode), any d % 32 == 0, d <= 1024 */
+#define GCA_ALGO_TCGEN05 2   /* TMA -> smem -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM); bf16 queue, d == 128 */
+
+/* graph head flags (0 = the reference's arithmetic) */
+#define GCA_GRAPH_REFERENCE 0u
+
+int         gca_version(void);
+const char* gca_last_error(void);
+/* number of SMs of the current device, or a negative error */
+int         gca_sm_count(void);
+/* number of kernels this library has launched in this process so far (bench.py's gpu_launches bookkeeping) */
+long long   gca_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * MoCo queue: in-place ring-buffer enqueue.
+ * Replaces BaseMoCo._update_memory (lib/memory/mem_moco.py:17-27): ids = (arange(N) + index) mod K,
+ * queue.index_copy_(0, ids, keys).  The caller keeps the pointer and advances it itself
+ * ((index + N) % K, mem_moco.py:14-15).
+ *   queue    : [k_end - k_begin, d] rows of the shard holding GLOBAL slots [k_begin, k_end) of a ring of
+ *              K_global slots (single GPU: k_begin = 0, k_end = K_global)
+ *   keys     : [N, d] fp32; stored as-is (GCA_F32) or rounded to nearest-even bf16 (GCA_BF16)
+ *   index    : global pointer BEFORE this enqueue.  Requires N <= K_global (the reference's index_copy_
+ *              with duplicate indices is undefined); d % 4 == 0.
+ * --------------------------------------------------------------------------------------------------------- */
+int gca_enqueue(void* queue, int dtype_queue, long long K_global, long long k_begin, long long k_end, int d,
+                const float* keys, int N, long long index, void* stream);
+
+/* Same enqueue with the ring pointer in DEVICE memory, for CUDA-graph replay: state[0] = pointer (read by the
+ * kernel, advanced by N modulo K_global when the kernel finishes), state[1] = scratch ticket, must start at 0. */
+int gca_enqueue_devptr(void* queue, int dtype_queue, long long K_global, long long k_begin, long long k_end, int d,
+                       const float* keys, int N, long long* state, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * InfoNCE head, single device.  One call = RGBMoCo._compute_logit (mem_moco.py:29-49) + NCESoftmaxLoss
+ * (lib/memory/criterion.py:34-45) + the rank of the positive that `accuracy` (lib/evaluation/metric.py:44-67)
+ * derives from the logits + (optionally) dLoss/dq, without the [B, K+1] logits ever reaching HBM.
+ *   q, k        : [B, d] fp32 (k is treated as a constant, mem_moco.py:69)
+ *   queue       : [K, d] (dtype_queue) -- read in place; the caller orders it before this step's enqueue
+ *   outputs     : loss_mean[1]   = mean_b (lse_b - pos_b)                   (criterion.py:44)
+ *                 loss_rows[B], lse[B] (log-sum-exp over the K+1 logits), pos_logit[B] = q_b.k_b / T
+ *                 rank_gt[B]     = number of negatives STRICTLY greater than the positive (top-k hit <=> < k)
+ *                 dq_unit[B, d]  = d loss_mean / d q (may be NULL: forward only)
+ *                 logits_out     = [B, K+1] fp32 materialised logits (may be NULL; FFMA algo only)
+ *   workspace   : gca_infonce_workspace_bytes(...) bytes of scratch
+ * Deterministic: partial results are merged in a fixed order (no floating-point atomics).
+ * --------------------------------------------------------------------------------------------------------- */
+size_t gca_infonce_workspace_bytes(int B, long long K, int d, int dtype_queue, int algo);
+
+int gca_infonce_fwd(const float* q, const float* k, const void* queue, int dtype_queue,
+                    int B, long long K, int d, float inv_T, int algo,
+                    float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt,
+                    float* dq_unit, float* logits_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stage 1 of gca_infonce_fwd on its own: only the queue-streaming kernel, leaving the per-split partials in the
+ * workspace (layout: csrc/gca_common.cuh).  For profiling / roofline timing of the dominant kernel. */
+int gca_infonce_partials(const float* q, const float* k, const void* queue, int dtype_queue,
+                         int B, long long K, int d, float inv_T, int algo, int want_acc,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Two-pass backward by recomputation (north_star formulation): dq = grad_scale * d sum_b(loss_b) / dq, given the
+ * row log-sum-exp from the forward pass.  The queue must still hold the rows the forward pass saw (i.e. call
+ * before the enqueue, or on a snapshot): mem_moco.py:72-73 take the logits from a clone made before :82. */
+int gca_infonce_bwd(const float* q, const float* k, const void* queue, int dtype_queue,
+                    int B, long long K, int d, float inv_T, int algo,
+                    const float* lse, float grad_scale, float* dq,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * InfoNCE head with the queue sharded along K over `W` ranks (replaces the replicated queue of
+ * tools/train_video_contrast_dis.py:233-242 + mem_moco.py:81-83).  Per step and rank:
+ *   1. gca_infonce_shard_fwd   : all B_glob gathered rows against the local shard -> online-softmax partials
+ *   2. (caller) all-gather of part_max / part_sum / part_cnt over ranks           -> [W, B_glob] each
+ *   3. gca_infonce_shard_combine: merge the W partials and the positive -> lse, loss rows, rank; scales this
+ *                                 rank's part_acc by exp(part_max - lse) in place
+ *   4. (caller) reduce-scatter(sum) of part_acc over ranks                         -> acc [B_loc, d]
+ *   5. gca_infonce_shard_finish: dq_unit = ((exp(pos - lse) - 1) k + acc) / (T * B_loc), loss_mean over B_loc
+ * part_max is in natural-log units (max logit of the shard), part_sum = sum exp(logit - part_max),
+ * part_acc[b, :] = sum_j exp(logit_bj - part_max_b) queue_j.
+ * --------------------------------------------------------------------------------------------------------- */
+int gca_infonce_shard_fwd(const float* q, const float* k, const void* shard, int dtype_queue,
+                          int B, long long K_shard, int d, float inv_T, int algo,
+                          float* pos_logit, float* part_max, float* part_sum, int* part_cnt, float* part_acc,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+int gca_infonce_shard_combine(const float* all_max, const float* all_sum, const int* all_cnt, int W, int rank_id,
+                              int B, int d, const float* pos_logit,
+                              float* lse, float* loss_rows, int* rank_gt, float* part_acc, void* stream);
+
+int gca_infonce_shard_finish(const float* acc, const float* k, const float* pos_logit, const float* lse,
+                             const float* loss_rows, int B_loc, int d, float inv_T,
+                             float* dq_unit, float* loss_mean, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Temporal clip-graph head.  Replaces, for one GCN layer (the shipped default), the part of
+ * TemporalGraphAug.forward (lib/ops/module_wrappers/temporal_graph.py:227-239) between the 1x1x1 convolutions:
+ * similarity + row softmax (:161-176), hop mask and theta(hop) weights (:25-36, :204-210), relaxed-Bernoulli
+ * re-sampling with caller-supplied uniforms (:187-192), aggregation + skip (:59-62).  The convolutions / pooling
+ * (:119-129, :58) stay with cuDNN in the caller.
+ *   gq, gk   : [B, Cq, T, S]  projections in conv-output layout (S = H'*W'); the dot product runs over (Cq, S)
+ *   support  : [B, C, T, HW]  GCN conv output
+ *   u        : [B, T, T]      uniforms in [0, 1) drawn by the caller (torch.rand, same generator state as the
+ *                             reference's rsample would consume)
+ *   outputs  : sim, adj, s [B, T, T] (kept for backward), y [B, C, T, HW]
+ *   T <= 32; S % 4 == 0 or S == 1 is handled; any HW.
+ * --------------------------------------------------------------------------------------------------------- */
+int gca_graph_fwd(const float* gq, const float* gk, int Cq, int S, const float* support, int C, int HW,
+                  int T, int B, const float* u, float alpha, int max_hop, float temperature, unsigned flags,
+                  float* sim, float* adj, float* s, float* y, void* stream);
+
+int gca_graph_bwd(const float* gq, const float* gk, int Cq, int S, const float* support, int C, int HW,
+                  int T, int B, const float* sim, const float* adj, const float* s, const float* dy,
+                  float alpha, int max_hop, float temperature, unsigned flags,
+                  float* d_gq, float* d_gk, float* d_support,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* scratch for gca_graph_bwd ([B, T, T] fp32 d_logit; only touched for large feature maps) */
+size_t gca_graph_workspace_bytes(int B, int T);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * SimSiam negative cosine.  Replaces D.forward 'v2' (lib/memory/criterion.py:53-62 == lib/modeling/
+ * graph_wrappers.py:99-108): loss = -mean_b cos(p_b, stopgrad(z_b)), eps = 1e-8 as F.cosine_similarity.
+ *   loss[1], cos_rows[B] (may be NULL), dp_unit[B, d] = d loss / d p (may be NULL)
+ * --------------------------------------------------------------------------------------------------------- */
+int gca_negcos_fwd_bwd(const float* p, const float* z, int B, int d, float* loss, float* cos_rows, float* dp_unit,
+                       void* workspace, size_t workspace_bytes, void* stream);
+size_t gca_negcos_workspace_bytes(int B, int d);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Retrieval: cosine similarity + per-query top-k.  Replaces the arithmetic of topk_retrieval
+ * (tools/video_retrieval.py:174-186): optional L2 normalisation, cosine distance matrix, argsort -- only the k
+ * nearest are produced (k <= 64), most similar first, ties towards the lower gallery index.
+ *   queries [Nq, d], gallery [Ng, d] fp32; idx_out [Nq, k] int32; val_out [Nq, k] fp32 cosine (may be NULL)
+ * --------------------------------------------------------------------------------------------------------- */
+size_t gca_sim_topk_workspace_bytes(int Nq, int Ng, int d, int k);
+int gca_sim_topk(const float* queries, const float* gallery, int Nq, int Ng, int d, int k, int normalize,
+                 int* idx_out, float* val_out, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCA_B200_H */

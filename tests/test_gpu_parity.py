@@ -1,0 +1,500 @@
+"""GPU parity tests proper: every C-ABI entry point against the CPU oracle / the golden fixtures generated from the
+reference, on the same seeded inputs.  Integer and index work is compared bit-exactly; floating point within the
+tolerances BASELINE.json states: loss 1e-5 relative (fp32 mode) / 2e-3 (bf16 mode), gradients 1e-2 relative.
+Run with `pytest -m gpu` on a B200."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from oracle import graph as og
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL_FP32 = 1e-5
+LOSS_RTOL_BF16 = 2e-3
+GRAD_RTOL = 1e-2
+
+
+def T_(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def cu(t):
+    return t.cuda()
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rel_max(a, b):
+    """max |a - b| / max |b|  (norm-wise relative error)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def GF(lib):
+    import gca_b200
+    from gca_b200 import functional
+    return functional
+
+
+def unit_rows(n, d, gen):
+    return F.normalize(torch.randn(n, d, generator=gen))
+
+
+# ============================================================================================ K3 enqueue
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("K,d,N,index", [(256, 128, 8, 0), (256, 128, 40, 236), (256, 128, 256, 17), (4096, 128, 64, 4086),
+                                         (96, 32, 96, 95), (65536, 128, 512, 65400), (64, 1024, 3, 62)])
+def test_enqueue_bit_exact(GF, dtype, K, d, N, index):
+    gen = torch.Generator().manual_seed(K + N + index)
+    mem = torch.randn(K, d, generator=gen).to(dtype)
+    keys = torch.randn(N, d, generator=gen)
+    ref = mem.clone()
+    new_ref = oracle.enqueue(ref, keys, index)
+    dev = cu(mem)
+    new_idx = GF.enqueue_(dev, cu(keys), index)
+    assert new_idx == new_ref                                        # pointer: exact
+    assert torch.equal(dev.cpu(), ref)                               # slot -> row mapping and contents: exact
+
+
+def test_enqueue_golden_wrap(GF, golden):
+    g = golden("infonce_wrap")
+    dev = cu(T_(g["memory_before"]).clone())
+    idx = int(g["start_index"])
+    for st in range(int(g["steps"])):
+        idx = GF.enqueue_(dev, cu(T_(g[f"all_k{st}"])), idx)
+        assert idx == int(g[f"index_after{st}"])
+    assert torch.equal(dev.cpu(), T_(g["memory_after"]))
+
+
+@pytest.mark.parametrize("W", [2, 4, 8])
+def test_enqueue_sharded_ownership(GF, W):
+    gen = torch.Generator().manual_seed(W)
+    K, d, N, index = 1024, 128, 200, 1024 - 70
+    full = torch.randn(K, d, generator=gen).to(torch.bfloat16)
+    keys = torch.randn(N, d, generator=gen)
+    ref = full.clone()
+    oracle.enqueue(ref, keys, index)
+    Ks = K // W
+    shards = [cu(full[r * Ks:(r + 1) * Ks].clone()) for r in range(W)]
+    for r in range(W):
+        assert GF.enqueue_(shards[r], cu(keys), index, K_global=K, k_begin=r * Ks) == (index + N) % K
+    assert torch.equal(torch.cat([s.cpu() for s in shards]), ref)
+
+
+# ============================================================================================ K1/K2 InfoNCE, fp32 parity mode
+def check_infonce(GF, q, k, mem, T, algo, loss_rtol, grad_rtol, ref_q=None, ref_mem=None, check_logits=False):
+    """Run the fused head on the GPU and compare with the fp64 oracle on (ref_q, ref_mem) (default: same inputs)."""
+    rq = (q if ref_q is None else ref_q).double()
+    rm = (mem.float() if ref_mem is None else ref_mem).double()
+    o = oracle.infonce_step(rq, k.double(), rm.clone(), 0, T)
+    r = GF.infonce_forward(cu(q), cu(k), cu(mem), T, algo=algo, want_grad=True, materialize=check_logits)
+    torch.cuda.synchronize()
+    loss = float(r["loss"])
+    assert abs(loss - float(o["loss"])) <= loss_rtol * abs(float(o["loss"])), (loss, float(o["loss"]))
+    assert rel_max(r["lse"], o["lse"]) <= loss_rtol
+    assert rel_max(r["loss_rows"], o["loss_rows"]) <= loss_rtol * 10
+    assert rel_max(r["dq_unit"], o["dq"]) <= grad_rtol, rel_max(r["dq_unit"], o["dq"])
+    if check_logits:
+        lg = oracle.logits_full(rq, k.double(), rm, T)
+        assert rel_max(r["logits"], lg) <= 1e-5
+    return r, o
+
+
+def test_infonce_fp32_golden_small(GF, golden):
+    g = golden("infonce_small")
+    T = float(g["T"])
+    mem = T_(g["memory_before"])
+    q, k = T_(g["q0"]), T_(g["k0"])
+    r, _ = check_infonce(GF, q, k, mem, T, "ffma", LOSS_RTOL_FP32, 1e-4, check_logits=True)
+    assert abs(float(r["loss"]) - float(g["loss0"])) <= LOSS_RTOL_FP32 * float(g["loss0"])     # vs the reference itself
+    np.testing.assert_allclose(r["dq_unit"].cpu().numpy(), g["dq0"], rtol=1e-3, atol=1e-7)
+    np.testing.assert_array_equal(r["rank"].cpu().numpy(), g["rank0"])                           # integer: exact
+    np.testing.assert_allclose(r["logits"][:, :9].cpu().numpy(), g["logits_head0"], rtol=1e-5, atol=1e-5)
+
+
+def test_infonce_fp32_config1(GF, golden):
+    """BASELINE config 1 / SURVEY Appendix C G1 (B=32, K=4096, d=128), inputs regenerated from the seed."""
+    g = golden("infonce_c1")
+    torch.manual_seed(1)
+    mem = F.normalize(torch.randn(4096, 128))
+    q = F.normalize(torch.randn(32, 128))
+    k = F.normalize(torch.randn(32, 128))
+    r, _ = check_infonce(GF, q, k, mem, 0.07, "ffma", LOSS_RTOL_FP32, 1e-4)
+    assert abs(float(r["loss"]) - 8.9238758087) <= LOSS_RTOL_FP32 * 8.9238758087
+    assert float(r["dq_unit"].abs().sum()) == pytest.approx(130.3457336426, rel=1e-4)
+    np.testing.assert_array_equal(r["rank"].cpu().numpy(), g["rank0"])
+    top1 = float((r["rank"] < 1).float().mean() * 100)
+    top5 = float((r["rank"] < 5).float().mean() * 100)
+    assert [top1, top5] == list(g["acc0"])
+
+
+@pytest.mark.parametrize("B,K,d", [(1, 256, 128), (32, 4096, 128), (64, 1000, 128), (256, 4096, 128), (5, 192, 64),
+                                   (130, 777, 32), (16, 512, 512), (9, 320, 1024), (256, 16384, 128)])
+@pytest.mark.parametrize("qdtype", [torch.float32, torch.bfloat16])
+def test_infonce_ffma_sweep(GF, B, K, d, qdtype):
+    gen = torch.Generator().manual_seed(B * 7 + K + d)
+    mem = unit_rows(K, d, gen).to(qdtype)
+    q, k = unit_rows(B, d, gen), unit_rows(B, d, gen)
+    r, o = check_infonce(GF, q, k, mem, 0.07, "ffma", LOSS_RTOL_FP32, 1e-4)
+    # ranks are integers: exact wherever the margin to the nearest negative is above fp32 noise
+    lg = oracle.logits_full(q.double(), k.double(), mem.double(), 0.07)
+    margin = (lg[:, 1:] - lg[:, :1]).abs().min(dim=1).values
+    ok = margin > 1e-4
+    assert ok.float().mean() > 0.9
+    assert torch.equal(r["rank"].cpu().long()[ok], o["rank"][ok])
+
+
+def test_infonce_ffma_unnormalised_inputs(GF):
+    """Online max must hold for logits far outside [-1/T, 1/T]."""
+    gen = torch.Generator().manual_seed(5)
+    mem = torch.randn(2048, 128, generator=gen) * 3
+    q, k = torch.randn(48, 128, generator=gen), torch.randn(48, 128, generator=gen)
+    check_infonce(GF, q, k, mem, 0.5, "ffma", LOSS_RTOL_FP32, 1e-4)
+
+
+# ============================================================================================ K1 tcgen05 (bf16 queue)
+TC_SHAPES = [(128, 128), (1, 128), (64, 256), (128, 384), (200, 1000), (256, 4096), (256, 65536), (64, 65536), (32, 4096),
+             (512, 8192)]
+
+
+@pytest.mark.parametrize("B,K", TC_SHAPES)
+def test_infonce_tcgen05_vs_bf16_input_oracle(GF, B, K):
+    """The kernel's arithmetic: bf16-rounded q and queue, fp32 accumulate.  Against the fp64 oracle fed the SAME
+    rounded inputs the loss must agree to ~1e-5 (only P is re-rounded, which touches the gradient alone)."""
+    gen = torch.Generator().manual_seed(B + K)
+    mem = unit_rows(K, 128, gen).to(torch.bfloat16)
+    q, k = unit_rows(B, 128, gen), unit_rows(B, 128, gen)
+    T = 0.07
+    rq = bf16r(q)
+    o = oracle.infonce_step(rq.double(), k.double(), mem.double().clone(), 0, T)
+    # the positive logit is taken from the unrounded q (fp32), the negatives from the rounded one
+    pos = (q.double() * k.double()).sum(1) / T
+    neg = (rq.double() @ mem.double().t()) / T
+    lse = torch.logsumexp(torch.cat([pos[:, None], neg], 1), 1)
+    loss_ref = float((lse - pos).mean())
+    r = GF.infonce_forward(cu(q), cu(k), cu(mem), T, algo="tcgen05", want_grad=True)
+    torch.cuda.synchronize()
+    assert abs(float(r["loss"]) - loss_ref) <= 2e-5 * abs(loss_ref), (float(r["loss"]), loss_ref)
+    assert rel_max(r["lse"], lse) <= 2e-5
+    assert rel_max(r["pos"], pos) <= 1e-5
+    p0 = torch.exp(pos - lse)
+    dq_ref = ((p0 - 1)[:, None] * k.double() + torch.exp(neg - lse[:, None]) @ mem.double()) / (T * B)
+    assert rel_max(r["dq_unit"], dq_ref) <= 5e-3, rel_max(r["dq_unit"], dq_ref)
+    rank_ref = (neg > pos[:, None]).sum(1)
+    margin = (neg - pos[:, None]).abs().min(dim=1).values
+    ok = margin > 1e-3
+    assert torch.equal(r["rank"].cpu().long()[ok], rank_ref[ok])
+    del o
+
+
+@pytest.mark.parametrize("B,K", [(32, 4096), (256, 65536)])
+def test_infonce_bf16_mode_within_baseline_tolerance(GF, B, K):
+    """bf16 mode against the fp32 reference arithmetic on UNrounded inputs: loss 2e-3, gradient 1e-2 (BASELINE.json)."""
+    gen = torch.Generator().manual_seed(K - B)
+    mem32 = unit_rows(K, 128, gen)
+    q, k = unit_rows(B, 128, gen), unit_rows(B, 128, gen)
+    check_infonce(GF, q, k, mem32.to(torch.bfloat16), 0.07, "tcgen05", LOSS_RTOL_BF16, GRAD_RTOL, ref_mem=mem32)
+
+
+def test_infonce_tcgen05_materialised_logits(GF):
+    gen = torch.Generator().manual_seed(77)
+    B, K = 70, 700
+    mem = unit_rows(K, 128, gen).to(torch.bfloat16)
+    q, k = unit_rows(B, 128, gen), unit_rows(B, 128, gen)
+    r = GF.infonce_forward(cu(q), cu(k), cu(mem), 0.07, algo="tcgen05", want_grad=False, materialize=True)
+    neg = (bf16r(q).double() @ mem.double().t()) / 0.07
+    assert rel_max(r["logits"][:, 1:], neg) <= 1e-5
+    assert rel_max(r["logits"][:, 0], (q.double() * k.double()).sum(1) / 0.07) <= 1e-5
+
+
+def test_infonce_tcgen05_unnormalised_inputs_trigger_rescale(GF):
+    """Rows whose max grows by more than 2^8 between tiles exercise the lazy O-rescale path."""
+    gen = torch.Generator().manual_seed(9)
+    B, K = 128, 2048
+    mem = torch.randn(K, 128, generator=gen)
+    mem[1500:] *= 6.0                                   # later tiles carry much larger logits
+    mem = mem.to(torch.bfloat16)
+    q, k = torch.randn(B, 128, generator=gen), torch.randn(B, 128, generator=gen)
+    T = 1.0
+    rq = bf16r(q)
+    pos = (q.double() * k.double()).sum(1) / T
+    neg = (rq.double() @ mem.double().t()) / T
+    lse = torch.logsumexp(torch.cat([pos[:, None], neg], 1), 1)
+    dq_ref = ((torch.exp(pos - lse) - 1)[:, None] * k.double() + torch.exp(neg - lse[:, None]) @ mem.double()) / (T * B)
+    r = GF.infonce_forward(cu(q), cu(k), cu(mem), T, algo="tcgen05", want_grad=True)
+    assert rel_max(r["lse"], lse) <= 2e-5
+    assert rel_max(r["dq_unit"], dq_ref) <= 5e-3
+
+
+@pytest.mark.parametrize("algo,qdtype", [("ffma", torch.float32), ("tcgen05", torch.bfloat16)])
+def test_infonce_two_pass_backward_equals_single_pass(GF, algo, qdtype):
+    gen = torch.Generator().manual_seed(31)
+    B, K = 96, 3000
+    mem = cu(unit_rows(K, 128, gen).to(qdtype))
+    q, k = cu(unit_rows(B, 128, gen)), cu(unit_rows(B, 128, gen))
+    r = GF.infonce_forward(q, k, mem, 0.07, algo=algo, want_grad=True)
+    dq = GF.infonce_backward_recompute(q, k, mem, 0.07, r["lse"], 1.0 / B, algo=algo)
+    assert rel_max(dq, r["dq_unit"]) <= (1e-5 if algo == "ffma" else 5e-3)
+
+
+@pytest.mark.parametrize("algo,qdtype", [("ffma", torch.float32), ("tcgen05", torch.bfloat16)])
+def test_infonce_deterministic(GF, algo, qdtype):
+    gen = torch.Generator().manual_seed(2)
+    mem = cu(unit_rows(8192, 128, gen).to(qdtype))
+    q, k = cu(unit_rows(256, 128, gen)), cu(unit_rows(256, 128, gen))
+    a = GF.infonce_forward(q, k, mem, 0.07, algo=algo)
+    b = GF.infonce_forward(q, k, mem, 0.07, algo=algo)
+    for key in ("loss", "lse", "dq_unit", "rank"):
+        assert torch.equal(a[key], b[key]), key
+
+
+# ============================================================================================ sharded path on one GPU
+@pytest.mark.parametrize("W,algo,qdtype", [(2, "ffma", torch.float32), (8, "ffma", torch.float32),
+                                           (4, "tcgen05", torch.bfloat16), (8, "tcgen05", torch.bfloat16)])
+def test_shard_abi_merge_equals_unsharded(GF, W, algo, qdtype):
+    """Size-independent property: K-shard partials + combine + finish == the unsharded fused head."""
+    from gca_b200.dist import ShardCompute
+    gen = torch.Generator().manual_seed(W)
+    B, K = 64, 8192
+    mem = cu(unit_rows(K, 128, gen).to(qdtype))
+    q, k = cu(unit_rows(B, 128, gen)), cu(unit_rows(B, 128, gen))
+    full = GF.infonce_forward(q, k, mem, 0.07, algo=algo)
+    comp = ShardCompute()
+    Ks = K // W
+    parts = [comp.shard_fwd(q, k, mem[r * Ks:(r + 1) * Ks].contiguous(), 0.07, algo, True) for r in range(W)]
+    all_stats = torch.stack([p[1] for p in parts])                    # [W, 3, B]  (what the all-gather delivers)
+    acc_sum = torch.zeros(B, 128, device="cuda")
+    for r in range(W):
+        lse, loss_rows, rank_gt = comp.shard_combine(all_stats, r, parts[r][0], parts[r][2])
+        acc_sum += parts[r][2]                                        # what the reduce-scatter delivers
+    dq_unit, loss = comp.shard_finish(acc_sum, k, parts[0][0], lse, loss_rows, 0.07)
+    tol = 1e-5 if algo == "ffma" else 1e-4
+    assert rel_max(lse, full["lse"]) <= 1e-6
+    assert abs(float(loss) - float(full["loss"])) <= 1e-6 * abs(float(full["loss"]))
+    assert torch.equal(rank_gt, full["rank"])
+    assert rel_max(dq_unit, full["dq_unit"]) <= tol
+
+
+# ============================================================================================ drop-in modules
+@pytest.mark.parametrize("queue_dtype", ["fp32", "bf16"])
+def test_rgbmoco_module_steps_like_reference(lib, golden, queue_dtype):
+    """Three consecutive trainer-style steps (train_video_contrast_dis.py:411-428) against the reference outputs."""
+    import gca_b200
+    g = golden("infonce_small")
+    moco = gca_b200.RGBMoCo(128, K=256, T=float(g["T"]), queue_dtype=queue_dtype).cuda()
+    moco.load_state_dict({"memory": T_(g["memory_before"])})
+    crit = gca_b200.NCESoftmaxLoss()
+    ltol, gtol = (LOSS_RTOL_FP32, 1e-3) if queue_dtype == "fp32" else (LOSS_RTOL_BF16, GRAD_RTOL)
+    for st in range(int(g["steps"])):
+        q = cu(T_(g[f"q{st}"])).requires_grad_(True)
+        k = cu(T_(g[f"k{st}"]))
+        out, labels = moco(q, k)
+        loss = crit(out)
+        loss.backward()
+        assert labels.dtype == torch.long and labels.shape == (8,) and int(labels.abs().sum()) == 0
+        assert out.shape[0] == 8 and out.shape[1] == 257
+        assert abs(float(loss) - float(g[f"loss{st}"])) <= ltol * float(g[f"loss{st}"])
+        assert rel_max(q.grad, T_(g[f"dq{st}"])) <= gtol
+        assert moco.index == int(g[f"index_after{st}"])                # pointer: exact
+        _, pred = out.detach().topk(5, 1, True, True)                  # what `accuracy` does
+        correct = pred.t().eq(labels.view(1, -1).expand_as(pred.t()))
+        acc = [float(correct[:kk].reshape(-1).float().sum() * (100.0 / 8)) for kk in (1, 5)]
+        if queue_dtype == "fp32":
+            assert acc == list(g[f"acc{st}"])
+    mem_after = moco.state_dict()["memory"].cpu()
+    if queue_dtype == "fp32":
+        assert torch.equal(mem_after, T_(g["memory_after"]))           # slot contents: exact
+    else:
+        assert torch.equal(mem_after, bf16r(T_(g["memory_after"])))    # exact RNE rounding of the same rows
+
+
+def test_rgbmoco_all_k_and_jig(lib, golden):
+    import gca_b200
+    g = golden("infonce_wrap")
+    moco = gca_b200.RGBMoCo(128, K=256, T=float(g["T"])).cuda()
+    moco.load_state_dict({"memory": T_(g["memory_before"])})
+    moco.index = int(g["start_index"])
+    q = cu(T_(g["q0"])).requires_grad_(True)
+    out, out_jig, labels = moco(q, cu(T_(g["k0"])), q_jig=q.detach().flip(0), all_k=cu(T_(g["all_k0"])))
+    assert abs(float(out.loss) - float(g["loss0"])) <= LOSS_RTOL_FP32 * float(g["loss0"])
+    assert moco.index == int(g["index_after0"]) and out_jig.shape == out.shape
+
+
+def test_materialized_logits_mode(lib, golden):
+    import gca_b200
+    g = golden("infonce_small")
+    moco = gca_b200.RGBMoCo(128, K=256, T=float(g["T"]), materialize=True).cuda()
+    moco.load_state_dict({"memory": T_(g["memory_before"])})
+    q = cu(T_(g["q0"])).requires_grad_(True)
+    out, labels = moco(q, cu(T_(g["k0"])))
+    assert isinstance(out, torch.Tensor) and out.shape == (8, 257)
+    loss = gca_b200.NCESoftmaxLoss()(out)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss0"])) <= LOSS_RTOL_FP32 * float(g["loss0"])
+    assert rel_max(q.grad, T_(g["dq0"])) <= 1e-4
+
+
+# ============================================================================================ K4/K5 graph head
+@pytest.mark.parametrize("name", ["graph_c1", "graph_fmap", "graph_odd", "graph_t2"])
+def test_graph_core_golden(GF, golden, name):
+    g = golden(name)
+    alpha, max_hop, temp, sub = float(g["alpha"]), int(g["max_hop"]), float(g["temperature"]), bool(g["sub_sample"])
+    x, wq, wk, wg, u, dy = (T_(g[n]) for n in ("x", "wq", "wk", "wg", "u", "dy"))
+    B, C, T = x.shape[:3]
+    gq = og._project(x, wq, sub, True)
+    gk = og._project(x, wk, sub, True)
+    sup = F.conv3d(x, wg)
+    gq_d, gk_d, sup_d = (cu(t).requires_grad_(True) for t in (gq, gk, sup))
+    y, sim, adj, s = GF.graph_core(gq_d, gk_d, sup_d, cu(u), alpha, max_hop, temp)
+    assert rel_max(sim, T_(g["sim"])) <= 1e-5
+    assert rel_max(adj, T_(g["adj"])) <= 1e-5
+    assert rel_max(s, T_(g["s"])) <= 1e-5
+    # hop mask is integer work: adj must be exactly zero outside max_hop and non-zero inside
+    hop = T_(g["hop"])
+    assert torch.equal((adj[0].cpu() == 0), (hop < 0))
+    assert rel_max(y.reshape(x.shape), T_(g["y"])) <= 1e-5
+    y.backward(cu(dy).reshape(y.shape))
+    assert rel_max(gq_d.grad.reshape(g["d_gq"].shape), T_(g["d_gq"])) <= 1e-3
+    assert rel_max(gk_d.grad.reshape(g["d_gk"].shape), T_(g["d_gk"])) <= 1e-3
+    assert rel_max(sup_d.grad.reshape(g["d_support"].shape), T_(g["d_support"])) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["graph_c1", "graph_fmap", "graph_odd"])
+def test_graph_module_end_to_end(lib, golden, name, monkeypatch):
+    """The drop-in module with the reference's weights and the reference's uniforms reproduces y, dx and dW."""
+    import gca_b200
+    g = golden(name)
+    x = T_(g["x"])
+    m = gca_b200.TemporalGraphAug(x.shape[1], sub_sample=bool(g["sub_sample"]), max_hop=int(g["max_hop"]),
+                                  alpah=float(g["alpha"]), temperature=float(g["temperature"]))
+    sd = {"gcns.0.conv.weight": T_(g["wg"])}
+    pre = "g_q.0.weight" if bool(g["sub_sample"]) else "g_q.weight"
+    sd[pre] = T_(g["wq"])
+    sd[pre.replace("g_q", "g_k")] = T_(g["wk"])
+    m.load_state_dict(sd)
+    m = m.cuda()
+    u = cu(T_(g["u"]))
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: u.clone())       # the one RNG draw of the forward
+    xd = cu(x).requires_grad_(True)
+    y = m(xd)
+    assert y.shape == x.shape and rel_max(y, T_(g["y"])) <= 1e-5
+    y.backward(cu(T_(g["dy"])))
+    assert rel_max(xd.grad, T_(g["dx"])) <= 1e-3
+    conv_q = m.g_q[0] if bool(g["sub_sample"]) else m.g_q
+    assert rel_max(conv_q.weight.grad, T_(g["dwq"])) <= 1e-3
+    assert rel_max(m.gcns[0].conv.weight.grad, T_(g["dwg"])) <= 1e-3
+
+
+def test_graph_module_draws_like_reference_rsample(lib):
+    """Seeded forward == functional call with u = torch.rand(B,T,T) drawn right after the same seed."""
+    import gca_b200
+    from gca_b200 import functional as GFm
+    torch.manual_seed(0)
+    m = gca_b200.TemporalGraphAug(32, sub_sample=False).cuda()
+    x = torch.randn(4, 32, 8, 1, 1, device="cuda")
+    torch.manual_seed(123)
+    y1, info = m(x, return_graph=True)
+    torch.manual_seed(123)
+    u = torch.rand(4, 8, 8, device="cuda")
+    assert torch.equal(info["u"], u)
+    y2, _, _, _ = GFm.graph_core(m.g_q(x), m.g_k(x), m.gcns[0].conv(x), u, 0.5, 3, 1.0)
+    assert torch.equal(y1, y2.view_as(y1))
+
+
+@pytest.mark.parametrize("shape,sub", [((3, 32, 8, 28, 28), True), ((2, 24, 16, 14, 14), False), ((2, 8, 32, 6, 6), False),
+                                       ((5, 64, 8, 7, 7), False), ((130, 256, 8, 1, 1), False)])
+def test_graph_core_random_shapes(GF, shape, sub):
+    """Large feature maps (split adjacency + grid aggregation path), odd spatial sizes, T up to 32."""
+    B, C, T, H, W = shape
+    gen = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=gen)
+    wq = torch.randn(C // 2, C, 1, 1, 1, generator=gen) / C ** 0.5
+    wk = torch.randn(C // 2, C, 1, 1, 1, generator=gen) / C ** 0.5
+    wg = torch.randn(C, C, 1, 1, 1, generator=gen) / C ** 0.5
+    u = torch.rand(B, T, T, generator=gen)
+    dy = torch.randn(*shape, generator=gen)
+    gq = og._project(x, wq, sub, True).reshape(B, C // 2, T, -1)
+    gk = og._project(x, wk, sub, True).reshape(B, C // 2, T, -1)
+    sup = F.conv3d(x, wg).reshape(B, C, T, -1)
+    y_ref, sim, adj, s = og.graph_core(gq, gk, sup, u)
+    d_ref = og.graph_core_backward(gq, gk, sup, sim, adj, s, dy.reshape(B, C, T, -1))
+    gq_d, gk_d, sup_d = (cu(t).requires_grad_(True) for t in (gq, gk, sup))
+    y, sim_d, adj_d, s_d = GF.graph_core(gq_d, gk_d, sup_d, cu(u))
+    assert rel_max(sim_d, sim) <= 2e-5 and rel_max(s_d, s) <= 2e-5
+    assert rel_max(y, y_ref) <= 2e-5
+    y.backward(cu(dy).reshape(y.shape))
+    for got, ref in zip((gq_d.grad, gk_d.grad, sup_d.grad), d_ref):
+        assert rel_max(got, ref) <= 2e-3
+
+
+# ============================================================================================ K6 SimSiam D
+def test_negcos_golden(lib, golden):
+    import gca_b200
+    g = golden("negcos")
+    p = cu(T_(g["p"])).requires_grad_(True)
+    loss = gca_b200.D()(p, cu(T_(g["z"])))
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6
+    assert rel_max(p.grad, T_(g["dp"])) <= 1e-5
+
+
+@pytest.mark.parametrize("B,d", [(128, 1024), (7, 2048), (33, 50), (1, 8)])
+def test_negcos_random(GF, B, d):
+    gen = torch.Generator().manual_seed(B + d)
+    p, z = torch.randn(B, d, generator=gen), torch.randn(B, d, generator=gen)
+    pd = cu(p).requires_grad_(True)
+    loss = GF.neg_cosine(pd, cu(z))
+    (loss * 3.0).backward()
+    assert abs(float(loss) - float(oracle.neg_cosine(p.double(), z.double()))) <= 1e-6
+    assert rel_max(pd.grad, 3.0 * oracle.neg_cosine_grad(p.double(), z.double())) <= 1e-5
+
+
+# ============================================================================================ K7 retrieval
+def test_retrieval_small_golden(GF, golden):
+    g = golden("retrieval")
+    idx, val = GF.cosine_topk(cu(T_(g["small_queries"])), cu(T_(g["small_gallery"])), 50)
+    np.testing.assert_array_equal(idx[:, :10].cpu().numpy(), g["small_top10"])
+    hits = oracle.recall_hits(idx.cpu().numpy(), g["small_query_labels"], g["small_gallery_labels"])
+    assert [hits[k] for k in oracle.retrieval.KS] == list(g["small_hits"])            # integer recall counts: exact
+    assert bool((val[:, :-1] >= val[:, 1:]).all())                                     # sortedness
+
+
+def test_retrieval_config5_full_size(GF, golden):
+    """BASELINE config 5 / SURVEY G3: 3,783 x 13,320 x 512, recall@{1,5,10,20,50} hit counts equal the reference's."""
+    g = golden("retrieval")
+    rng = np.random.default_rng(0)
+    gal = rng.standard_normal((13320, 512)).astype(np.float32)
+    qry = rng.standard_normal((3783, 512)).astype(np.float32)
+    gl = rng.integers(0, 101, 13320)
+    ql = rng.integers(0, 101, 3783)
+    idx, val = GF.cosine_topk(cu(T_(qry)), cu(T_(gal)), 50)
+    hits = oracle.recall_hits(idx.cpu().numpy(), ql, gl)
+    assert [hits[k] for k in oracle.retrieval.KS] == list(g["c5_hits"]) == [28, 151, 349, 666, 1478]
+    assert bool((val[:, :-1] >= val[:, 1:]).all())
+    assert len(set(idx[0].cpu().tolist())) == 50
+
+
+# ============================================================================================ full-size properties
+def test_headline_shape_full_size(GF):
+    """BASELINE metric shape (B=256, K=65536, d=128): both modes against the fp64 oracle, pointer wrap over a lap."""
+    import gca_b200
+    gen = torch.Generator().manual_seed(1)
+    mem32 = unit_rows(65536, 128, gen)
+    q, k = unit_rows(256, 128, gen), unit_rows(256, 128, gen)
+    check_infonce(GF, q, k, mem32, 0.07, "ffma", LOSS_RTOL_FP32, 1e-3)
+    check_infonce(GF, q, k, mem32.to(torch.bfloat16), 0.07, "tcgen05", LOSS_RTOL_BF16, GRAD_RTOL, ref_mem=mem32)
+    moco = gca_b200.RGBMoCo(128, K=65536, queue_dtype="bf16").cuda()
+    moco.index = 65536 - 256 * 2
+    ref_mem = moco.memory.cpu().clone()
+    idx = moco.index
+    for _ in range(4):                                                    # crosses the end of the ring
+        kk = unit_rows(256, 128, gen)
+        moco(cu(unit_rows(256, 128, gen)), cu(kk))
+        idx = oracle.enqueue(ref_mem, kk, idx)
+    assert moco.index == idx == 512 and torch.equal(moco.memory.cpu(), ref_mem)

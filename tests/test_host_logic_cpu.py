@@ -1,0 +1,116 @@
+"""CPU: host-side mirror of the reference interfaces (no kernels run here)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import gca_b200
+from gca_b200.memory.moco_queue import FusedLogits
+
+
+def cfg(mem_type="moco", crit="crossentropy", K=256, **extra):
+    c = types.SimpleNamespace(
+        CONTRAST=types.SimpleNamespace(MEM_TYPE=mem_type, NCE_K=K, NCE_T=0.07, NCE_M=0.5, **extra),
+        CROSS=types.SimpleNamespace(MODALITY="visual", FEAT_DIM=128, CRITERION=crit))
+    return c
+
+
+def test_factories_follow_reference_contract():
+    m = gca_b200.create_contrast(cfg(), n_data=1000)
+    assert isinstance(m, gca_b200.RGBMoCo) and m.K == 256 and m.T == 0.07 and m.index == 0
+    assert list(m.state_dict().keys()) == ["memory"] and m.memory.shape == (256, 128) and m.memory.dtype == torch.float32
+    assert gca_b200.create_contrast(cfg("simsiam"), 1) is None                       # lib/memory/build.py:13-14
+    assert isinstance(gca_b200.create_criterion(cfg(), 1), gca_b200.NCESoftmaxLoss)
+    assert isinstance(gca_b200.create_criterion(cfg(crit="simsiam_d"), 1), gca_b200.D)
+    with pytest.raises(NotImplementedError):
+        gca_b200.create_contrast(cfg("nope"), 1)
+    with pytest.raises(NotImplementedError):
+        gca_b200.create_criterion(cfg(crit="nope"), 1)
+    b = gca_b200.create_contrast(cfg(QUEUE_DTYPE="bf16"), 1)
+    assert b.memory.dtype == torch.bfloat16
+
+
+def test_queue_init_consumes_rng_like_reference():
+    torch.manual_seed(1)
+    m = gca_b200.RGBMoCo(128, K=4096)
+    torch.manual_seed(1)
+    ref = torch.nn.functional.normalize(torch.randn(4096, 128))                       # mem_moco.py:57-58
+    assert torch.equal(m.memory, ref)
+    assert torch.allclose(m.memory.norm(dim=1), torch.ones(4096), atol=1e-6)
+
+
+def test_bf16_queue_checkpoints_as_fp32():
+    torch.manual_seed(0)
+    m = gca_b200.RGBMoCo(32, K=64, queue_dtype="bf16")
+    sd = m.state_dict()
+    assert sd["memory"].dtype == torch.float32 and torch.equal(sd["memory"].to(torch.bfloat16), m.memory)
+    m2 = gca_b200.RGBMoCo(32, K=64, queue_dtype="bf16")
+    m2.load_state_dict(sd)
+    assert m2.memory.dtype == torch.bfloat16 and torch.equal(m2.memory, m.memory)
+    ref_style = {"memory": torch.nn.functional.normalize(torch.randn(64, 32))}        # an upstream fp32 checkpoint
+    m2.load_state_dict(ref_style)
+    assert torch.equal(m2.memory, ref_style["memory"].to(torch.bfloat16))
+
+
+def test_pointer_bookkeeping():
+    m = gca_b200.RGBMoCo(32, K=64)
+    m.index = 60
+    m._update_pointer(10)
+    assert m.index == 6                                                               # mem_moco.py:14-15
+
+
+def test_fused_logits_topk_drives_reference_accuracy():
+    """`accuracy` (metric.py:44-67, reshape-fixed) on the handle must equal accuracy on real logits."""
+    import oracle
+    torch.manual_seed(3)
+    lg = torch.randn(64, 257)
+    lg[:8, 0] += 5.0
+    rank = oracle.positive_rank(lg)
+    h = FusedLogits(torch.tensor(0.), torch.zeros(64), torch.zeros(64), lg[:, 0], rank.int(), 64, 256)
+    assert h.shape[0] == 64 and h.size(1) == 257 and h.detach().shape == h.shape
+    _, pred = h.topk(5, 1, True, True)
+    correct = pred.t().eq(torch.zeros(1, 64, dtype=pred.dtype))
+    mine = [float(correct[:k].reshape(-1).float().sum() * (100.0 / 64)) for k in (1, 5)]
+    ref = [float(a) for a in oracle.topk_accuracy(lg, (1, 5))]
+    assert mine == ref and ref[0] > 0
+    crit = gca_b200.NCESoftmaxLoss()
+    assert crit(h) is h.loss
+    assert float(crit(lg)) == pytest.approx(float(oracle.infonce_loss(lg)), rel=1e-6)
+
+
+def test_graph_module_matches_reference_layout_and_init(golden):
+    g = golden("graph_c1")
+    torch.manual_seed(3)
+    m = gca_b200.TemporalGraphAug(128, sub_sample=False)
+    # same parameter names, shapes and -- for the same seed -- the same values as the (shimmed) reference ctor
+    sd = m.state_dict()
+    assert sorted(sd) == ["g_k.weight", "g_q.weight", "gcns.0.conv.weight"]
+    np.testing.assert_array_equal(sd["g_q.weight"].numpy(), g["wq"])
+    np.testing.assert_array_equal(sd["g_k.weight"].numpy(), g["wk"])
+    np.testing.assert_array_equal(sd["gcns.0.conv.weight"].numpy(), g["wg"])
+    m2 = gca_b200.TemporalGraphAug(16)                         # sub_sample=True default -> Sequential(conv, pool)
+    assert sorted(m2.state_dict()) == ["g_k.0.weight", "g_q.0.weight", "gcns.0.conv.weight"]
+    assert m2.inter_channels == 8 and m2.gcns[0].conv.out_channels == 16 and m2.alpha == 0.5 and m2.max_hop == 3
+    with pytest.raises(NotImplementedError):
+        gca_b200.TemporalGraphAug(16, mask_frame=True)
+    with pytest.raises(NotImplementedError):
+        gca_b200.TemporalGraphAug(16, num_gcn_layers=2)
+
+
+def test_build_aug_block_wraps_named_modules():
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.base = nn.Sequential(nn.Conv3d(3, 8, 1), nn.ReLU(), nn.Conv3d(8, 16, 1),
+                                      nn.Sequential(nn.ReLU(), nn.Conv3d(16, 4, 1)))
+            self.layer2 = nn.Conv3d(4, 4, 1)
+
+    net = gca_b200.build_aug_block(Net(), ["base.2", "base.3", "layer2"], n_segments=16)
+    for mod, cin in ((net.base[2], 8), (net.base[3], 16), (net.layer2, 4)):
+        assert isinstance(mod, nn.Sequential) and isinstance(mod[0], gca_b200.TemporalGraphAug)
+        assert mod[0].in_channels == cin
+    assert isinstance(net.base[0], nn.Conv3d)
+    agg = gca_b200.get_agg("avg", "3D")
+    assert agg(torch.ones(2, 3, 4)).shape == (2, 4)            # upstream always pools dim 1 (build.py:6)

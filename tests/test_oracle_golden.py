@@ -1,0 +1,155 @@
+"""CPU: the oracle restatements against the fixtures generated from the reference (oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from oracle import graph as og
+
+
+def T_(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("name", ["infonce_small", "infonce_wrap", "infonce_d64"])
+def test_infonce_steps_match_reference(golden, name):
+    g = golden(name)
+    mem = T_(g["memory_before"]).clone()
+    idx = int(g["start_index"])
+    T = float(g["T"])
+    for st in range(int(g["steps"])):
+        q, k = T_(g[f"q{st}"]), T_(g[f"k{st}"])
+        all_k = T_(g[f"all_k{st}"]) if f"all_k{st}" in g else None
+        lg = oracle.logits_full(q, k, mem, T)
+        np.testing.assert_allclose(lg[:, :9].numpy(), g[f"logits_head{st}"], rtol=1e-6, atol=1e-6)
+        o = oracle.infonce_step(q, k, mem, idx, T, all_k=all_k)
+        idx = o["index"]
+        assert idx == int(g[f"index_after{st}"])                                   # integer: exact
+        assert abs(float(o["loss"]) - float(g[f"loss{st}"])) <= 1e-5 * abs(float(g[f"loss{st}"]))
+        np.testing.assert_allclose(o["dq"].numpy(), g[f"dq{st}"], rtol=1e-4, atol=1e-8)
+        np.testing.assert_array_equal(o["rank"].numpy(), g[f"rank{st}"])
+        np.testing.assert_allclose(o["lse"].double().numpy(), g[f"lse{st}"], rtol=1e-6)
+        assert float(mem.double().sum()) == pytest.approx(float(g[f"memory_sum_after{st}"]), abs=1e-9)
+    assert torch.equal(mem, T_(g["memory_after"]))                                  # slot contents: exact
+
+
+def test_wrap_around_slots(golden):
+    g = golden("infonce_wrap")
+    assert int(g["start_index"]) == 236 and int(g["index_after0"]) == (236 + 40) % 256
+    mem0, mem1 = g["memory_before"], g["memory_after"]
+    all_k0 = g["all_k0"]
+    # after step 0 rows 236..255 hold all_k0[:20], rows 0..19 hold all_k0[20:] (then step 1 overwrites 20..59)
+    np.testing.assert_array_equal(mem1[236:], all_k0[:20])
+    np.testing.assert_array_equal(mem1[:20], all_k0[20:])
+    np.testing.assert_array_equal(mem1[60:236], mem0[60:236])
+    np.testing.assert_array_equal(oracle.ring_slots(236, 40, 256)[[0, 19, 20, 39]], [236, 255, 0, 19])
+
+
+def test_config1_by_seed(golden):
+    """inputs regenerated from the seed, outputs from the reference."""
+    g = golden("infonce_c1")
+    torch.manual_seed(1)
+    mem = F.normalize(torch.randn(4096, 128))
+    q = F.normalize(torch.randn(32, 128))
+    k = F.normalize(torch.randn(32, 128))
+    assert float(mem.double().sum()) == pytest.approx(float(g["memory_before_sum"]), abs=1e-9), "RNG stream changed"
+    np.testing.assert_array_equal(mem[:4].numpy(), g["memory_before_head"])
+    np.testing.assert_array_equal(q.numpy(), g["q0"])
+    o = oracle.infonce_step(q, k, mem, 0, 0.07)
+    assert float(o["loss"]) == pytest.approx(8.9238758087, rel=1e-6)
+    assert float(o["dq"].abs().sum()) == pytest.approx(130.3457336426, rel=1e-5)
+    np.testing.assert_allclose(o["dq"][0, :3].numpy(), [-0.0333443545, -0.0277747400, -0.0518033244], rtol=1e-5)
+    assert o["index"] == 32 and torch.equal(mem[:32], k)
+    assert float(mem.double().sum()) == pytest.approx(-3.7303031141, abs=1e-6)
+    np.testing.assert_array_equal(g["acc0"], [0.0, 0.0])
+
+
+def test_reference_head_step_port_matches_closed_form(golden):
+    g = golden("infonce_small")
+    mem_a, mem_b = T_(g["memory_before"]).clone(), T_(g["memory_before"]).clone()
+    q = T_(g["q0"]).clone().requires_grad_(True)
+    k = T_(g["k0"])
+    loss, dq, idx, acc = oracle.infonce.reference_head_step(q, k, mem_a, 0, float(g["T"]))
+    o = oracle.infonce_step(q.detach(), k, mem_b, 0, float(g["T"]))
+    assert float(loss) == pytest.approx(float(o["loss"]), rel=1e-6)
+    np.testing.assert_allclose(dq.numpy(), o["dq"].numpy(), rtol=1e-4, atol=1e-8)
+    assert idx == o["index"] and torch.equal(mem_a, mem_b)
+    assert [float(a) for a in acc] == list(g["acc0"])
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_sharded_merge_equals_unsharded(golden, world):
+    g = golden("infonce_small")
+    q, k, mem = T_(g["q0"]), T_(g["k0"]), T_(g["memory_before"])
+    full = oracle.infonce_step(q, k, mem.clone(), 0, float(g["T"]))
+    sh = oracle.sharded_infonce(q, k, mem, float(g["T"]), world)
+    assert float(sh["loss"]) == pytest.approx(float(full["loss"]), rel=2e-6)
+    np.testing.assert_array_equal(sh["rank"].numpy(), full["rank"].numpy())
+    np.testing.assert_allclose(sh["dq"].numpy(), full["dq"].numpy(), rtol=2e-4, atol=1e-8)
+
+
+def test_sharded_enqueue_ownership():
+    torch.manual_seed(0)
+    K, d, W = 64, 8, 4
+    full = torch.randn(K, d)
+    shards = [full[r * 16:(r + 1) * 16].clone() for r in range(W)]
+    keys = torch.randn(24, d)
+    idx_full = oracle.enqueue(full, keys, 54)
+    for r in range(W):
+        assert oracle.ring.enqueue_sharded(shards[r], keys, 54, K, r * 16) == idx_full
+    assert torch.equal(torch.cat(shards), full) and idx_full == (54 + 24) % 64
+
+
+def test_enqueue_rejects_more_rows_than_slots():
+    with pytest.raises(ValueError):
+        oracle.enqueue(torch.zeros(4, 8), torch.zeros(5, 8), 0)
+
+
+@pytest.mark.parametrize("name", ["graph_c1", "graph_fmap", "graph_odd", "graph_t2"])
+def test_graph_forward_backward_match_reference(golden, name):
+    g = golden(name)
+    kw = dict(alpha=float(g["alpha"]), max_hop=int(g["max_hop"]), temperature=float(g["temperature"]),
+              sub_sample=bool(g["sub_sample"]))
+    x, wq, wk, wg, u, dy = (T_(g[n]) for n in ("x", "wq", "wk", "wg", "u", "dy"))
+    y, sim, adj, s = oracle.graph_forward(x, wq, wk, wg, u, **kw)
+    assert torch.equal(y, T_(g["y"]))                                               # bit-equal to the reference
+    np.testing.assert_array_equal(s.numpy(), g["s"])
+    np.testing.assert_array_equal(oracle.hop_distance(x.shape[2], kw["max_hop"]), g["hop"])
+    _, dx, dwq, dwk, dwg = oracle.graph_forward_backward(x, wq, wk, wg, u, dy, **kw)
+    for a, n in ((dx, "dx"), (dwq, "dwq"), (dwk, "dwk"), (dwg, "dwg")):
+        np.testing.assert_allclose(a.numpy(), g[n], rtol=1e-4, atol=1e-6)
+    # closed-form core backward (what the CUDA kernel implements) vs the reference's autograd
+    B, C, T = x.shape[:3]
+    gq = og._project(x, wq, kw["sub_sample"], True).reshape(B, wq.shape[0], T, -1)
+    gk = og._project(x, wk, kw["sub_sample"], True).reshape(B, wk.shape[0], T, -1)
+    sup = F.conv3d(x, wg).reshape(B, C, T, -1)
+    d_gq, d_gk, d_sup = og.graph_core_backward(gq, gk, sup, sim, adj, s, dy.reshape(B, C, T, -1), kw["alpha"],
+                                               kw["max_hop"], kw["temperature"])
+    np.testing.assert_allclose(d_gq.numpy(), g["d_gq"], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(d_gk.numpy(), g["d_gk"], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(d_sup.numpy(), g["d_support"], rtol=2e-4, atol=1e-6)
+
+
+def test_graph_config1_known_answers(golden):
+    """SURVEY Appendix C G2."""
+    g = golden("graph_c1")
+    assert float(g["y"].astype(np.float64).sum()) == pytest.approx(54.6891079033, abs=1e-4)
+    np.testing.assert_allclose(g["y"][0, 0, :, 0, 0], [-0.4872, 0.2106, -0.0156, -0.5280], atol=5e-5)
+    np.testing.assert_allclose(g["theta"], [1.0, 0.8240271, 0.6329011, 0.5496640], rtol=1e-6)
+
+
+def test_negcos_matches_reference(golden):
+    g = golden("negcos")
+    p, z = T_(g["p"]), T_(g["z"])
+    assert float(oracle.neg_cosine(p, z)) == pytest.approx(float(g["loss"]), abs=1e-7)
+    np.testing.assert_allclose(oracle.neg_cosine_grad(p, z).numpy(), g["dp"], rtol=1e-4, atol=1e-8)
+
+
+def test_retrieval_small_matches_reference(golden):
+    g = golden("retrieval")
+    idx, _ = oracle.cosine_topk(g["small_queries"], g["small_gallery"], 50)
+    np.testing.assert_array_equal(idx[:, :10], g["small_top10"])
+    hits = oracle.recall_hits(idx, g["small_query_labels"], g["small_gallery_labels"])
+    assert [hits[k] for k in oracle.retrieval.KS] == list(g["small_hits"])
+    assert list(g["c5_hits"]) == [28, 151, 349, 666, 1478]

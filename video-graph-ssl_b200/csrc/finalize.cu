@@ -1,0 +1,209 @@
+// Fixed-order merge of the per-split online-softmax partials written by the InfoNCE stream kernels, plus the
+// K-shard (multi-GPU) combine / finish steps.  Everything here is deterministic: no floating-point atomics,
+// every sum has a fixed association order.  Math: SURVEY.md Appendix A.1-A.4.
+#include "gca_common.cuh"
+#include "infonce_params.cuh"
+
+namespace gca {
+
+constexpr int FIN_THREADS = 128;
+constexpr int FIN_MAX_SPLITS = 1024;
+
+// last-block ticket: returns true in exactly one block, after every other block's global writes are visible
+__device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigned int nblocks, int* flag_smem)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(counter, 1u);
+        *flag_smem = (t == nblocks - 1);
+    }
+    __syncthreads();
+    const bool last = (*flag_smem != 0);
+    if (last) __threadfence();
+    return last;
+}
+
+// mean of rows[0..n) in a fixed order, by one block
+__device__ __forceinline__ float block_mean_fixed(const float* rows, int n, float* red)
+{
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += FIN_THREADS) a += __ldcg(rows + i);
+    return block_sum<FIN_THREADS>(a, red) / (float)n;
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(FIN_THREADS)
+infonce_finalize_kernel(const FinalizeParams F)
+{
+    __shared__ float w_s[FIN_MAX_SPLITS];
+    __shared__ float red[FIN_THREADS / 32];
+    __shared__ int   flag;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int ns = F.nsplit;
+
+    float lse = 0.f, pos = 0.f;
+    if (kMode == FIN_BWD) {
+        lse = F.lse_in[b];
+        pos = F.pos ? F.pos[b] : 0.f;
+    } else {
+        // M = max over splits (and the positive), S = sum of rescaled split sums: fixed order
+        float m = -INFINITY;
+        for (int s = tid; s < ns; s += FIN_THREADS) m = fmaxf(m, F.part_max[(size_t)s * F.Bpad + b]);
+        m = warp_max(m);
+        if ((tid & 31) == 0) red[tid >> 5] = m;
+        __syncthreads();
+        m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+        __syncthreads();
+        if (kMode == FIN_FULL) { pos = F.pos[b]; m = fmaxf(m, pos); }
+        float part = 0.f;
+        int cnt = 0;
+        for (int s = tid; s < ns; s += FIN_THREADS) {
+            const size_t o = (size_t)s * F.Bpad + b;
+            const float pm = F.part_max[o];
+            const float e = (pm == -INFINITY) ? 0.f : __expf(pm - m);
+            w_s[s] = e;                                        // exp(part_max - M); turned into exp(. - lse) below
+            part += F.part_sum[o] * e;
+            cnt += F.part_cnt[o];
+        }
+        float S = block_sum<FIN_THREADS>(part, red);
+        cnt = warp_sum_i(cnt);
+        __shared__ int cnt_s[FIN_THREADS / 32];
+        if ((tid & 31) == 0) cnt_s[tid >> 5] = cnt;
+        __syncthreads();
+        cnt = cnt_s[0] + cnt_s[1] + cnt_s[2] + cnt_s[3];
+        if (kMode == FIN_FULL) {
+            S += __expf(pos - m);
+            lse = m + logf(S);
+            if (tid == 0) {
+                F.lse[b] = lse;
+                F.loss_rows[b] = lse - pos;
+                F.rank_gt[b] = cnt;
+            }
+            const float corr = __expf(m - lse);                // = 1 / S
+            for (int s = tid; s < ns; s += FIN_THREADS) w_s[s] *= corr;
+        } else {                                               // FIN_SHARD: keep the merged partial relative to m
+            if (tid == 0) { F.out_max[b] = m; F.out_sum[b] = S; F.out_cnt[b] = cnt; }
+        }
+        __syncthreads();
+    }
+
+    // gradient accumulator: fixed-order sum over splits, one feature column per thread
+    float* out = (kMode == FIN_SHARD) ? F.out_acc : F.dq;
+    if (out != nullptr && F.part_acc != nullptr) {
+        const float p0m1 = (kMode == FIN_SHARD) ? 0.f : (__expf(pos - lse) - 1.f);
+        const float scale = (kMode == FIN_FULL) ? F.inv_T / (float)F.B
+                          : (kMode == FIN_BWD)  ? F.inv_T * F.grad_scale : 1.f;
+        for (int c = tid; c < F.d; c += FIN_THREADS) {
+            float a = 0.f;
+            const float* src = F.part_acc + (size_t)b * F.d + c;
+            const size_t stride = (size_t)F.Bpad * F.d;
+            if (kMode == FIN_BWD) { for (int s = 0; s < ns; ++s) a += __ldcg(src + s * stride); }
+            else                  { for (int s = 0; s < ns; ++s) a = fmaf(w_s[s], __ldcg(src + s * stride), a); }
+            if (kMode != FIN_SHARD) a = scale * fmaf(p0m1, F.k[(size_t)b * F.d + c], a);
+            out[(size_t)b * F.d + c] = a;
+        }
+    }
+
+    if (kMode == FIN_FULL && F.loss_mean != nullptr) {
+        if (last_block_ticket(F.counter, gridDim.x, &flag)) {
+            const float mean = block_mean_fixed(F.loss_rows, F.B, red);
+            if (tid == 0) { *F.loss_mean = mean; *F.counter = 0u; }
+        }
+    }
+}
+
+int infonce_finalize_launch(const FinalizeParams& F, int mode, cudaStream_t st)
+{
+    if (F.nsplit > FIN_MAX_SPLITS) return set_err(GCA_ERR_UNSUPPORTED, "finalize: %d splits > %d", F.nsplit, FIN_MAX_SPLITS);
+    if (mode == FIN_FULL)       infonce_finalize_kernel<FIN_FULL><<<F.B, FIN_THREADS, 0, st>>>(F);
+    else if (mode == FIN_SHARD) infonce_finalize_kernel<FIN_SHARD><<<F.B, FIN_THREADS, 0, st>>>(F);
+    else                        infonce_finalize_kernel<FIN_BWD><<<F.B, FIN_THREADS, 0, st>>>(F);
+    GCA_LAUNCH_CHECK("infonce_finalize_kernel");
+    count_launch(1);
+    return GCA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K-shard combine: merge the W per-rank partials (+ the positive) and rescale this rank's accumulator
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FIN_THREADS)
+shard_combine_kernel(const float* __restrict__ all_max, const float* __restrict__ all_sum,
+                     const int* __restrict__ all_cnt, int W, int rank_id, int B, int d,
+                     const float* __restrict__ pos_logit, float* lse_out, float* loss_rows, int* rank_gt,
+                     float* part_acc)
+{
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float pos = pos_logit[b];
+    float m = pos;
+    for (int r = 0; r < W; ++r) m = fmaxf(m, all_max[(size_t)r * B + b]);
+    float S = __expf(pos - m);
+    int cnt = 0;
+    for (int r = 0; r < W; ++r) {                            // fixed rank order on every rank -> identical lse everywhere
+        const float pm = all_max[(size_t)r * B + b];
+        S += (pm == -INFINITY) ? 0.f : all_sum[(size_t)r * B + b] * __expf(pm - m);
+        cnt += all_cnt[(size_t)r * B + b];
+    }
+    const float lse = m + logf(S);
+    if (tid == 0) {
+        lse_out[b] = lse;
+        if (loss_rows) loss_rows[b] = lse - pos;
+        if (rank_gt) rank_gt[b] = cnt;
+    }
+    if (part_acc) {
+        const float pm = all_max[(size_t)rank_id * B + b];
+        const float w = (pm == -INFINITY) ? 0.f : __expf(pm - lse);
+        for (int c = tid; c < d; c += FIN_THREADS) part_acc[(size_t)b * d + c] *= w;
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+shard_finish_kernel(const float* __restrict__ acc, const float* __restrict__ k, const float* __restrict__ pos_logit,
+                    const float* __restrict__ lse, const float* loss_rows, int B_loc, int d, float inv_T,
+                    float* dq_unit, float* loss_mean, unsigned int* counter_unused)
+{
+    __shared__ float red[FIN_THREADS / 32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (b < B_loc && dq_unit) {
+        const float p0m1 = __expf(pos_logit[b] - lse[b]) - 1.f;
+        const float scale = inv_T / (float)B_loc;
+        for (int c = tid; c < d; c += FIN_THREADS)
+            dq_unit[(size_t)b * d + c] = scale * fmaf(p0m1, k[(size_t)b * d + c], acc[(size_t)b * d + c]);
+    }
+    if (b == B_loc && loss_mean) {                            // one extra block: the mean over the local rows
+        const float mean = block_mean_fixed(loss_rows, B_loc, red);
+        if (tid == 0) *loss_mean = mean;
+    }
+}
+
+}  // namespace gca
+
+extern "C" int gca_infonce_shard_combine(const float* all_max, const float* all_sum, const int* all_cnt, int W,
+                                         int rank_id, int B, int d, const float* pos_logit, float* lse,
+                                         float* loss_rows, int* rank_gt, float* part_acc, void* stream)
+{
+    using namespace gca;
+    GCA_CHECK_ARG(all_max && all_sum && all_cnt && pos_logit && lse, "gca_infonce_shard_combine: null pointer");
+    GCA_CHECK_ARG(W >= 1 && rank_id >= 0 && rank_id < W && B >= 1 && d >= 1, "gca_infonce_shard_combine: bad sizes");
+    shard_combine_kernel<<<B, FIN_THREADS, 0, (cudaStream_t)stream>>>(all_max, all_sum, all_cnt, W, rank_id, B, d,
+                                                                     pos_logit, lse, loss_rows, rank_gt, part_acc);
+    GCA_LAUNCH_CHECK("shard_combine_kernel");
+    count_launch(1);
+    return GCA_OK;
+}
+
+extern "C" int gca_infonce_shard_finish(const float* acc, const float* k, const float* pos_logit, const float* lse,
+                                        const float* loss_rows, int B_loc, int d, float inv_T, float* dq_unit,
+                                        float* loss_mean, void* stream)
+{
+    using namespace gca;
+    GCA_CHECK_ARG(pos_logit && lse, "gca_infonce_shard_finish: null pointer");
+    GCA_CHECK_ARG(!dq_unit || (acc && k), "gca_infonce_shard_finish: dq_unit needs acc and k");
+    GCA_CHECK_ARG(!loss_mean || loss_rows, "gca_infonce_shard_finish: loss_mean needs loss_rows");
+    GCA_CHECK_ARG(B_loc >= 1 && d >= 1, "gca_infonce_shard_finish: bad sizes");
+    shard_finish_kernel<<<B_loc + 1, FIN_THREADS, 0, (cudaStream_t)stream>>>(acc, k, pos_logit, lse, loss_rows, B_loc,
+                                                                            d, inv_T, dq_unit, loss_mean, nullptr);
+    GCA_LAUNCH_CHECK("shard_finish_kernel");
+    count_launch(1);
+    return GCA_OK;
+}

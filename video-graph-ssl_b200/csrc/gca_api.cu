@@ -1,0 +1,215 @@
+// C-ABI entry points of the InfoNCE head + library-wide helpers.  See include/gca_b200.h for the contract.
+#include "gca_common.cuh"
+#include "infonce_params.cuh"
+#include <string.h>
+#include <atomic>
+
+namespace gca {
+
+char* err_buf()
+{
+    static thread_local char buf[512] = "";
+    return buf;
+}
+
+int set_err(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count_cached()
+{
+    static int cached_dev = -1, cached_sms = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev != cached_dev) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cached_sms = sms;
+        cached_dev = dev;
+    }
+    return cached_sms;
+}
+
+int infonce_max_splits(int B)
+{
+    // every kernel family uses at most (#SMs / row blocks) splits with >= 32-row blocks; 1024 bounds finalize's smem
+    (void)B;
+    int sms = sm_count_cached();
+    if (sms < 1) sms = 148;
+    return sms < 1024 ? sms : 1024;
+}
+
+InfoNceWs infonce_ws_carve(void* base, int B, int d, int nsplit)
+{
+    InfoNceWs w{};
+    w.nsplit = nsplit;
+    w.Bpad = infonce_bpad(B);
+    char* p = (char*)base;
+    size_t off = 0;
+    w.counter = (unsigned int*)(p + off);              off += 256;
+    const size_t rows = (size_t)nsplit * w.Bpad;
+    w.part_max = (float*)(p + off);                    off += align_up(rows * sizeof(float), 256);
+    w.part_sum = (float*)(p + off);                    off += align_up(rows * sizeof(float), 256);
+    w.part_cnt = (int*)(p + off);                      off += align_up(rows * sizeof(int), 256);
+    w.pos_tmp  = (float*)(p + off);                    off += align_up((size_t)w.Bpad * sizeof(float), 256);
+    w.part_acc = (float*)(p + off);                    off += align_up(rows * d * sizeof(float), 256);
+    w.bytes = off;
+    return w;
+}
+
+static int pick_algo(int algo, int dtype_queue, int d)
+{
+    if (algo == GCA_ALGO_AUTO) return (dtype_queue == GCA_BF16 && d == 128) ? GCA_ALGO_TCGEN05 : GCA_ALGO_FFMA;
+    return algo;
+}
+
+static int check_infonce_args(const char* fn, const void* q, const void* k, const void* queue, int dtype_queue, int B,
+                              long long K, int d, float inv_T, int algo)
+{
+    GCA_CHECK_ARG(q && k && queue, "%s: null pointer", fn);
+    GCA_CHECK_ARG(dtype_queue == GCA_F32 || dtype_queue == GCA_BF16, "%s: bad dtype_queue %d", fn, dtype_queue);
+    GCA_CHECK_ARG(B >= 1 && K >= 1, "%s: need B >= 1 and K >= 1 (B=%d K=%lld)", fn, B, K);
+    GCA_CHECK_ARG(inv_T > 0.f, "%s: inv_T must be > 0", fn);
+    GCA_CHECK_ARG(algo == GCA_ALGO_AUTO || algo == GCA_ALGO_FFMA || algo == GCA_ALGO_TCGEN05, "%s: bad algo %d", fn, algo);
+    const int a = pick_algo(algo, dtype_queue, d);
+    if (a == GCA_ALGO_TCGEN05) {
+        if (dtype_queue != GCA_BF16 || d != 128)
+            return set_err(GCA_ERR_UNSUPPORTED, "%s: GCA_ALGO_TCGEN05 needs a bf16 queue and d == 128", fn);
+    } else {
+        if (d % 32 != 0 || d < 32 || d > 1024)
+            return set_err(GCA_ERR_UNSUPPORTED, "%s: GCA_ALGO_FFMA needs d %% 32 == 0 and 32 <= d <= 1024 (d=%d)", fn, d);
+    }
+    return GCA_OK;
+}
+
+static int nsplit_for(int algo, int B, long long K, int d)
+{
+    return algo == GCA_ALGO_TCGEN05 ? infonce_tc_nsplit(B, K) : infonce_ffma_nsplit(B, K, d);
+}
+
+// launch the stream kernel of the chosen family; fills `ws`
+static int run_stream(const float* q, const float* k, const void* queue, int dtype_queue, int B, long long K, int d,
+                      float inv_T, int algo, const float* lse_fixed, bool want_acc, float* pos_out, float* logits_out,
+                      void* workspace, size_t workspace_bytes, InfoNceWs* ws_out, cudaStream_t st)
+{
+    const int a = pick_algo(algo, dtype_queue, d);
+    if (sm_count_cached() < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    const int nsplit = nsplit_for(a, B, K, d);
+    InfoNceWs ws = infonce_ws_carve(workspace, B, d, nsplit);
+    if (!workspace || workspace_bytes < ws.bytes)
+        return set_err(GCA_ERR_WORKSPACE, "InfoNCE workspace too small: %zu bytes given, %zu needed", workspace_bytes, ws.bytes);
+    InfoNceStreamParams P{};
+    P.q = q; P.k = k; P.queue = queue; P.B = B; P.K = K; P.d = d; P.inv_T = inv_T; P.lse_fixed = lse_fixed;
+    P.counter = ws.counter; P.part_max = ws.part_max; P.part_sum = ws.part_sum; P.part_cnt = ws.part_cnt;
+    P.part_acc = want_acc ? ws.part_acc : nullptr;
+    P.nsplit = nsplit; P.Bpad = ws.Bpad; P.pos_out = pos_out ? pos_out : ws.pos_tmp; P.logits_out = logits_out; P.ld_logits = K + 1;
+    *ws_out = ws;
+    count_launch(1);
+    if (a == GCA_ALGO_TCGEN05) return infonce_tc_launch(P, lse_fixed != nullptr, st);
+    return infonce_ffma_launch(P, dtype_queue, lse_fixed != nullptr, st);
+}
+
+}  // namespace gca
+
+extern "C" int gca_version(void) { return GCA_ABI_VERSION; }
+extern "C" const char* gca_last_error(void) { return gca::err_buf(); }
+extern "C" long long gca_launch_count(void) { return gca::g_launches.load(); }
+extern "C" int gca_sm_count(void)
+{
+    const int n = gca::sm_count_cached();
+    return n > 0 ? n : gca::set_err(GCA_ERR_CUDA, "no CUDA device available");
+}
+
+extern "C" size_t gca_infonce_workspace_bytes(int B, long long K, int d, int dtype_queue, int algo)
+{
+    using namespace gca;
+    (void)K; (void)dtype_queue; (void)algo;
+    if (B < 1 || d < 1) return 0;
+    // sized for the largest split count any family may choose on this device (so one allocation serves all calls)
+    return infonce_ws_carve(nullptr, B, d, infonce_max_splits(B)).bytes;
+}
+
+extern "C" int gca_infonce_fwd(const float* q, const float* k, const void* queue, int dtype_queue, int B, long long K,
+                               int d, float inv_T, int algo, float* loss_mean, float* loss_rows, float* lse,
+                               float* pos_logit, int* rank_gt, float* dq_unit, float* logits_out, void* workspace,
+                               size_t workspace_bytes, void* stream)
+{
+    using namespace gca;
+    int rc = check_infonce_args("gca_infonce_fwd", q, k, queue, dtype_queue, B, K, d, inv_T, algo);
+    if (rc != GCA_OK) return rc;
+    GCA_CHECK_ARG(loss_rows && lse && pos_logit && rank_gt, "gca_infonce_fwd: loss_rows, lse, pos_logit, rank_gt are required");
+    cudaStream_t st = (cudaStream_t)stream;
+    InfoNceWs ws;
+    rc = run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, dq_unit != nullptr, pos_logit, logits_out,
+                    workspace, workspace_bytes, &ws, st);
+    if (rc != GCA_OK) return rc;
+    FinalizeParams F{};
+    F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
+    F.part_acc = dq_unit ? ws.part_acc : nullptr;
+    F.nsplit = ws.nsplit; F.Bpad = ws.Bpad; F.B = B; F.d = d; F.inv_T = inv_T; F.k = k; F.pos = pos_logit;
+    F.lse = lse; F.loss_rows = loss_rows; F.rank_gt = rank_gt; F.dq = dq_unit; F.loss_mean = loss_mean;
+    return infonce_finalize_launch(F, FIN_FULL, st);
+}
+
+extern "C" int gca_infonce_partials(const float* q, const float* k, const void* queue, int dtype_queue, int B,
+                                    long long K, int d, float inv_T, int algo, int want_acc, void* workspace,
+                                    size_t workspace_bytes, void* stream)
+{
+    using namespace gca;
+    int rc = check_infonce_args("gca_infonce_partials", q, k, queue, dtype_queue, B, K, d, inv_T, algo);
+    if (rc != GCA_OK) return rc;
+    InfoNceWs ws;
+    return run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, want_acc != 0, nullptr, nullptr, workspace,
+                      workspace_bytes, &ws, (cudaStream_t)stream);
+}
+
+extern "C" int gca_infonce_bwd(const float* q, const float* k, const void* queue, int dtype_queue, int B, long long K,
+                               int d, float inv_T, int algo, const float* lse, float grad_scale, float* dq,
+                               void* workspace, size_t workspace_bytes, void* stream)
+{
+    using namespace gca;
+    int rc = check_infonce_args("gca_infonce_bwd", q, k, queue, dtype_queue, B, K, d, inv_T, algo);
+    if (rc != GCA_OK) return rc;
+    GCA_CHECK_ARG(lse && dq, "gca_infonce_bwd: lse and dq are required");
+    cudaStream_t st = (cudaStream_t)stream;
+    InfoNceWs ws;
+    // the stream kernel recomputes the positive logits into ws.pos_tmp
+    rc = run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, lse, true, nullptr, nullptr, workspace,
+                    workspace_bytes, &ws, st);
+    if (rc != GCA_OK) return rc;
+    FinalizeParams F{};
+    F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
+    F.part_acc = ws.part_acc; F.nsplit = ws.nsplit; F.Bpad = ws.Bpad; F.B = B; F.d = d; F.inv_T = inv_T; F.k = k;
+    F.pos = ws.pos_tmp; F.lse_in = lse; F.grad_scale = grad_scale; F.dq = dq;
+    return infonce_finalize_launch(F, FIN_BWD, st);
+}
+
+extern "C" int gca_infonce_shard_fwd(const float* q, const float* k, const void* shard, int dtype_queue, int B,
+                                     long long K_shard, int d, float inv_T, int algo, float* pos_logit, float* part_max,
+                                     float* part_sum, int* part_cnt, float* part_acc, void* workspace,
+                                     size_t workspace_bytes, void* stream)
+{
+    using namespace gca;
+    int rc = check_infonce_args("gca_infonce_shard_fwd", q, k, shard, dtype_queue, B, K_shard, d, inv_T, algo);
+    if (rc != GCA_OK) return rc;
+    GCA_CHECK_ARG(pos_logit && part_max && part_sum && part_cnt, "gca_infonce_shard_fwd: null output pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    InfoNceWs ws;
+    rc = run_stream(q, k, shard, dtype_queue, B, K_shard, d, inv_T, algo, nullptr, part_acc != nullptr, pos_logit, nullptr,
+                    workspace, workspace_bytes, &ws, st);
+    if (rc != GCA_OK) return rc;
+    FinalizeParams F{};
+    F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
+    F.part_acc = part_acc ? ws.part_acc : nullptr;
+    F.nsplit = ws.nsplit; F.Bpad = ws.Bpad; F.B = B; F.d = d; F.inv_T = inv_T; F.k = k; F.pos = pos_logit;
+    F.out_max = part_max; F.out_sum = part_sum; F.out_cnt = part_cnt; F.out_acc = part_acc;
+    return infonce_finalize_launch(F, FIN_SHARD, st);
+}

@@ -1,0 +1,184 @@
+// K4: temporal clip-graph head, forward (lib/ops/module_wrappers/temporal_graph.py:150-239 between the 1x1x1
+// convolutions), the grid-parallel aggregation kernel and the C-ABI entry points of both directions.
+// Two device primitives (graph_dev.cuh) cover everything:
+//   pair_dots : M[i][j] = sum_{c,s} A[c][i][s] * B[c][j][s]        (similarity logits; ds in backward)
+//   aggregate : out[c][i][:] = sum_j M(i,j) in[c][j][:] (+ in[c][i][:])   (GCN aggregation; all three input grads)
+// Small videos (embedding-level heads) run ONE CTA per video with everything in shared memory; large feature maps
+// split into an adjacency kernel (one CTA per video) and a grid-parallel aggregation kernel with 128-bit loads.
+// All sums have a fixed order (deterministic).
+#include "graph_dev.cuh"
+
+namespace gca {
+
+// forward, one CTA per video.  kAgg: also aggregate (fused path); otherwise only sim/adj/s are produced.
+template <int TMAX, int VH, bool kAgg>
+__global__ void __launch_bounds__(G_THREADS)
+graph_fwd_kernel(const GraphArgs a)
+{
+    extern __shared__ __align__(16) float gsm[];
+    float* tiles = gsm;
+    float* red = tiles + 2 * G_CHUNK_FLOATS;
+    float* m0 = red + 4 * G_THREADS;                  // logits -> s
+    float* m1 = m0 + G_TMAXMAX * G_TMAXMAX;           // sim
+    float* m2 = m1 + G_TMAXMAX * G_TMAXMAX;           // adj
+    const int b = blockIdx.x, T = a.T;
+    const size_t tt = (size_t)b * T * T;
+    pair_dots(a.gq + (size_t)b * a.Cq * T * a.S, a.gk + (size_t)b * a.Cq * T * a.S, a.Cq, T, a.S, tiles, red, m0);
+    adj_forward(m0, m1, m2, a.u + tt, a.th, T, a.max_hop, a.inv_temp, a.sim + tt, a.adj + tt, a.s + tt);
+    if constexpr (kAgg) {
+        const size_t off = (size_t)b * a.C * T * a.HW;
+        aggregate_items<TMAX, VH>(a.support + off, a.y + off, m0, false, true, a.C, T, a.HW, threadIdx.x, G_THREADS);
+    }
+}
+
+// grid-parallel aggregation for large feature maps: grid = (chunks, B, jobs)
+template <int TMAX>
+__global__ void __launch_bounds__(G_THREADS)
+graph_agg_kernel(const AggJobs jobs)
+{
+    __shared__ float M[G_TMAXMAX * G_TMAXMAX];
+    const AggJob jb = jobs.j[blockIdx.z];
+    const int T = jobs.T, b = blockIdx.y;
+    for (int p = threadIdx.x; p < T * T; p += G_THREADS) M[p] = __ldg(jb.M + (size_t)b * T * T + p);
+    __syncthreads();
+    const size_t off = (size_t)b * jb.Cn * T * jb.S;
+    const int begin = blockIdx.x * G_THREADS + threadIdx.x, stride = gridDim.x * G_THREADS;
+    if (TMAX <= 16 && jb.S % 4 == 0)
+        aggregate_items<TMAX, (TMAX <= 16 ? 4 : 1)>(jb.in + off, jb.out + off, M, jb.transpose != 0, jb.skip != 0, jb.Cn, T,
+                                                    jb.S, begin, stride);
+    else
+        aggregate_items<TMAX, 1>(jb.in + off, jb.out + off, M, jb.transpose != 0, jb.skip != 0, jb.Cn, T, jb.S, begin, stride);
+}
+
+void fill_theta(GraphTheta& th, float alpha, int max_hop)
+{
+    for (int h = 0; h <= G_TMAXMAX; ++h) {
+        const double e = exp(-(double)h);
+        th.w[h] = (h <= max_hop) ? (float)(e / (1.0 + e * e) + (double)alpha) : 0.f;   // temporal_graph.py:206
+    }
+}
+
+template <int TM, int VH, bool kAgg>
+static int launch_fwd_one(const GraphArgs& a, cudaStream_t st)
+{
+    const size_t smem = G_SMEM_FLOATS * sizeof(float);
+    auto kern = graph_fwd_kernel<TM, VH, kAgg>;
+    GCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<a.B, G_THREADS, smem, st>>>(a);
+    GCA_LAUNCH_CHECK("graph_fwd_kernel");
+    count_launch(1);
+    return GCA_OK;
+}
+
+static int graph_fwd_adj_launch(const GraphArgs& a, bool fused, cudaStream_t st)
+{
+    if (!fused) return launch_fwd_one<4, 1, false>(a, st);
+    const bool v4 = (a.HW % 4 == 0);
+    switch (pick_tmax(a.T)) {
+        case 4:  return v4 ? launch_fwd_one<4, 4, true>(a, st) : launch_fwd_one<4, 1, true>(a, st);
+        case 8:  return v4 ? launch_fwd_one<8, 4, true>(a, st) : launch_fwd_one<8, 1, true>(a, st);
+        case 16: return v4 ? launch_fwd_one<16, 4, true>(a, st) : launch_fwd_one<16, 1, true>(a, st);
+        default: return launch_fwd_one<32, 1, true>(a, st);
+    }
+}
+
+int graph_agg_launch(const AggJobs& jobs, int njobs, int B, cudaStream_t st)
+{
+    long long max_items = 0;
+    for (int i = 0; i < njobs; ++i) {
+        const long long it = (long long)jobs.j[i].Cn * (jobs.j[i].S % 4 == 0 ? jobs.j[i].S / 4 : jobs.j[i].S);
+        if (it > max_items) max_items = it;
+    }
+    int chunks = (int)((max_items + G_THREADS - 1) / G_THREADS);
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    dim3 grid(chunks, B, njobs);
+    switch (pick_tmax(jobs.T)) {
+        case 4:  graph_agg_kernel<4><<<grid, G_THREADS, 0, st>>>(jobs); break;
+        case 8:  graph_agg_kernel<8><<<grid, G_THREADS, 0, st>>>(jobs); break;
+        case 16: graph_agg_kernel<16><<<grid, G_THREADS, 0, st>>>(jobs); break;
+        default: graph_agg_kernel<32><<<grid, G_THREADS, 0, st>>>(jobs); break;
+    }
+    GCA_LAUNCH_CHECK("graph_agg_kernel");
+    count_launch(1);
+    return GCA_OK;
+}
+
+// one CTA per video is the right shape while a video's tensors are small; above this the aggregation is spread
+// over the whole grid
+static bool use_fused(const GraphArgs& a)
+{
+    const size_t per_video = ((size_t)a.C * a.HW + 2ull * a.Cq * a.S) * a.T * sizeof(float);
+    return per_video <= 256u * 1024u;
+}
+
+static int check_graph_args(const char* fn, int Cq, int S, int C, int HW, int T, int B, int max_hop, float temperature,
+                            unsigned flags)
+{
+    GCA_CHECK_ARG(Cq >= 1 && S >= 1 && C >= 1 && HW >= 1 && B >= 1, "%s: bad sizes", fn);
+    GCA_CHECK_ARG(T >= 1 && T <= G_TMAXMAX, "%s: T=%d outside [1, %d]", fn, T, G_TMAXMAX);
+    GCA_CHECK_ARG(max_hop >= 0, "%s: max_hop < 0", fn);
+    GCA_CHECK_ARG(temperature > 0.f, "%s: temperature must be > 0", fn);
+    if (flags != GCA_GRAPH_REFERENCE) return set_err(GCA_ERR_UNSUPPORTED, "%s: flags 0x%x not supported", fn, flags);
+    return GCA_OK;
+}
+
+}  // namespace gca
+
+extern "C" size_t gca_graph_workspace_bytes(int B, int T)
+{
+    return (B > 0 && T > 0) ? (size_t)B * T * T * sizeof(float) : 0;
+}
+
+extern "C" int gca_graph_fwd(const float* gq, const float* gk, int Cq, int S, const float* support, int C, int HW,
+                             int T, int B, const float* u, float alpha, int max_hop, float temperature, unsigned flags,
+                             float* sim, float* adj, float* s, float* y, void* stream)
+{
+    using namespace gca;
+    GCA_CHECK_ARG(gq && gk && support && u && sim && adj && s && y, "gca_graph_fwd: null pointer");
+    int rc = check_graph_args("gca_graph_fwd", Cq, S, C, HW, T, B, max_hop, temperature, flags);
+    if (rc != GCA_OK) return rc;
+    GraphArgs a{};
+    a.gq = gq; a.gk = gk; a.Cq = Cq; a.S = S; a.support = support; a.C = C; a.HW = HW; a.T = T; a.B = B; a.u = u;
+    a.max_hop = max_hop; a.inv_temp = 1.f / temperature; a.sim = sim; a.adj = adj; a.s = s; a.y = y;
+    fill_theta(a.th, alpha, max_hop);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (use_fused(a)) return graph_fwd_adj_launch(a, true, st);
+    rc = graph_fwd_adj_launch(a, false, st);
+    if (rc != GCA_OK) return rc;
+    AggJobs jobs{};
+    jobs.T = T;
+    jobs.j[0] = AggJob{support, y, s, 0, 1, C, HW};
+    return graph_agg_launch(jobs, 1, B, st);
+}
+
+extern "C" int gca_graph_bwd(const float* gq, const float* gk, int Cq, int S, const float* support, int C, int HW,
+                             int T, int B, const float* sim, const float* adj, const float* s, const float* dy,
+                             float alpha, int max_hop, float temperature, unsigned flags,
+                             float* d_gq, float* d_gk, float* d_support, void* workspace, size_t workspace_bytes,
+                             void* stream)
+{
+    using namespace gca;
+    GCA_CHECK_ARG(gq && gk && support && sim && adj && s && dy && d_gq && d_gk && d_support, "gca_graph_bwd: null pointer");
+    int rc = check_graph_args("gca_graph_bwd", Cq, S, C, HW, T, B, max_hop, temperature, flags);
+    if (rc != GCA_OK) return rc;
+    GraphArgs a{};
+    a.gq = gq; a.gk = gk; a.Cq = Cq; a.S = S; a.support = support; a.C = C; a.HW = HW; a.T = T; a.B = B;
+    a.max_hop = max_hop; a.inv_temp = 1.f / temperature;
+    a.sim = const_cast<float*>(sim); a.adj = const_cast<float*>(adj); a.s = const_cast<float*>(s);
+    a.dy = dy; a.d_gq = d_gq; a.d_gk = d_gk; a.d_support = d_support;
+    fill_theta(a.th, alpha, max_hop);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (use_fused(a)) return graph_bwd_adj_launch(a, true, st);
+    if (!workspace || workspace_bytes < gca_graph_workspace_bytes(B, T))
+        return set_err(GCA_ERR_WORKSPACE, "gca_graph_bwd: workspace of %zu bytes needed", gca_graph_workspace_bytes(B, T));
+    a.dl = (float*)workspace;
+    rc = graph_bwd_adj_launch(a, false, st);
+    if (rc != GCA_OK) return rc;
+    AggJobs jobs{};
+    jobs.T = T;
+    jobs.j[0] = AggJob{dy, d_support, s, 1, 1, C, HW};
+    jobs.j[1] = AggJob{gk, d_gq, a.dl, 0, 0, Cq, S};
+    jobs.j[2] = AggJob{gq, d_gk, a.dl, 1, 0, Cq, S};
+    return graph_agg_launch(jobs, 3, B, st);
+}

@@ -1,0 +1,54 @@
+// Parameter block shared by the two InfoNCE stream kernel families (ffma, tcgen05).
+#pragma once
+#include "gca_common.cuh"
+
+namespace gca {
+
+struct InfoNceStreamParams {
+    const float* q;          // [B, d] fp32
+    const float* k;          // [B, d] fp32 (positive keys)
+    const void*  queue;      // [K, d] fp32 or bf16
+    int          B;
+    long long    K;
+    int          d;
+    float        inv_T;
+    const float* lse_fixed;  // [B] row log-sum-exp (fixed-max / backward-recompute mode) or NULL
+    // split partials (workspace)
+    unsigned int* counter;
+    float* part_max;         // [nsplit, Bpad]
+    float* part_sum;         // [nsplit, Bpad]
+    int*   part_cnt;         // [nsplit, Bpad]
+    float* part_acc;         // [nsplit, Bpad, d] or NULL (no gradient wanted)
+    int    nsplit;
+    int    Bpad;
+    float* pos_out;          // [B] or NULL
+    float* logits_out;       // [B, ld_logits] or NULL (ffma family only)
+    long long ld_logits;
+};
+
+// ffma family (infonce_ffma.cu)
+int infonce_ffma_nsplit(int B, long long K, int d);
+int infonce_ffma_launch(const InfoNceStreamParams& P, int dtype_queue, bool fixed_max, cudaStream_t st);
+// tcgen05 family (infonce_tc.cu)
+int infonce_tc_nsplit(int B, long long K);
+int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t st);
+
+// finalize.cu
+enum FinalizeMode { FIN_FULL = 0, FIN_SHARD = 1, FIN_BWD = 2 };
+struct FinalizeParams {
+    // split partials
+    unsigned int* counter;
+    const float* part_max; const float* part_sum; const int* part_cnt; const float* part_acc;
+    int nsplit, Bpad, B, d;
+    float inv_T;
+    const float* k;          // [B, d]
+    const float* pos;        // [B]
+    const float* lse_in;     // FIN_BWD: given lse
+    float grad_scale;        // FIN_BWD
+    // outputs
+    float* lse; float* loss_rows; int* rank_gt; float* dq; float* loss_mean;     // FIN_FULL / FIN_BWD (dq)
+    float* out_max; float* out_sum; int* out_cnt; float* out_acc;                // FIN_SHARD
+};
+int infonce_finalize_launch(const FinalizeParams& F, int mode, cudaStream_t st);
+
+}  // namespace gca

@@ -1,0 +1,142 @@
+// K7: retrieval -- cosine similarity matrix + per-query top-k (k <= 64), replacing sklearn cosine_distances +
+// full-row np.argsort in tools/video_retrieval.py:174-186.  Three launches: row inverse norms, a tiled fp32 GEMM
+// that writes the [Nq, Ng] similarity panel into the workspace, and a per-row k-round arg-max selection with
+// ties going to the lower gallery index (== stable argsort of the distances).
+#include "gca_common.cuh"
+
+namespace gca {
+
+__global__ void __launch_bounds__(128)
+row_inv_norm_kernel(const float* __restrict__ x, int n, int d, int normalize, float* __restrict__ inv)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * 4 + warp;
+    if (row >= n) return;
+    float a = 0.f;
+    if (normalize) {
+        const float* r = x + (size_t)row * d;
+        for (int c = lane; c < d; c += 32) { const float v = __ldg(r + c); a = fmaf(v, v, a); }
+        a = warp_sum(a);
+        a = 1.f / fmaxf(sqrtf(a), 1e-12f);
+    } else {
+        a = 1.f;
+    }
+    if (lane == 0) inv[row] = a;
+}
+
+// C[i][j] = invq[i] * invg[j] * sum_c Q[i][c] G[j][c];  64x64 tile, 256 threads, 4x4 micro-tiles, 16-wide k-chunks
+constexpr int ST_BM = 64, ST_BN = 64, ST_BK = 16;
+__global__ void __launch_bounds__(256)
+sim_gemm_kernel(const float* __restrict__ Q, const float* __restrict__ G, int Nq, int Ng, int d,
+                const float* __restrict__ invq, const float* __restrict__ invg, float* __restrict__ C)
+{
+    __shared__ float As[ST_BK][ST_BM + 1];
+    __shared__ float Bs[ST_BK][ST_BN + 1];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.y * ST_BM, j0 = blockIdx.x * ST_BN;
+    float acc[4][4] = {};
+    for (int c0 = 0; c0 < d; c0 += ST_BK) {
+        for (int e = tid; e < ST_BM * ST_BK; e += 256) {
+            const int r = e / ST_BK, c = e % ST_BK;
+            As[c][r] = (i0 + r < Nq && c0 + c < d) ? __ldg(Q + (size_t)(i0 + r) * d + c0 + c) : 0.f;
+            Bs[c][r] = (j0 + r < Ng && c0 + c < d) ? __ldg(G + (size_t)(j0 + r) * d + c0 + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < ST_BK; ++c) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[c][ty * 4 + i]; b[i] = Bs[c][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i0 + ty * 4 + i;
+        if (r >= Nq) continue;
+        const float sq = invq[r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cidx = j0 + tx * 4 + j;
+            if (cidx < Ng) C[(size_t)r * Ng + cidx] = acc[i][j] * sq * invg[cidx];
+        }
+    }
+}
+
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+// one CTA per query row; k rounds of block arg-max with per-thread cached candidates
+__global__ void __launch_bounds__(256)
+row_topk_kernel(float* __restrict__ sim, int Ng, int k, int* __restrict__ idx_out, float* __restrict__ val_out)
+{
+    __shared__ float wv[8];
+    __shared__ int wi[8];
+    __shared__ int win_idx;
+    __shared__ float win_val;
+    float* row = sim + (size_t)blockIdx.x * Ng;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int j = tid; j < Ng; j += 256) { const float v = row[j]; if (better(v, j, bv, bi)) { bv = v; bi = j; } }
+    for (int r = 0; r < k; ++r) {
+        float v = bv; int i = bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (better(ov, oi, v, i)) { v = ov; i = oi; }
+        }
+        if (lane == 0) { wv[warp] = v; wi[warp] = i; }
+        __syncthreads();
+        if (tid == 0) {
+            float fv = wv[0]; int fi = wi[0];
+            for (int w = 1; w < 8; ++w) if (better(wv[w], wi[w], fv, fi)) { fv = wv[w]; fi = wi[w]; }
+            win_idx = fi; win_val = fv;
+            idx_out[(size_t)blockIdx.x * k + r] = (fi == 0x7fffffff) ? -1 : fi;
+            if (val_out) val_out[(size_t)blockIdx.x * k + r] = fv;
+        }
+        __syncthreads();
+        const int w = win_idx;
+        if (w != 0x7fffffff && (w & 255) == tid) {           // the owner retires the winner and rescans its elements
+            row[w] = -INFINITY;
+            bv = -INFINITY; bi = 0x7fffffff;
+            for (int j = tid; j < Ng; j += 256) { const float x = row[j]; if (better(x, j, bv, bi)) { bv = x; bi = j; } }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace gca
+
+extern "C" size_t gca_sim_topk_workspace_bytes(int Nq, int Ng, int d, int k)
+{
+    (void)d; (void)k;
+    if (Nq <= 0 || Ng <= 0) return 0;
+    return gca::align_up((size_t)Nq * Ng * sizeof(float), 256) + gca::align_up((size_t)(Nq + Ng) * sizeof(float), 256);
+}
+
+extern "C" int gca_sim_topk(const float* queries, const float* gallery, int Nq, int Ng, int d, int k, int normalize,
+                            int* idx_out, float* val_out, void* workspace, size_t workspace_bytes, void* stream)
+{
+    using namespace gca;
+    GCA_CHECK_ARG(queries && gallery && idx_out, "gca_sim_topk: null pointer");
+    GCA_CHECK_ARG(Nq >= 1 && Ng >= 1 && d >= 1, "gca_sim_topk: bad sizes");
+    GCA_CHECK_ARG(k >= 1 && k <= 64 && k <= Ng, "gca_sim_topk: k=%d must be in [1, min(64, Ng)]", k);
+    if (!workspace || workspace_bytes < gca_sim_topk_workspace_bytes(Nq, Ng, d, k))
+        return set_err(GCA_ERR_WORKSPACE, "gca_sim_topk: workspace of %zu bytes needed", gca_sim_topk_workspace_bytes(Nq, Ng, d, k));
+    cudaStream_t st = (cudaStream_t)stream;
+    float* sim = (float*)workspace;
+    float* invq = (float*)((char*)workspace + align_up((size_t)Nq * Ng * sizeof(float), 256));
+    float* invg = invq + Nq;
+    row_inv_norm_kernel<<<(Nq + 3) / 4, 128, 0, st>>>(queries, Nq, d, normalize, invq);
+    row_inv_norm_kernel<<<(Ng + 3) / 4, 128, 0, st>>>(gallery, Ng, d, normalize, invg);
+    dim3 grid((Ng + ST_BN - 1) / ST_BN, (Nq + ST_BM - 1) / ST_BM);
+    sim_gemm_kernel<<<grid, 256, 0, st>>>(queries, gallery, Nq, Ng, d, invq, invg, sim);
+    row_topk_kernel<<<Nq, 256, 0, st>>>(sim, Ng, k, idx_out, val_out);
+    GCA_LAUNCH_CHECK("sim_topk kernels");
+    count_launch(4);
+    return GCA_OK;
+}

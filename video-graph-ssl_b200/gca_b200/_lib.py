@@ -1,0 +1,103 @@
+"""ctypes binding of libgca_b200.so (include/gca_b200.h).
+
+There is no CPU fallback anywhere in this package: if the shared library is missing every op raises
+`GcaLibraryError` (build it with `python video-graph-ssl_b200/build.py` or `__graft_entry__.build()`),
+and if no CUDA device is present the library's compute entry points return GCA_ERR_CUDA.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgca_b200.so")
+
+GCA_OK = 0
+GCA_F32, GCA_BF16 = 0, 1
+ALGO = {"auto": 0, "ffma": 1, "tcgen05": 2}
+
+
+class GcaLibraryError(RuntimeError):
+    pass
+
+
+class GcaError(RuntimeError):
+    def __init__(self, fn, code, msg):
+        super().__init__("%s failed with code %d: %s" % (fn, code, msg))
+        self.code = code
+
+
+# name -> (restype, argtypes); must list every symbol include/gca_b200.h declares (tests check this)
+SIGNATURES = {
+    "gca_version": (c_int, []),
+    "gca_last_error": (c_char_p, []),
+    "gca_sm_count": (c_int, []),
+    "gca_launch_count": (c_longlong, []),
+    "gca_enqueue_devptr": (c_int, [c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_int, c_void_p, c_int, c_void_p,
+                                   c_void_p]),
+    "gca_infonce_partials": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int, c_int,
+                                     c_void_p, c_size_t, c_void_p]),
+    "gca_enqueue": (c_int, [c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_int, c_void_p, c_int, c_longlong,
+                            c_void_p]),
+    "gca_infonce_workspace_bytes": (c_size_t, [c_int, c_longlong, c_int, c_int, c_int]),
+    "gca_infonce_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_size_t, c_void_p]),
+    "gca_infonce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
+                                c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gca_infonce_shard_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gca_infonce_shard_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gca_infonce_shard_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                         c_void_p, c_void_p, c_void_p]),
+    "gca_graph_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                              c_float, c_int, c_float, c_uint, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gca_graph_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_float, c_uint,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gca_graph_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gca_negcos_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                   c_void_p]),
+    "gca_negcos_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gca_sim_topk_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "gca_sim_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                             c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise loudly when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GcaLibraryError(
+                "%s is missing: build it with `python video-graph-ssl_b200/build.py` "
+                "(there is no CPU or PyTorch fallback for the hot path)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().gca_last_error().decode("utf-8", "replace")
+
+
+def check(fn_name, rc):
+    if rc != GCA_OK:
+        raise GcaError(fn_name, rc, last_error())
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def call(name, *args):
+    rc = getattr(load(), name)(*args)
+    check(name, rc)

@@ -1,0 +1,160 @@
+"""MoCo queue sharded along K over a torch.distributed process group (one process per GPU, NCCL over NVLink).
+
+The reference replicates the queue on every rank: it is broadcast once (train_video_contrast_dis.py:233-242) and
+every rank enqueues the same gathered keys (mem_moco.py:81-83, train...:222), so all replicas stay identical.
+Sharding therefore changes no observable result: rank r owns global slots [r*K/W, (r+1)*K/W), every rank scores
+ALL gathered query rows against its shard, and the online-softmax partials are merged with two small collectives
+(SURVEY.md section 8e, Appendix A.4):
+
+    all-gather q, k                      [B_loc, d] -> [B_glob, d]       (the key gather the reference already does)
+    shard kernel                         (max, sum-exp, count, acc) of every row against the local shard
+    all-gather of the [3, B_glob] stats  12*B_glob bytes per rank
+    combine kernel                       lse, loss rows, rank; acc *= exp(max_r - lse)
+    reduce-scatter(sum) of acc           [B_glob, d] -> [B_loc, d]
+    finish kernel                        dq_unit, mean loss over the local rows (DDP averages across ranks)
+
+Compute goes through `ShardCompute` (the C ABI).  The collectives are plain torch.distributed calls; on the gloo
+backend (CPU tests) reduce-scatter is emulated with all-reduce + slice.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from . import functional as GF
+from ._lib import ptr
+from .memory.moco_queue import FusedLogits
+
+
+class ShardCompute(object):
+    """The four per-rank compute steps on the CUDA library (include/gca_b200.h, 'sharded' section)."""
+
+    def shard_fwd(self, q_all, k_all, shard, T, algo, want_grad):
+        GF._need_cuda(q_all, k_all, shard)
+        B, d = q_all.shape
+        dev = q_all.device
+        qd = GF.queue_dtype_code(shard)
+        pos = torch.empty(B, dtype=torch.float32, device=dev)
+        stats = torch.empty(3, B, dtype=torch.float32, device=dev)          # max, sum, count (int32 bits)
+        acc = torch.empty(B, d, dtype=torch.float32, device=dev) if want_grad else None
+        ws = GF.workspace(dev, GF.infonce_workspace_bytes(B, shard.shape[0], d, qd, algo), "infonce")
+        _lib.call("gca_infonce_shard_fwd", ptr(q_all), ptr(k_all), ptr(shard), qd, B, shard.shape[0], d, 1.0 / T,
+                  _lib.ALGO[algo], ptr(pos), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]), ptr(acc), ptr(ws), ws.numel(),
+                  GF._stream(q_all))
+        return pos, stats, acc
+
+    def shard_combine(self, all_stats, rank_id, pos, acc):
+        W, _, B = all_stats.shape
+        dev = pos.device
+        lse = torch.empty(B, dtype=torch.float32, device=dev)
+        loss_rows = torch.empty(B, dtype=torch.float32, device=dev)
+        rank_gt = torch.empty(B, dtype=torch.int32, device=dev)
+        st = all_stats.permute(1, 0, 2).contiguous()                        # [3, W, B]
+        d = acc.shape[1] if acc is not None else 1
+        _lib.call("gca_infonce_shard_combine", ptr(st[0]), ptr(st[1]), ptr(st[2]), W, rank_id, B, d, ptr(pos), ptr(lse),
+                  ptr(loss_rows), ptr(rank_gt), ptr(acc), GF._stream(pos))
+        return lse, loss_rows, rank_gt
+
+    def shard_finish(self, acc_loc, k_loc, pos_loc, lse_loc, loss_rows_loc, T):
+        B_loc = pos_loc.shape[0]
+        dev = pos_loc.device
+        d = k_loc.shape[1]
+        dq_unit = torch.empty(B_loc, d, dtype=torch.float32, device=dev) if acc_loc is not None else None
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        _lib.call("gca_infonce_shard_finish", ptr(acc_loc), ptr(k_loc), ptr(pos_loc), ptr(lse_loc), ptr(loss_rows_loc),
+                  B_loc, d, 1.0 / T, ptr(dq_unit), ptr(loss), GF._stream(pos_loc))
+        return dq_unit, loss
+
+    def enqueue(self, shard, keys, index, K, k_begin):
+        return GF.enqueue_(shard, keys, index, K_global=K, k_begin=k_begin)
+
+
+def _all_gather_rows(x, group):
+    W = dist.get_world_size(group)
+    out = torch.empty((W * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def _reduce_scatter_rows(x, group):
+    """[W*n, d] summed over ranks, rank r keeps rows [r*n, (r+1)*n)."""
+    W, r = dist.get_world_size(group), dist.get_rank(group)
+    n = x.shape[0] // W
+    if dist.get_backend(group) == "gloo":                   # gloo has no reduce-scatter
+        y = x.clone()
+        dist.all_reduce(y, group=group)
+        return y[r * n:(r + 1) * n].contiguous()
+    out = torch.empty((n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.reduce_scatter_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+class _ShardedInfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k_all_or_k, shard, owner):
+        group, T, comp = owner.group, owner.T, owner.compute
+        W, r = dist.get_world_size(group), dist.get_rank(group)
+        want = ctx.needs_input_grad[0]
+        B_loc = q.shape[0]
+        q32 = q.detach().float().contiguous()
+        q_all = _all_gather_rows(q32, group)
+        k_all = k_all_or_k if k_all_or_k.shape[0] == q_all.shape[0] else _all_gather_rows(k_all_or_k.float(), group)
+        k_all = k_all.float().contiguous()
+        pos, stats, acc = comp.shard_fwd(q_all, k_all, shard, T, owner.algo, want)
+        all_stats = _all_gather_rows(stats.unsqueeze(0), group)              # [W, 3, B_glob]
+        lse, loss_rows, rank_gt = comp.shard_combine(all_stats, r, pos, acc)
+        acc_loc = _reduce_scatter_rows(acc, group) if want else None
+        sl = slice(r * B_loc, (r + 1) * B_loc)
+        dq_unit, loss = comp.shard_finish(acc_loc, k_all[sl].contiguous(), pos[sl].contiguous(), lse[sl].contiguous(),
+                                          loss_rows[sl].contiguous(), T)
+        if want:
+            ctx.save_for_backward(dq_unit)
+        ctx.in_dtype = q.dtype
+        outs = (loss, loss_rows[sl].contiguous(), lse[sl].contiguous(), pos[sl].contiguous(), rank_gt[sl].contiguous(),
+                k_all)
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        (dq_unit,) = ctx.saved_tensors
+        return (dq_unit * g_loss).to(ctx.in_dtype), None, None, None
+
+
+class ShardedRGBMoCo(nn.Module):
+    """`RGBMoCo` with the queue split along K over `group`.  `forward(q, k, all_k=None)` takes the LOCAL q, k
+    (and optionally the already gathered keys, as the trainer passes them) and returns (FusedLogits, labels) for the
+    local rows; the loss is the mean over local rows, exactly what each DDP replica of the reference computes."""
+
+    def __init__(self, n_dim, K=65536, T=0.07, group=None, queue_dtype="fp32", algo="auto", compute=None, device=None):
+        super(ShardedRGBMoCo, self).__init__()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if K % self.world != 0:
+            raise ValueError("K=%d must divide evenly over %d ranks" % (K, self.world))
+        self.K, self.T, self.index = K, T, 0
+        self.algo = algo
+        self.compute = compute if compute is not None else ShardCompute()
+        self.k_begin = self.rank * (K // self.world)
+        # every rank draws the full queue like the reference (mem_moco.py:57-58); rank 0's draw wins
+        # (train_video_contrast_dis.py:233-242), then each rank keeps only the slots it owns
+        full = F.normalize(torch.randn(K, n_dim))
+        if device is not None:
+            full = full.to(device)
+        dist.broadcast(full, 0, group=self.group)
+        shard = full[self.k_begin:self.k_begin + K // self.world].clone()
+        self.register_buffer('memory', shard.to(torch.bfloat16) if queue_dtype == "bf16" else shard)
+
+    def forward(self, q, k, all_k=None):
+        k = k.detach()
+        src = all_k.detach() if all_k is not None else k
+        loss, loss_rows, lse, pos, rank_gt, k_all = _ShardedInfoNCE.apply(q, src, self.memory, self)
+        with torch.no_grad():
+            self.index = self.compute.enqueue(self.memory, k_all, self.index, self.K, self.k_begin)
+        labels = torch.zeros(q.shape[0], dtype=torch.long, device=q.device)
+        return FusedLogits(loss, loss_rows, lse, pos, rank_gt, q.shape[0], self.K), labels
+
+    def gather_full_queue(self):
+        """The whole [K, d] queue in fp32 (checkpoint format of the reference, train...:278)."""
+        return _all_gather_rows(self.memory.float(), self.group)

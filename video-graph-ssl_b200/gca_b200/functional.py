@@ -1,0 +1,232 @@
+"""torch-facing wrappers of the C ABI: argument checks, output allocation, stream hand-off and the
+`torch.autograd.Function`s.  PyTorch is plumbing here (device memory, streams, autograd graph); every
+arithmetic step of the hot path runs inside libgca_b200.so.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GCA_BF16, GCA_F32, ptr
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gca_b200 ops run on CUDA tensors only (got a %s tensor); there is no CPU path" % t.device)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def queue_dtype_code(queue):
+    if queue.dtype == torch.float32:
+        return GCA_F32
+    if queue.dtype == torch.bfloat16:
+        return GCA_BF16
+    raise TypeError("queue must be float32 or bfloat16, got %s" % queue.dtype)
+
+
+_WS = {}
+
+
+def workspace(device, nbytes, tag="default"):
+    """Per-(device, tag) scratch buffer, grown on demand; never shrinks."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+# --------------------------------------------------------------------------------------------- queue
+def enqueue_(queue, keys, index, K_global=None, k_begin=0):
+    """In-place ring-buffer enqueue (mem_moco.py:17-27).  Returns the new pointer (mem_moco.py:14-15).
+
+    `queue` may be a K-shard holding global slots [k_begin, k_begin + len(queue)) of a ring of K_global."""
+    _need_cuda(queue, keys)
+    K_local, d = queue.shape
+    K_global = K_local if K_global is None else int(K_global)
+    if not queue.is_contiguous():
+        raise ValueError("queue must be contiguous")
+    keys = _f32c(keys.detach())
+    N = keys.shape[0]
+    if keys.shape[1] != d:
+        raise ValueError("keys have %d features, queue has %d" % (keys.shape[1], d))
+    _lib.call("gca_enqueue", ptr(queue), queue_dtype_code(queue), K_global, int(k_begin), int(k_begin) + K_local, d,
+              ptr(keys), N, int(index), _stream(queue))
+    return (int(index) + N) % K_global
+
+
+# --------------------------------------------------------------------------------------------- InfoNCE
+def infonce_workspace_bytes(B, K, d, queue_dtype, algo="auto"):
+    return int(_lib.load().gca_infonce_workspace_bytes(B, K, d, queue_dtype, _lib.ALGO[algo]))
+
+
+def infonce_forward(q, k, queue, T, algo="auto", want_grad=True, materialize=False):
+    """Raw fused head: returns dict(loss, loss_rows, lse, pos, rank, dq_unit | None, logits | None)."""
+    _need_cuda(q, k, queue)
+    q, k = _f32c(q.detach()), _f32c(k.detach())
+    B, d = q.shape
+    K = queue.shape[0]
+    dev = q.device
+    qd = queue_dtype_code(queue)
+    out = {
+        "loss": torch.empty((), dtype=torch.float32, device=dev),
+        "loss_rows": torch.empty(B, dtype=torch.float32, device=dev),
+        "lse": torch.empty(B, dtype=torch.float32, device=dev),
+        "pos": torch.empty(B, dtype=torch.float32, device=dev),
+        "rank": torch.empty(B, dtype=torch.int32, device=dev),
+        "dq_unit": torch.empty(B, d, dtype=torch.float32, device=dev) if want_grad else None,
+        "logits": torch.empty(B, K + 1, dtype=torch.float32, device=dev) if materialize else None,
+    }
+    ws = workspace(dev, infonce_workspace_bytes(B, K, d, qd, algo), "infonce")
+    _lib.call("gca_infonce_fwd", ptr(q), ptr(k), ptr(queue), qd, B, K, d, 1.0 / T, _lib.ALGO[algo],
+              ptr(out["loss"]), ptr(out["loss_rows"]), ptr(out["lse"]), ptr(out["pos"]), ptr(out["rank"]),
+              ptr(out["dq_unit"]), ptr(out["logits"]), ptr(ws), ws.numel(), _stream(q))
+    return out
+
+
+def infonce_backward_recompute(q, k, queue, T, lse, grad_scale, algo="auto"):
+    """Two-pass backward (gca_infonce_bwd): dq = grad_scale * d(sum_b loss_b)/dq against the given queue."""
+    _need_cuda(q, k, queue, lse)
+    q, k = _f32c(q.detach()), _f32c(k.detach())
+    B, d = q.shape
+    K = queue.shape[0]
+    qd = queue_dtype_code(queue)
+    dq = torch.empty(B, d, dtype=torch.float32, device=q.device)
+    ws = workspace(q.device, infonce_workspace_bytes(B, K, d, qd, algo), "infonce")
+    _lib.call("gca_infonce_bwd", ptr(q), ptr(k), ptr(queue), qd, B, K, d, 1.0 / T, _lib.ALGO[algo],
+              ptr(_f32c(lse)), float(grad_scale), ptr(dq), ptr(ws), ws.numel(), _stream(q))
+    return dq
+
+
+class _InfoNCEFused(torch.autograd.Function):
+    """loss (mean CE vs label 0), loss_rows, lse, pos, rank = f(q; k, queue).  Single pass: the unit gradient
+    d loss / d q is produced by the forward kernels, so backward is one multiply and never
+    re-reads the queue -- which the enqueue that follows the logits (mem_moco.py:82) is free to overwrite."""
+
+    @staticmethod
+    def forward(ctx, q, k, queue, T, algo):
+        want = ctx.needs_input_grad[0]
+        o = infonce_forward(q, k, queue, T, algo, want_grad=want)
+        ctx.B = q.shape[0]
+        ctx.in_dtype = q.dtype
+        if want:
+            ctx.save_for_backward(o["dq_unit"])
+        ctx.mark_non_differentiable(o["lse"], o["pos"], o["rank"])
+        return o["loss"], o["loss_rows"], o["lse"], o["pos"], o["rank"]
+
+    @staticmethod
+    def backward(ctx, g_loss, g_rows, *_):
+        (dq_unit,) = ctx.saved_tensors
+        dq = None
+        if g_loss is not None:
+            dq = dq_unit * g_loss
+        if g_rows is not None:                       # d loss_rows[b] / d q_b = B * dq_unit[b]
+            extra = dq_unit * (g_rows * float(ctx.B)).unsqueeze(1)
+            dq = extra if dq is None else dq + extra
+        if dq is not None and dq.dtype != ctx.in_dtype:
+            dq = dq.to(ctx.in_dtype)
+        return dq, None, None, None, None
+
+
+def infonce_fused(q, k, queue, T, algo="auto"):
+    return _InfoNCEFused.apply(q, k.detach(), queue, float(T), algo)
+
+
+# --------------------------------------------------------------------------------------------- graph head
+class _GraphCore(torch.autograd.Function):
+    """y = GCN-aggregate(resample(hop-weight(softmax(gq . gk)))) for one layer (temporal_graph.py:161-239)."""
+
+    @staticmethod
+    def forward(ctx, gq, gk, support, u, alpha, max_hop, temperature):
+        _need_cuda(gq, gk, support, u)
+        gq, gk, support, u = _f32c(gq), _f32c(gk), _f32c(support), _f32c(u)
+        B, Cq, T = gq.shape[:3]
+        S = gq[0, 0, 0].numel()
+        C = support.shape[1]
+        HW = support[0, 0, 0].numel()
+        dev = gq.device
+        sim = torch.empty(B, T, T, dtype=torch.float32, device=dev)
+        adj = torch.empty_like(sim)
+        s = torch.empty_like(sim)
+        y = torch.empty_like(support)
+        _lib.call("gca_graph_fwd", ptr(gq), ptr(gk), Cq, S, ptr(support), C, HW, T, B, ptr(u), float(alpha), int(max_hop),
+                  float(temperature), 0, ptr(sim), ptr(adj), ptr(s), ptr(y), _stream(gq))
+        ctx.save_for_backward(gq, gk, support, sim, adj, s)
+        ctx.cfg = (float(alpha), int(max_hop), float(temperature))
+        ctx.mark_non_differentiable(sim, adj, s)
+        return y, sim, adj, s
+
+    @staticmethod
+    def backward(ctx, dy, *_):
+        gq, gk, support, sim, adj, s = ctx.saved_tensors
+        alpha, max_hop, temperature = ctx.cfg
+        dy = _f32c(dy)
+        B, Cq, T = gq.shape[:3]
+        S = gq[0, 0, 0].numel()
+        C = support.shape[1]
+        HW = support[0, 0, 0].numel()
+        d_gq, d_gk, d_sup = torch.empty_like(gq), torch.empty_like(gk), torch.empty_like(support)
+        ws = workspace(gq.device, int(_lib.load().gca_graph_workspace_bytes(B, T)), "graph")
+        _lib.call("gca_graph_bwd", ptr(gq), ptr(gk), Cq, S, ptr(support), C, HW, T, B, ptr(sim), ptr(adj), ptr(s), ptr(dy),
+                  alpha, max_hop, temperature, 0, ptr(d_gq), ptr(d_gk), ptr(d_sup), ptr(ws), ws.numel(), _stream(gq))
+        return d_gq, d_gk, d_sup, None, None, None, None
+
+
+def graph_core(gq, gk, support, u, alpha=0.5, max_hop=3, temperature=1.0):
+    """gq, gk [B,Cq,T,...], support [B,C,T,...], u [B,T,T] -> (y like support, sim, adj, s)."""
+    return _GraphCore.apply(gq, gk, support, u, alpha, max_hop, temperature)
+
+
+# --------------------------------------------------------------------------------------------- SimSiam D
+class _NegCos(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, z):
+        _need_cuda(p, z)
+        ctx.in_dtype = p.dtype
+        ctx.shape = p.shape
+        p2, z2 = _f32c(p.detach()).reshape(-1, p.shape[-1]), _f32c(z.detach()).reshape(-1, z.shape[-1])
+        B, d = p2.shape
+        loss = torch.empty((), dtype=torch.float32, device=p.device)
+        want = ctx.needs_input_grad[0]
+        dp = torch.empty_like(p2) if want else None
+        ws = workspace(p.device, int(_lib.load().gca_negcos_workspace_bytes(B, d)), "negcos")
+        _lib.call("gca_negcos_fwd_bwd", ptr(p2), ptr(z2), B, d, ptr(loss), None, ptr(dp), ptr(ws), ws.numel(), _stream(p))
+        if want:
+            ctx.save_for_backward(dp)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dp,) = ctx.saved_tensors
+        return (dp * g).reshape(ctx.shape).to(ctx.in_dtype), None
+
+
+def neg_cosine(p, z):
+    """-mean cosine_similarity(p, stopgrad(z), dim=-1) (criterion.py:60)."""
+    return _NegCos.apply(p, z.detach())
+
+
+# --------------------------------------------------------------------------------------------- retrieval
+def cosine_topk(queries, gallery, k, normalize=True):
+    """Indices [Nq, k] (int32) and cosine similarities of the k nearest gallery rows of every query."""
+    _need_cuda(queries, gallery)
+    queries, gallery = _f32c(queries), _f32c(gallery)
+    Nq, d = queries.shape
+    Ng = gallery.shape[0]
+    idx = torch.empty(Nq, k, dtype=torch.int32, device=queries.device)
+    val = torch.empty(Nq, k, dtype=torch.float32, device=queries.device)
+    ws = workspace(queries.device, int(_lib.load().gca_sim_topk_workspace_bytes(Nq, Ng, d, k)), "topk")
+    _lib.call("gca_sim_topk", ptr(queries), ptr(gallery), Nq, Ng, d, k, 1 if normalize else 0, ptr(idx), ptr(val),
+              ptr(ws), ws.numel(), _stream(queries))
+    return idx, val

@@ -1,0 +1,43 @@
+"""Factories with the reference's signatures (lib/memory/build.py:5-32).
+
+Extra, optional config keys (absent keys keep upstream behaviour):
+  cfg.CONTRAST.QUEUE_DTYPE  'fp32' (default, parity mode) | 'bf16' (tcgen05 path)
+  cfg.CONTRAST.ALGO         'auto' | 'ffma' | 'tcgen05'
+"""
+from .moco_queue import RGBMoCo, CMCMoCo
+from .losses import NCESoftmaxLoss, D
+
+
+def _opt(node, name, default):
+    try:
+        return getattr(node, name)
+    except (AttributeError, KeyError):
+        return default
+
+
+def create_contrast(cfg, n_data):
+    if cfg.CONTRAST.MEM_TYPE == 'moco':
+        mem_func = RGBMoCo if cfg.CROSS.MODALITY == 'visual' else CMCMoCo
+        memory = mem_func(cfg.CROSS.FEAT_DIM, cfg.CONTRAST.NCE_K, cfg.CONTRAST.NCE_T,
+                          queue_dtype=_opt(cfg.CONTRAST, 'QUEUE_DTYPE', 'fp32'),
+                          algo=_opt(cfg.CONTRAST, 'ALGO', 'auto'))
+    elif cfg.CONTRAST.MEM_TYPE == 'simsiam':
+        memory = None
+    elif cfg.CONTRAST.MEM_TYPE == 'bank':
+        # NPID instance bank (lib/memory/mem_bank.py) is outside the hot path this package rebuilds
+        raise NotImplementedError("MEM_TYPE 'bank' is not provided by gca_b200; use the reference's lib.memory for it")
+    else:
+        raise NotImplementedError('mem not suported: {}'.format(cfg.CONTRAST.MEM_TYPE))
+    return memory
+
+
+def create_criterion(cfg, n_data):
+    if cfg.CROSS.CRITERION == 'crossentropy':
+        criterion = NCESoftmaxLoss()
+    elif cfg.CROSS.CRITERION == 'simsiam_d':
+        criterion = D()
+    elif cfg.CROSS.CRITERION == 'NCE':
+        raise NotImplementedError("criterion 'NCE' is not provided by gca_b200; use the reference's lib.memory for it")
+    else:
+        raise NotImplementedError('criterion not suported: {}'.format(cfg.CROSS.CRITERION))
+    return criterion

@@ -1,0 +1,35 @@
+"""Contrastive criteria behind the reference's interfaces (lib/memory/criterion.py:34-62)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import functional as GF
+from .moco_queue import FusedLogits
+
+
+class NCESoftmaxLoss(nn.Module):
+    """Softmax cross-entropy against label 0 (criterion.py:34-45).  Given the `FusedLogits` handle of the fused
+    head the loss has already been reduced inside the kernel; a real logits tensor takes the library path."""
+
+    def __init__(self):
+        super(NCESoftmaxLoss, self).__init__()
+
+    def forward(self, x):
+        if isinstance(x, FusedLogits):
+            return x.loss
+        label = torch.zeros(x.shape[0], dtype=torch.long, device=x.device)
+        return F.cross_entropy(x, label)
+
+
+class D(nn.Module):
+    """SimSiam negative cosine (criterion.py:47-62; duplicate at lib/modeling/graph_wrappers.py:93-108)."""
+
+    def __init__(self, fun_type='v2'):
+        super(D, self).__init__()
+        if fun_type not in ('v1', 'v2'):
+            raise NotImplementedError('Unknown type in simsiam D!')
+        self.fun_type = fun_type
+
+    def forward(self, logit, feat):
+        # v1 (normalise both, dot, mean) and v2 (cosine_similarity) are the same function; one fused kernel
+        return GF.neg_cosine(logit, feat.detach())
