@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: contrastive-head fwd+bwd steps/s at B=256, K=65536, d=128.
+
+One step = what the trainer does around the head (tools/train_video_contrast_dis.py:411-428): MoCo logits against the
+queue + InfoNCE loss + gradient w.r.t. q + top-1/top-5 of the positive + in-place enqueue of the gathered keys and
+pointer update.  Arms:
+  (default)          the B200 path: libgca_b200.so through gca_b200.GraphedMoCoStep (N=1) / ShardedRGBMoCo (N>1)
+  --impl reference   the reference's CPU implementation of the same step (oracle port; the reference is pure Python
+                     and does not exist on the GPU box), all host threads, rank 0 only
+Prints ONE JSON line (contract in the task statement): value = device-timed steps/s with inputs resident in HBM,
+e2e = same step from pinned HOST buffers with the H2D / D2H copies inside the timed region, roofline for the dominant
+kernel (infonce_tc_kernel) timed alone, cpu_baseline = the oracle port timed on this box's host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "video-graph-ssl_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "contrastive_head_fwd_bwd_steps_per_s"
+UNIT = "steps/s (1 step = fwd+bwd+top-k+enqueue of 256 query rows against the 65536 x 128 queue)"
+B, K, D, T = 256, 65536, 128, 0.07
+POOL = 8                                  # distinct input batches cycled through the timed steps
+L2_FLUSH_BYTES = 256 << 20                # > 126 MB L2
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(object):
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any("Active" == r[5 + i].strip() and "Not" not in r[5 + i] for r in rows)]
+        out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(rows[0][2]), reasons=reasons, samples=len(rows),
+                   power_w_max=max(float(r[3]) for r in rows))
+        return out
+
+
+def synthetic_batches(gen_seed, n, rows_q, rows_k, device=None, pin=False):
+    """POOL batches of L2-normalised rows, generated on the CPU with a fixed seed."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(gen_seed)
+    out = []
+    for _ in range(n):
+        packed = torch.cat([F.normalize(torch.randn(rows_q, D, generator=g)), F.normalize(torch.randn(rows_q, D, generator=g)),
+                            F.normalize(torch.randn(rows_k, D, generator=g))])
+        if pin:
+            packed = packed.pin_memory()
+        out.append(packed if device is None else packed.to(device))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- CPU (reference arm)
+def cpu_head_rate(steps, warmup, budget_s):
+    """The oracle port of the reference step on the host cores: fp32, all threads, same shapes."""
+    import torch
+    import torch.nn.functional as F
+    import oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(1)
+    mem = F.normalize(torch.randn(K, D, generator=g))
+    batches = synthetic_batches(2, 4, B, B)
+    idx, times = 0, []
+    t_start = time.perf_counter()
+    for i in range(warmup + steps):
+        pk = batches[i % len(batches)]
+        q = pk[:B].clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        _, _, idx, _ = oracle.infonce.reference_head_step(q, pk[B:2 * B], mem, idx, T, all_k=pk[2 * B:])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if i >= warmup + 2 and time.perf_counter() - t_start > budget_s:
+            break
+    mean = sum(times) / len(times)
+    return 1.0 / mean, mean * 1e3, len(times), torch.get_num_threads()
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = min(args.steps, 400)
+    rate, ms, n, cores = cpu_head_rate(steps, min(args.warmup, 5), budget_s=150.0)
+    sample = "%d full-size steps (B=%d, K=%d, d=%d, fp32) of the oracle port of the reference step, %s" % (n, B, K, D, cpu_model())
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 5),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "moco_head_B256_K65536_d128", "B": B, "K": K, "d": D, "T": T, "device": "cpu"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm, N = 1
+def run_single(args):
+    import torch
+    import torch.nn.functional as F
+    import gca_b200
+    from gca_b200 import _lib
+    from gca_b200.graphed import GraphedMoCoStep
+    from gca_b200 import functional as GF
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(1)
+    moco = gca_b200.RGBMoCo(D, K=K, T=T, queue_dtype="bf16").to(dev)
+    batches = synthetic_batches(2, POOL, B, B, device=dev)
+    state = torch.tensor([0, 0], dtype=torch.int64, device=dev)
+    steps_g = []
+    for i in range(POOL):                                  # one captured step per pool entry, shared queue + ring pointer
+        s = GraphedMoCoStep(moco, B, B, state=state)
+        s.inputs.copy_(batches[i])
+        steps_g.append(s)
+    for s in steps_g:
+        s.capture()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+
+    def one(i):
+        steps_g[i % POOL].step()
+
+    for i in range(args.warmup):
+        flush.fill_(i & 1)
+        one(i)
+    sampler = ClockSampler(0)
+    launches0 = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 1)                                 # L2 flush between timed iterations (not inside the events)
+        ev[i][0].record()
+        one(args.warmup + i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dev_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    ms_per_step = sum(dev_ms) / len(dev_ms)
+    launches = steps_g[0].launches_per_step * args.steps
+    loss_last = float(steps_g[(args.warmup + args.steps - 1) % POOL].loss)
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of loss/top-k/dq, synchronised every step
+    host_in = synthetic_batches(3, POOL, B, B, pin=True)
+    g0 = steps_g[0]
+    host_out = torch.empty_like(g0.outputs, device="cpu").pin_memory()
+    e2e_t = []
+    for i in range(args.warmup + args.steps):
+        flush.fill_(i & 1)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        g0.inputs.copy_(host_in[i % POOL], non_blocking=True)
+        g0.step()
+        host_out.copy_(g0.outputs, non_blocking=True)
+        torch.cuda.synchronize()
+        if i >= args.warmup:
+            e2e_t.append(time.perf_counter() - t1)
+    e2e_ms = sum(e2e_t) / len(e2e_t) * 1e3
+    h2d = g0.inputs.numel() * 4
+    d2h = g0.outputs.numel() * 4
+
+    # ---- dominant kernel alone (roofline): the queue-streaming tcgen05 kernel, cold L2
+    q, k = batches[0][:B].contiguous(), batches[0][B:2 * B].contiguous()
+    ws = GF.workspace(dev, GF.infonce_workspace_bytes(B, K, D, 1, "tcgen05"), "bench")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    kt = []
+    for i in range(60):
+        flush.fill_(i & 1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.call("gca_infonce_partials", _lib.ptr(q), _lib.ptr(k), _lib.ptr(moco.memory), 1, B, K, D, 1.0 / T, 2, 1,
+                  _lib.ptr(ws), ws.numel(), st)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 10:
+            kt.append(a.elapsed_time(b))
+    k_ms = sum(kt) / len(kt)
+    pk = peaks()
+    flops = 4.0 * B * K * D                                 # single pass: S = q Q^T and O += P Q
+    alg_bytes = K * D * 2 + 2 * B * D * 4 + 74 * B * (D + 3) * 4   # queue once + q,k + split partials written
+    t_tensor = flops / (pk["bf16_tflops"] * 1e12)
+    t_hbm = alg_bytes / (pk["hbm_gbs"] * 1e9)
+    ach_tf = flops / (k_ms * 1e-3) / 1e12
+    roof = {"bound": "tensor" if t_tensor >= t_hbm else "hbm", "achieved": ach_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": ach_tf / pk["bf16_tflops"], "traffic": None, "kernel": "infonce_tc_kernel<acc,online-max>", "kernel_ms": k_ms,
+            "alg_flops": flops, "alg_bytes": alg_bytes, "hbm_achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
+            "hbm_frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peaks": pk["source"] + ", burst bf16 (kernel timed alone)",
+            "l2": "flushed before every launch"}
+    prof = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roof["traffic"] = json.load(open(prof)).get("infonce_tc_kernel_dram_bytes")
+        except (ValueError, OSError):
+            pass
+
+    cpu_rate, cpu_ms, cpu_n, cores = cpu_head_rate(60, 2, budget_s=15.0) if not args.no_cpu else (None, None, 0, 0)
+    line = {
+        "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "moco_head_B256_K65536_d128", "B": B, "K": K, "d": D, "T": T, "queue_dtype": "bf16",
+                   "algo": "tcgen05 single-pass (loss + dq in one queue sweep)", "cuda_graph": True, "input_pool": POOL,
+                   "l2": "flushed between timed iterations (256 MiB write, outside the per-step events)",
+                   "timing": "per-step CUDA events on the launch stream; value = 1000 / mean(ms)"},
+        "ms_per_step_median": dev_ms[len(dev_ms) // 2], "wall_s_total": wall, "loss_last": loss_last,
+        "clocks": clocks,
+        "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "path": "pinned host q|k|all_k -> H2D -> GraphedMoCoStep (C ABI) -> D2H loss|top-k hits|dq, sync per step"},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": None if args.no_cpu else {
+            "value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": cpu_ms,
+            "sample": "%d full-size steps (B=%d, K=%d, d=%d, fp32) of the oracle port of the reference step, %s" % (cpu_n, B, K, D, cpu_model())},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm, N > 1
+def run_sharded(args, rank, world, local_rank):
+    """Weak scaling: 256 rows per GPU, the 65536-row queue sharded along K; per-shard partials merged with NCCL."""
+    import torch
+    import torch.distributed as dist
+    import gca_b200
+    from gca_b200 import _lib
+    from gca_b200.dist import ShardedRGBMoCo
+    lib = _lib.load()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1)
+    moco = ShardedRGBMoCo(D, K=K, T=T, queue_dtype="bf16", device=dev)
+    crit = gca_b200.NCESoftmaxLoss()
+    batches = synthetic_batches(100 + rank, POOL, B, 0, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def one(i):
+        pk = batches[i % POOL]
+        q = pk[:B].clone().requires_grad_(True)
+        out, labels = moco(q, pk[B:2 * B])
+        loss = crit(out)
+        loss.backward()
+        hits = ((out.rank < 1).sum(), (out.rank < 5).sum())
+        return loss, q.grad, hits
+
+    for i in range(args.warmup):
+        flush.fill_(i & 1)
+        one(i)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    n0 = lib.gca_launch_count()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 1)
+        ev[i][0].record()
+        loss, _, _ = one(args.warmup + i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = time.perf_counter() - t0
+    launches = int(lib.gca_launch_count() - n0)
+    clocks = sampler.stop() if sampler else None
+    tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev)
+    dist.all_reduce(tot, op=dist.ReduceOp.MAX)              # max over ranks of the device-timed total
+    ms_per_step = float(tot) / args.steps
+    # end to end: host q, k per rank -> H2D -> step -> D2H loss + dq, synchronised per step
+    host_in = synthetic_batches(200 + rank, POOL, B, 0, pin=True)
+    dev_in = torch.empty_like(batches[0])
+    e2e_t = []
+    for i in range(args.warmup + args.steps):
+        flush.fill_(i & 1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t1 = time.perf_counter()
+        dev_in.copy_(host_in[i % POOL], non_blocking=True)
+        q = dev_in[:B].clone().requires_grad_(True)
+        out, _ = moco(q, dev_in[B:2 * B])
+        l = crit(out)
+        l.backward()
+        res = (l.detach().cpu(), q.grad.cpu())
+        torch.cuda.synchronize()
+        if i >= args.warmup:
+            e2e_t.append(time.perf_counter() - t1)
+    e2e = torch.tensor([sum(e2e_t) / len(e2e_t) * 1e3], device=dev)
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": world * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "moco_head_B256perGPU_K65536sharded_d128", "B_per_gpu": B, "B_global": B * world, "K": K, "d": D,
+                       "T": T, "queue_dtype": "bf16", "parallelism": "queue sharded along K over %d ranks; NCCL all-gather of q,k and "
+                       "of the (max,sum,count) partials, reduce-scatter of the gradient accumulator" % world,
+                       "cuda_graph": False, "l2": "flushed between timed iterations (256 MiB write, outside the per-step events)",
+                       "timing": "per-step CUDA events, total = max over ranks; value = n_gpus * 1000 / ms_per_step "
+                                 "(each global step processes n_gpus x 256 rows)"},
+            "wall_s_total": wall, "loss_last": float(loss), "clocks": clocks,
+            "e2e": {"value": world * 1e3 / float(e2e), "unit": UNIT, "h2d_bytes_per_step": 2 * B * D * 4, "d2h_bytes_per_step": B * D * 4 + 4,
+                    "ms_per_step": float(e2e)},
+            "gpu_launches": launches,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if world > 1:
+        return run_sharded(args, rank, world, local_rank)
+    if args.gpus > 1:
+        print("bench.py --gpus %d must be launched with torch.distributed.run (one rank per GPU)" % args.gpus, file=sys.stderr)
+        sys.exit(2)
+    return run_single(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -80,6 +80,8 @@ int gca_enqueue_devptr(void* queue, int dtype_queue, long long K_global, long lo
  *   outputs     : loss_mean[1]   = mean_b (lse_b - pos_b)                   (criterion.py:44)
  *                 loss_rows[B], lse[B] (log-sum-exp over the K+1 logits), pos_logit[B] = q_b.k_b / T
  *                 rank_gt[B]     = number of negatives STRICTLY greater than the positive (top-k hit <=> < k)
+ *                 top_hits[2]    = #rows with rank_gt < 1, #rows with rank_gt < 5 (the counts behind
+ *                                  accuracy(topk=(1,5)), train_video_contrast_dis.py:428); may be NULL
  *                 dq_unit[B, d]  = d loss_mean / d q (may be NULL: forward only)
  *                 logits_out     = [B, K+1] fp32 materialised logits (may be NULL; FFMA algo only)
  *   workspace   : gca_infonce_workspace_bytes(...) bytes of scratch
@@ -89,7 +91,7 @@ size_t gca_infonce_workspace_bytes(int B, long long K, int d, int dtype_queue, i
 
 int gca_infonce_fwd(const float* q, const float* k, const void* queue, int dtype_queue,
                     int B, long long K, int d, float inv_T, int algo,
-                    float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt,
+                    float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt, int* top_hits,
                     float* dq_unit, float* logits_out,
                     void* workspace, size_t workspace_bytes, void* stream);
 

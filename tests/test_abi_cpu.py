@@ -57,7 +57,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.gca_enqueue(null, 0, 16, 0, 16, 8, one, 1, 0, null) == -1
     assert lib.gca_enqueue(one, 0, 16, 0, 16, 8, one, 0, 0, null) == 0              # empty enqueue is a no-op
     # infonce: unsupported shapes are reported, not silently rerouted
-    args = [one, one, one, 1, 4, 64, 100, 1.0, 1] + [one] * 7 + [one, 1 << 20, null]
+    args = [one, one, one, 1, 4, 64, 100, 1.0, 1] + [one] * 8 + [one, 1 << 20, null]
     assert lib.gca_infonce_fwd(*args) == -2                                         # ffma: d % 32
     args[6] = 64
     args[8] = 2

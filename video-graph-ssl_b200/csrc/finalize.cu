@@ -105,10 +105,23 @@ infonce_finalize_kernel(const FinalizeParams F)
         }
     }
 
-    if (kMode == FIN_FULL && F.loss_mean != nullptr) {
+    if (kMode == FIN_FULL && (F.loss_mean != nullptr || F.top_hits != nullptr)) {
         if (last_block_ticket(F.counter, gridDim.x, &flag)) {
             const float mean = block_mean_fixed(F.loss_rows, F.B, red);
-            if (tid == 0) { *F.loss_mean = mean; *F.counter = 0u; }
+            int h1 = 0, h5 = 0;                                   // integer counts: exact, order-independent
+            for (int i = tid; i < F.B; i += FIN_THREADS) { const int r = __ldcg(F.rank_gt + i); h1 += (r < 1); h5 += (r < 5); }
+            h1 = warp_sum_i(h1); h5 = warp_sum_i(h5);
+            __shared__ int hit_s[2][FIN_THREADS / 32];
+            if ((tid & 31) == 0) { hit_s[0][tid >> 5] = h1; hit_s[1][tid >> 5] = h5; }
+            __syncthreads();
+            if (tid == 0) {
+                if (F.loss_mean) *F.loss_mean = mean;
+                if (F.top_hits) {
+                    F.top_hits[0] = hit_s[0][0] + hit_s[0][1] + hit_s[0][2] + hit_s[0][3];
+                    F.top_hits[1] = hit_s[1][0] + hit_s[1][1] + hit_s[1][2] + hit_s[1][3];
+                }
+                *F.counter = 0u;
+            }
         }
     }
 }

@@ -139,7 +139,7 @@ extern "C" size_t gca_infonce_workspace_bytes(int B, long long K, int d, int dty
 
 extern "C" int gca_infonce_fwd(const float* q, const float* k, const void* queue, int dtype_queue, int B, long long K,
                                int d, float inv_T, int algo, float* loss_mean, float* loss_rows, float* lse,
-                               float* pos_logit, int* rank_gt, float* dq_unit, float* logits_out, void* workspace,
+                               float* pos_logit, int* rank_gt, int* top_hits, float* dq_unit, float* logits_out, void* workspace,
                                size_t workspace_bytes, void* stream)
 {
     using namespace gca;
@@ -155,7 +155,7 @@ extern "C" int gca_infonce_fwd(const float* q, const float* k, const void* queue
     F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
     F.part_acc = dq_unit ? ws.part_acc : nullptr;
     F.nsplit = ws.nsplit; F.Bpad = ws.Bpad; F.B = B; F.d = d; F.inv_T = inv_T; F.k = k; F.pos = pos_logit;
-    F.lse = lse; F.loss_rows = loss_rows; F.rank_gt = rank_gt; F.dq = dq_unit; F.loss_mean = loss_mean;
+    F.lse = lse; F.loss_rows = loss_rows; F.rank_gt = rank_gt; F.dq = dq_unit; F.loss_mean = loss_mean; F.top_hits = top_hits;
     return infonce_finalize_launch(F, FIN_FULL, st);
 }
 

@@ -47,6 +47,7 @@ struct FinalizeParams {
     float grad_scale;        // FIN_BWD
     // outputs
     float* lse; float* loss_rows; int* rank_gt; float* dq; float* loss_mean;     // FIN_FULL / FIN_BWD (dq)
+    int* top_hits;                                                               // FIN_FULL: [2] rows with rank < 1, < 5
     float* out_max; float* out_sum; int* out_cnt; float* out_acc;                // FIN_SHARD
 };
 int infonce_finalize_launch(const FinalizeParams& F, int mode, cudaStream_t st);

@@ -40,7 +40,7 @@ SIGNATURES = {
                             c_void_p]),
     "gca_infonce_workspace_bytes": (c_size_t, [c_int, c_longlong, c_int, c_int, c_int]),
     "gca_infonce_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_size_t, c_void_p]),
     "gca_infonce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
                                 c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),

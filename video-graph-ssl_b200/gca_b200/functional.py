@@ -85,12 +85,13 @@ def infonce_forward(q, k, queue, T, algo="auto", want_grad=True, materialize=Fal
         "lse": torch.empty(B, dtype=torch.float32, device=dev),
         "pos": torch.empty(B, dtype=torch.float32, device=dev),
         "rank": torch.empty(B, dtype=torch.int32, device=dev),
+        "hits": torch.empty(2, dtype=torch.int32, device=dev),
         "dq_unit": torch.empty(B, d, dtype=torch.float32, device=dev) if want_grad else None,
         "logits": torch.empty(B, K + 1, dtype=torch.float32, device=dev) if materialize else None,
     }
     ws = workspace(dev, infonce_workspace_bytes(B, K, d, qd, algo), "infonce")
     _lib.call("gca_infonce_fwd", ptr(q), ptr(k), ptr(queue), qd, B, K, d, 1.0 / T, _lib.ALGO[algo],
-              ptr(out["loss"]), ptr(out["loss_rows"]), ptr(out["lse"]), ptr(out["pos"]), ptr(out["rank"]),
+              ptr(out["loss"]), ptr(out["loss_rows"]), ptr(out["lse"]), ptr(out["pos"]), ptr(out["rank"]), ptr(out["hits"]),
               ptr(out["dq_unit"]), ptr(out["logits"]), ptr(ws), ws.numel(), _stream(q))
     return out
 
