@@ -95,6 +95,15 @@ int gca_infonce_fwd(const float* q, const float* k, const void* queue, int dtype
                     float* dq_unit, float* logits_out,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* One whole trainer-side head step in two launches: gca_infonce_fwd followed by the enqueue of `enqueue_keys[N, d]`
+ * into the SAME queue (RGBMoCo.forward, mem_moco.py:60-88: logits from the queue as it was, then _update_memory, then
+ * _update_pointer), the enqueue riding in the finalize launch.  Pointer: `state` == NULL -> `index` (host value, the
+ * caller advances its copy); `state` != NULL -> device-resident {pointer, ticket} as in gca_enqueue_devptr. */
+int gca_moco_step(const float* q, const float* k, void* queue, int dtype_queue, int B, long long K, int d, float inv_T,
+                  int algo, const float* enqueue_keys, int N, long long index, long long* state,
+                  float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt, int* top_hits,
+                  float* dq_unit, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Stage 1 of gca_infonce_fwd on its own: only the queue-streaming kernel, leaving the per-split partials in the
  * workspace (layout: csrc/gca_common.cuh).  For profiling / roofline timing of the dominant kernel. */
 int gca_infonce_partials(const float* q, const float* k, const void* queue, int dtype_queue,

@@ -502,3 +502,34 @@ def test_headline_shape_full_size(GF):
         moco(cu(unit_rows(256, 128, gen)), cu(kk))
         idx = oracle.enqueue(ref_mem, kk, idx)
     assert moco.index == idx == 512 and torch.equal(moco.memory.cpu(), ref_mem)
+
+
+# ============================================================================================ captured step (CUDA graph)
+@pytest.mark.parametrize("queue_dtype,B,N,K", [("bf16", 64, 64, 1024), ("fp32", 32, 48, 256), ("bf16", 256, 256, 4096)])
+def test_graphed_step_matches_oracle_over_a_lap(lib, queue_dtype, B, N, K):
+    """gca_moco_step replayed from a CUDA graph: loss, gradient, top-k hits, queue contents and the device-resident ring
+    pointer after enough steps to wrap the ring (integer state bit-exact against the oracle)."""
+    import gca_b200
+    from gca_b200.graphed import GraphedMoCoStep
+    gen = torch.Generator().manual_seed(B + N + K)
+    moco = gca_b200.RGBMoCo(128, K=K, T=0.07, queue_dtype=queue_dtype).cuda()
+    moco.index = K - N - 5                                   # the second step wraps
+    ref_mem = moco.memory.cpu().clone()
+    idx = moco.index
+    step = GraphedMoCoStep(moco, B, N).capture()
+    assert step.launches_per_step == 2                       # streaming kernel + finalize(with the enqueue riding in it)
+    for it in range(K // N + 3):
+        q, k, all_k = unit_rows(B, 128, gen), unit_rows(B, 128, gen), unit_rows(N, 128, gen)
+        loss = step.step(cu(q), cu(k), cu(all_k))
+        rq = bf16r(q) if queue_dtype == "bf16" else q
+        o = oracle.infonce_step(rq.double(), k.double(), ref_mem.double(), 0, 0.07)
+        idx = oracle.enqueue(ref_mem, all_k, idx)
+        tol = LOSS_RTOL_BF16 if queue_dtype == "bf16" else LOSS_RTOL_FP32
+        assert abs(float(loss) - float(o["loss"])) <= tol * abs(float(o["loss"]))
+        assert rel_max(step.dq, o["dq"]) <= GRAD_RTOL
+        hits = step.hits.cpu().tolist()
+        assert hits[0] <= hits[1] <= B
+        assert moco.index == idx
+    torch.cuda.synchronize()
+    assert int(step.state[0]) == idx and int(step.state[1]) == 0           # device pointer == host pointer == oracle
+    assert torch.equal(moco.memory.cpu(), ref_mem)                          # slot contents: exact

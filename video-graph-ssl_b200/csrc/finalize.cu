@@ -6,7 +6,9 @@
 
 namespace gca {
 
-constexpr int FIN_THREADS = 128;
+constexpr int FIN_THREADS = 512;
+constexpr int FIN_COLS = 128;                 // feature columns per slab
+constexpr int FIN_GROUPS = FIN_THREADS / FIN_COLS;
 constexpr int FIN_MAX_SPLITS = 1024;
 
 // last-block ticket: returns true in exactly one block, after every other block's global writes are visible
@@ -32,14 +34,63 @@ __device__ __forceinline__ float block_mean_fixed(const float* rows, int n, floa
     return block_sum<FIN_THREADS>(a, red) / (float)n;
 }
 
+// Optional fused tail of the step: the ring-buffer enqueue (mem_moco.py:17-27) rides in extra CTAs of the finalize
+// launch -- legal because the launch is stream-ordered after the queue-streaming kernel, the only reader of the queue.
+template <typename QT>
+__device__ __forceinline__ void enqueue_rows(const FinalizeParams& F, int blk, int nblk)
+{
+    QT* queue = reinterpret_cast<QT*>(F.enq_queue);
+    long long index = F.enq_state ? *reinterpret_cast<volatile long long*>(F.enq_state) : F.enq_index;
+    const int d4 = F.d / 4;
+    const long long total = (long long)F.enq_N * d4;
+    const float4* keys = reinterpret_cast<const float4*>(F.enq_keys);
+    for (long long i = (long long)blk * FIN_THREADS + threadIdx.x; i < total; i += (long long)nblk * FIN_THREADS) {
+        const int row = (int)(i / d4), c4 = (int)(i - (long long)row * d4);
+        long long slot = index + row;
+        if (slot >= F.enq_K) slot -= F.enq_K;
+        const float4 v = __ldg(keys + i);
+        const long long off = slot * d4 + c4;
+        if constexpr (sizeof(QT) == 4) {
+            reinterpret_cast<float4*>(queue)[off] = v;
+        } else {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(queue)[off] = pk;
+        }
+    }
+    if (F.enq_state) {                                        // device-resident pointer: the last enqueue CTA advances it
+        __shared__ int last;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            last = (atomicAdd(reinterpret_cast<unsigned long long*>(F.enq_state + 1), 1ull) == (unsigned long long)(nblk - 1));
+        __syncthreads();
+        if (last && threadIdx.x == 0) {
+            long long nx = index + F.enq_N;
+            if (nx >= F.enq_K) nx -= F.enq_K;
+            F.enq_state[0] = nx;
+            F.enq_state[1] = 0;
+        }
+    }
+}
+
 template <int kMode>
 __global__ void __launch_bounds__(FIN_THREADS)
 infonce_finalize_kernel(const FinalizeParams F)
 {
     __shared__ float w_s[FIN_MAX_SPLITS];
     __shared__ float red[FIN_THREADS / 32];
+    __shared__ int   cnt_s[FIN_THREADS / 32];
+    __shared__ float colsum[FIN_GROUPS][FIN_COLS];
     __shared__ int   flag;
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
+    if (kMode == FIN_FULL && (int)blockIdx.x >= F.B) {        // fused enqueue CTAs
+        if (F.enq_dtype == GCA_F32) enqueue_rows<float>(F, blockIdx.x - F.B, gridDim.x - F.B);
+        else                        enqueue_rows<__nv_bfloat16>(F, blockIdx.x - F.B, gridDim.x - F.B);
+        return;
+    }
+    const int b = blockIdx.x;
     const int ns = F.nsplit;
 
     float lse = 0.f, pos = 0.f;
@@ -53,7 +104,9 @@ infonce_finalize_kernel(const FinalizeParams F)
         m = warp_max(m);
         if ((tid & 31) == 0) red[tid >> 5] = m;
         __syncthreads();
-        m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+        m = red[0];
+#pragma unroll
+        for (int w = 1; w < FIN_THREADS / 32; ++w) m = fmaxf(m, red[w]);
         __syncthreads();
         if (kMode == FIN_FULL) { pos = F.pos[b]; m = fmaxf(m, pos); }
         float part = 0.f;
@@ -68,10 +121,11 @@ infonce_finalize_kernel(const FinalizeParams F)
         }
         float S = block_sum<FIN_THREADS>(part, red);
         cnt = warp_sum_i(cnt);
-        __shared__ int cnt_s[FIN_THREADS / 32];
         if ((tid & 31) == 0) cnt_s[tid >> 5] = cnt;
         __syncthreads();
-        cnt = cnt_s[0] + cnt_s[1] + cnt_s[2] + cnt_s[3];
+        cnt = 0;
+#pragma unroll
+        for (int w = 0; w < FIN_THREADS / 32; ++w) cnt += cnt_s[w];
         if (kMode == FIN_FULL) {
             S += __expf(pos - m);
             lse = m + logf(S);
@@ -88,25 +142,41 @@ infonce_finalize_kernel(const FinalizeParams F)
         __syncthreads();
     }
 
-    // gradient accumulator: fixed-order sum over splits, one feature column per thread
+    // Gradient accumulator.  FIN_GROUPS thread groups take interleaved splits of one column slab (many independent
+    // loads in flight), then the groups are added in a fixed order: deterministic for a given split count.
     float* out = (kMode == FIN_SHARD) ? F.out_acc : F.dq;
     if (out != nullptr && F.part_acc != nullptr) {
         const float p0m1 = (kMode == FIN_SHARD) ? 0.f : (__expf(pos - lse) - 1.f);
         const float scale = (kMode == FIN_FULL) ? F.inv_T / (float)F.B
                           : (kMode == FIN_BWD)  ? F.inv_T * F.grad_scale : 1.f;
-        for (int c = tid; c < F.d; c += FIN_THREADS) {
+        const int grp = tid / FIN_COLS, col = tid % FIN_COLS;
+        const size_t stride = (size_t)F.Bpad * F.d;
+        for (int c0 = 0; c0 < F.d; c0 += FIN_COLS) {
+            const int c = c0 + col;
             float a = 0.f;
-            const float* src = F.part_acc + (size_t)b * F.d + c;
-            const size_t stride = (size_t)F.Bpad * F.d;
-            if (kMode == FIN_BWD) { for (int s = 0; s < ns; ++s) a += __ldcg(src + s * stride); }
-            else                  { for (int s = 0; s < ns; ++s) a = fmaf(w_s[s], __ldcg(src + s * stride), a); }
-            if (kMode != FIN_SHARD) a = scale * fmaf(p0m1, F.k[(size_t)b * F.d + c], a);
-            out[(size_t)b * F.d + c] = a;
+            if (c < F.d) {
+                const float* src = F.part_acc + (size_t)b * F.d + c;
+#pragma unroll 8
+                for (int s = grp; s < ns; s += FIN_GROUPS) {
+                    const float v = __ldcg(src + s * stride);
+                    a = (kMode == FIN_BWD) ? a + v : fmaf(w_s[s], v, a);
+                }
+            }
+            colsum[grp][col] = a;
+            __syncthreads();
+            if (grp == 0 && c < F.d) {
+                float t = colsum[0][col];
+#pragma unroll
+                for (int g = 1; g < FIN_GROUPS; ++g) t += colsum[g][col];
+                if (kMode != FIN_SHARD) t = scale * fmaf(p0m1, F.k[(size_t)b * F.d + c], t);
+                out[(size_t)b * F.d + c] = t;
+            }
+            __syncthreads();
         }
     }
 
     if (kMode == FIN_FULL && (F.loss_mean != nullptr || F.top_hits != nullptr)) {
-        if (last_block_ticket(F.counter, gridDim.x, &flag)) {
+        if (last_block_ticket(F.counter, (unsigned int)F.B, &flag)) {
             const float mean = block_mean_fixed(F.loss_rows, F.B, red);
             int h1 = 0, h5 = 0;                                   // integer counts: exact, order-independent
             for (int i = tid; i < F.B; i += FIN_THREADS) { const int r = __ldcg(F.rank_gt + i); h1 += (r < 1); h5 += (r < 5); }
@@ -115,11 +185,10 @@ infonce_finalize_kernel(const FinalizeParams F)
             if ((tid & 31) == 0) { hit_s[0][tid >> 5] = h1; hit_s[1][tid >> 5] = h5; }
             __syncthreads();
             if (tid == 0) {
+                int t1 = 0, t5 = 0;
+                for (int w = 0; w < FIN_THREADS / 32; ++w) { t1 += hit_s[0][w]; t5 += hit_s[1][w]; }
                 if (F.loss_mean) *F.loss_mean = mean;
-                if (F.top_hits) {
-                    F.top_hits[0] = hit_s[0][0] + hit_s[0][1] + hit_s[0][2] + hit_s[0][3];
-                    F.top_hits[1] = hit_s[1][0] + hit_s[1][1] + hit_s[1][2] + hit_s[1][3];
-                }
+                if (F.top_hits) { F.top_hits[0] = t1; F.top_hits[1] = t5; }
                 *F.counter = 0u;
             }
         }
@@ -129,7 +198,12 @@ infonce_finalize_kernel(const FinalizeParams F)
 int infonce_finalize_launch(const FinalizeParams& F, int mode, cudaStream_t st)
 {
     if (F.nsplit > FIN_MAX_SPLITS) return set_err(GCA_ERR_UNSUPPORTED, "finalize: %d splits > %d", F.nsplit, FIN_MAX_SPLITS);
-    if (mode == FIN_FULL)       infonce_finalize_kernel<FIN_FULL><<<F.B, FIN_THREADS, 0, st>>>(F);
+    int enq_blocks = 0;
+    if (mode == FIN_FULL && F.enq_queue != nullptr && F.enq_N > 0) {
+        enq_blocks = (int)(((long long)F.enq_N * (F.d / 4) + FIN_THREADS - 1) / FIN_THREADS);
+        if (enq_blocks > 64) enq_blocks = 64;
+    }
+    if (mode == FIN_FULL)       infonce_finalize_kernel<FIN_FULL><<<F.B + enq_blocks, FIN_THREADS, 0, st>>>(F);
     else if (mode == FIN_SHARD) infonce_finalize_kernel<FIN_SHARD><<<F.B, FIN_THREADS, 0, st>>>(F);
     else                        infonce_finalize_kernel<FIN_BWD><<<F.B, FIN_THREADS, 0, st>>>(F);
     GCA_LAUNCH_CHECK("infonce_finalize_kernel");

@@ -49,6 +49,9 @@ struct FinalizeParams {
     float* lse; float* loss_rows; int* rank_gt; float* dq; float* loss_mean;     // FIN_FULL / FIN_BWD (dq)
     int* top_hits;                                                               // FIN_FULL: [2] rows with rank < 1, < 5
     float* out_max; float* out_sum; int* out_cnt; float* out_acc;                // FIN_SHARD
+    // optional fused enqueue (FIN_FULL): keys [enq_N, d] into the full ring queue [enq_K, d]
+    void* enq_queue; int enq_dtype; long long enq_K; const float* enq_keys; int enq_N;
+    long long enq_index; long long* enq_state;
 };
 int infonce_finalize_launch(const FinalizeParams& F, int mode, cudaStream_t st);
 

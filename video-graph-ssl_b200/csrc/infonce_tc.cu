@@ -2,11 +2,11 @@
 //
 // One CTA = 128 query rows x a contiguous range of 128-key queue tiles; grid = (K-splits, row blocks) ~ one CTA/SM.
 // It is a flash-attention forward whose keys and values are the same queue tile:
-//     S = q Q^T        tcgen05.mma, A = q (bf16, resident in TMEM), B = queue tile in smem, K-major
+//     S = q Q^T        tcgen05.mma, A = q (bf16 smem tile), B = queue tile in smem, both K-major
 //     p = 2^(S c - m)  one thread per query row, online max with lazy rescale, row sum, rank count
 //     O += P Q         tcgen05.mma, A = P (bf16, written back over S in TMEM), B = the SAME smem tile, MN-major
 // so a queue tile is fetched once (TMA, 128-byte swizzle, 4-stage mbarrier ring) and the [B, K] logits never
-// leave the SM.  Warp roles: warps 0-3 softmax (TMEM lane quarter = warp), warp 4 TMA producer, warp 5 MMA
+// leave the SM.  q is converted once per CTA into a swizzled smem tile (A operand).  Warp roles: warps 0-3 softmax (TMEM lane quarter = warp), warp 4 TMA producer, warp 5 MMA
 // issuer + TMEM allocator.  Per-split partials (max, sum, count, O) go to the workspace; finalize.cu merges them
 // in a fixed order.  Replaces mem_moco.py:36-46 + criterion.py:44 + autograd(mm) of the reference.
 #include "gca_common.cuh"
@@ -22,9 +22,12 @@ constexpr int TC_STAGE_BYTES = TC_BN * TC_D * 2;          // 32 KB: two [128 key
 constexpr int TC_HALF_BYTES = TC_STAGE_BYTES / 2;
 constexpr int TC_THREADS = 192;
 constexpr uint32_t TM_COLS = 512;
-constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O = 256, TM_Q = 384;   // TMEM column map (fp32 S x2, fp32 O, bf16 q)
+constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O = 256;   // TMEM column map (fp32 S double buffer, fp32 O)
 constexpr float TC_RESCALE_LOG2 = 8.f;                    // rescale O only when the row max grows by > 2^8
-constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 256;
+constexpr int TC_OST_STRIDE = 132;                        // fp32 O staging row (128 + 4 floats): conflict-free row writes
+constexpr size_t TC_QTILE_BYTES = (size_t)TC_BM * TC_D * 2;   // bf16 q block, same swizzled layout as a queue tile
+constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + TC_QTILE_BYTES + 512;
+static_assert((size_t)TC_BM * TC_OST_STRIDE * 4 <= (size_t)TC_STAGES * TC_STAGE_BYTES, "O staging must fit in the tile ring");
 
 struct TcDebug { uint32_t lbo1, sbo1, kstep1, lbo2, sbo2, kstep2; };
 
@@ -35,7 +38,7 @@ struct TcBarriers {
     uint64_t p_full[2];           // softmax finished with S (and wrote P)
     uint64_t o_done;              // one phase per completed O += P Q
     uint64_t acc_final;           // last O += P Q completed
-    uint64_t q_ready;             // q rows are in TMEM
+    uint64_t q_ready;             // the bf16 q block is in shared memory (A operand of S = q Q^T)
     uint32_t tmem_base;
 };
 
@@ -44,12 +47,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const InfoNceStreamParams P, const TcDebug dbg)
 {
     using namespace ptx;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    TcBarriers* bar = reinterpret_cast<TcBarriers*>(stages + (size_t)TC_STAGES * TC_STAGE_BYTES);
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, row0 = blockIdx.y * TC_BM;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* qtile = stages + (size_t)TC_STAGES * TC_STAGE_BYTES;         // bf16 q block, two swizzled [128][64] boxes
+    TcBarriers* bar = reinterpret_cast<TcBarriers*>(qtile + TC_QTILE_BYTES);
+    const int nrows = (P.B - row0 < TC_BM) ? (P.B - row0) : TC_BM;        // valid query rows of this block
+
     const long long ntiles = (P.K + TC_BN - 1) / TC_BN;
     const long long t_begin = ntiles * split / P.nsplit, t_end = ntiles * (split + 1) / P.nsplit;
     const int n = (int)(t_end - t_begin);
@@ -78,26 +83,36 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const InfoNceStreamP
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
         const float c2 = P.inv_T * 1.4426950408889634f;                 // logits -> log2 domain
 
-        // q row -> bf16 -> TMEM (A operand of S = q Q^T); positive logit in fp32 on the way
+        // Prologue.  Each warp converts ITS 32 query rows with coalesced 128-bit loads (lane = 4 features): the
+        // positive logit q.k in fp32 (fixed shuffle order: every split computes the same bits) and q -> bf16 written in
+        // the 128-byte-swizzled K-major layout of a queue tile, so S = q Q^T is a plain smem x smem tcgen05.mma.
         float pos_dot = 0.f;
         {
-            const float4* qr = reinterpret_cast<const float4*>(P.q + (size_t)row * TC_D);
-            const float4* kr = reinterpret_cast<const float4*>(P.k + (size_t)row * TC_D);
+            const float4* qg = reinterpret_cast<const float4*>(P.q + (size_t)row0 * TC_D);
+            const float4* kg = reinterpret_cast<const float4*>(P.k + (size_t)row0 * TC_D);
+            const int sub = lane >> 4, chunk = (lane & 15) >> 1, half = lane & 1;    // 64-feature box, 16-byte chunk, 8-byte half
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t pk[32];
+            for (int batch = 0; batch < 2; ++batch) {
+                float4 a[16], b[16];
 #pragma unroll
-                for (int v = 0; v < 16; ++v) {
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                    if (valid) { a = __ldg(qr + h * 16 + v); b = __ldg(kr + h * 16 + v); }
-                    pos_dot = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, pos_dot))));
-                    pk[2 * v] = pack_bf16(a.x, a.y);
-                    pk[2 * v + 1] = pack_bf16(a.z, a.w);
+                for (int u = 0; u < 16; ++u) {
+                    const int r = warp * 32 + batch * 16 + u;
+                    a[u] = make_float4(0.f, 0.f, 0.f, 0.f); b[u] = a[u];
+                    if (r < nrows) { a[u] = __ldg(qg + r * 32 + lane); b[u] = __ldg(kg + r * 32 + lane); }
                 }
-                tmem_st32(lane_addr + TM_Q + h * 32, pk);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int r = warp * 32 + batch * 16 + u;
+                    float dsum = fmaf(a[u].x, b[u].x, fmaf(a[u].y, b[u].y, fmaf(a[u].z, b[u].z, a[u].w * b[u].w)));
+                    dsum = warp_sum(dsum);
+                    if (lane == batch * 16 + u) pos_dot = dsum;
+                    uint2 pk2;
+                    pk2.x = pack_bf16(a[u].x, a[u].y);
+                    pk2.y = pack_bf16(a[u].z, a[u].w);
+                    *reinterpret_cast<uint2*>(qtile + sub * TC_HALF_BYTES + r * 128 + ((chunk ^ (r & 7)) << 4) + half * 8) = pk2;
+                }
             }
-            tc_wait_st();
-            tc_fence_before();
+            fence_proxy_async();                               // generic-proxy smem writes -> visible to the tensor core
             mbar_arrive(&bar->q_ready);
         }
         const float pos_nat = pos_dot * P.inv_T;
@@ -135,7 +150,11 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const InfoNceStreamP
             float tmax = -INFINITY;
             int c = 0;
 #pragma unroll
-            for (int j = 0; j < TC_BN; ++j) { tmax = fmaxf(tmax, sv[j]); c += (sv[j] > pos_dot) ? 1 : 0; }
+            for (int j = 0; j < TC_BN; j += 2) {
+                tmax = max3(tmax, sv[j], sv[j + 1]);
+                c += (sv[j] > pos_dot) ? 1 : 0;
+                c += (sv[j + 1] > pos_dot) ? 1 : 0;
+            }
             cnt += c;
 
             if (!kFixedMax) {
@@ -189,9 +208,11 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const InfoNceStreamP
         P.part_sum[po] = s_run;
         P.part_cnt[po] = cnt;
         if (kWantAcc) {
+            // O row (thread-owned in TMEM) -> padded smem staging (the tile ring is idle now) -> coalesced 512-byte rows
             mbar_wait(&bar->acc_final, 0);
             tc_fence_after();
-            float4* dst = reinterpret_cast<float4*>(P.part_acc + po * TC_D);
+            float* ost = reinterpret_cast<float*>(stages);
+            float4* mine = reinterpret_cast<float4*>(ost + (size_t)(warp * 32 + lane) * TC_OST_STRIDE);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t t[32];
@@ -199,8 +220,15 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const InfoNceStreamP
                 tc_wait_ld();
 #pragma unroll
                 for (int v = 0; v < 8; ++v)
-                    dst[ch * 8 + v] = make_float4(__uint_as_float(t[4 * v]), __uint_as_float(t[4 * v + 1]),
-                                                  __uint_as_float(t[4 * v + 2]), __uint_as_float(t[4 * v + 3]));
+                    mine[ch * 8 + v] = make_float4(__uint_as_float(t[4 * v]), __uint_as_float(t[4 * v + 1]),
+                                                   __uint_as_float(t[4 * v + 2]), __uint_as_float(t[4 * v + 3]));
+            }
+            __syncwarp();                                   // each warp drains exactly the 32 rows it staged
+            float4* dst = reinterpret_cast<float4*>(P.part_acc + ((size_t)split * P.Bpad + row0 + warp * 32) * TC_D);
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+                if (warp * 32 + rr < nrows)
+                    dst[rr * 32 + lane] = *reinterpret_cast<const float4*>(ost + (size_t)(warp * 32 + rr) * TC_OST_STRIDE + lane * 4);
             }
         }
     } else if (warp == 4) {
@@ -223,6 +251,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const InfoNceStreamP
             constexpr uint32_t idesc_o = make_idesc_bf16(TC_BM, TC_D, 0, 1);    // O: B = tile, MN-major (N = features)
             mbar_wait(&bar->q_ready, 0);
             tc_fence_after();
+            const uint32_t qbase = smem_u32(qtile);
             for (int i = 0; i <= n; ++i) {
                 if (i < n) {
                     const int stage = i % TC_STAGES;
@@ -236,7 +265,9 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const InfoNceStreamP
                         // 16 features per MMA: 32 bytes along the swizzled 128-byte row, next box after 4 steps
                         const uint64_t bd = make_smem_desc_sw128(sbase + (kk >> 2) * TC_HALF_BYTES + (kk & 3) * dbg.kstep1,
                                                                  dbg.lbo1, dbg.sbo1);
-                        mma_ts(d_tmem, tmem + TM_Q + kk * 8, bd, idesc_s, kk > 0);
+                        const uint64_t ad = make_smem_desc_sw128(qbase + (kk >> 2) * TC_HALF_BYTES + (kk & 3) * dbg.kstep1,
+                                                                 dbg.lbo1, dbg.sbo1);
+                        mma_ss(d_tmem, ad, bd, idesc_s, kk > 0);
                     }
                     tc_commit(&bar->s_full[i & 1]);
                     if (!kWantAcc) tc_commit(&bar->empty[stage]);

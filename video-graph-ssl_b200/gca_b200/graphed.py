@@ -4,8 +4,8 @@ At the headline shape the whole head (logits + loss + gradient + top-k + enqueue
 the cost of launching its three kernels from Python one by one (SURVEY.md section 7.2 "microsecond budgets").
 `GraphedMoCoStep` captures
 
-    gca_infonce_fwd  (queue-streaming kernel + fixed-order finalize: loss, lse, rank, top-1/top-5 hits, d loss/d q)
-    gca_enqueue_devptr (in-place ring enqueue; the ring pointer lives in device memory and advances on the device)
+    gca_moco_step = queue-streaming kernel + fixed-order finalize (loss, lse, rank, top-1/top-5 hits, d loss/d q) with
+                    the in-place ring enqueue riding in the finalize launch; the ring pointer lives in device memory
 
 once, over static input/output buffers, and replays it per step -- the same arithmetic as
 `RGBMoCo.forward` -> `NCESoftmaxLoss` -> `loss.backward()` -> `accuracy` (train_video_contrast_dis.py:411-428)
@@ -53,11 +53,10 @@ class GraphedMoCoStep(object):
 
     def _enqueue_work(self, stream):
         m = self.moco
-        _lib.call("gca_infonce_fwd", ptr(self.q), ptr(self.k), ptr(m.memory), self.qd, self.B, self.K, self.d, 1.0 / m.T,
-                  _lib.ALGO[self.algo], ptr(self.loss), ptr(self.loss_rows), ptr(self.lse), ptr(self.pos), ptr(self.rank),
-                  ptr(self.hits), ptr(self.dq), None, ptr(self.ws), self.ws.numel(), stream)
-        _lib.call("gca_enqueue_devptr", ptr(m.memory), self.qd, self.K, 0, self.K, self.d, ptr(self.all_k), self.N,
-                  ptr(self.state), stream)
+        _lib.call("gca_moco_step", ptr(self.q), ptr(self.k), ptr(m.memory), self.qd, self.B, self.K, self.d, 1.0 / m.T,
+                  _lib.ALGO[self.algo], ptr(self.all_k), self.N, 0, ptr(self.state),
+                  ptr(self.loss), ptr(self.loss_rows), ptr(self.lse), ptr(self.pos), ptr(self.rank), ptr(self.hits),
+                  ptr(self.dq), ptr(self.ws), self.ws.numel(), stream)
 
     def capture(self):
         lib = _lib.load()
