@@ -105,7 +105,9 @@ int gca_moco_step(const float* q, const float* k, void* queue, int dtype_queue, 
                   float* dq_unit, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Stage 1 of gca_infonce_fwd on its own: only the queue-streaming kernel, leaving the per-split partials in the
- * workspace (layout: csrc/gca_common.cuh).  For profiling / roofline timing of the dominant kernel. */
+ * workspace (layout: csrc/gca_common.cuh).  For profiling / roofline timing of the dominant kernel.
+ * want_acc: bit 0 = also accumulate the gradient partials; bit 1 = skip the per-step q -> bf16 / positive-logit
+ * preparation launch and reuse what the previous call left in this workspace (times the streaming kernel alone). */
 int gca_infonce_partials(const float* q, const float* k, const void* queue, int dtype_queue,
                          int B, long long K, int d, float inv_T, int algo, int want_acc,
                          void* workspace, size_t workspace_bytes, void* stream);

@@ -41,7 +41,7 @@ def run_once(B, K, want_grad=True):
 
 
 if __name__ == "__main__":
-    if "--sweep" in sys.argv:
+    if False and "--sweep" in sys.argv:   # descriptor knobs were removed once the layouts were validated on hardware
         variants = ["16,1024,32,16384,1024,2048",      # canonical
                     "16,1024,32,1024,16384,2048",      # GEMM2 LBO/SBO swapped
                     "1,1024,32,16384,1024,2048",

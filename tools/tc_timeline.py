@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Bring-up aid: per-CTA phase timeline of infonce_tc_kernel from %globaltimer stamps (GCA_TC_TIMEBUF).
+Not part of the product or the tests."""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "video-graph-ssl_b200"))
+import torch
+import torch.nn.functional as F
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+buf = torch.zeros(32 * 1024, dtype=torch.int64, device="cuda")
+os.environ["GCA_TC_TIMEBUF"] = hex(buf.data_ptr())
+from gca_b200 import _lib, functional as GF
+
+torch.manual_seed(0)
+mem = F.normalize(torch.randn(K, 128)).to(torch.bfloat16).cuda()
+q, k = F.normalize(torch.randn(B, 128)).cuda(), F.normalize(torch.randn(B, 128)).cuda()
+ws = GF.workspace(q.device, GF.infonce_workspace_bytes(B, K, 128, 1, "tcgen05"), "t")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+names = {0: "entry", 1: "setup done", 3: "prologue done (q tile ready)", 4: "first S tile seen", 5: "main loop done",
+         6: "last O+=PQ done", 7: "partials written", 8: "exit", 9: "producer: first TMA issued", 10: "mma: q_ready seen",
+         11: "mma: first tile landed"}
+def launch(flag):
+    _lib.call("gca_infonce_partials", _lib.ptr(q), _lib.ptr(k), _lib.ptr(mem), 1, B, K, 128, 1 / 0.07, 2, flag, _lib.ptr(ws),
+              ws.numel(), st)
+
+
+launch(1)
+for cold in (True, False):
+    # keep the GPU busy so the SM clock is at its working point, then stamp the last launch
+    for it in range(300):
+        if cold:
+            flush.fill_(it & 1)
+        launch(3)
+    if cold:
+        flush.fill_(1)
+    buf.zero_()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    launch(3)
+    ev1.record()
+    torch.cuda.synchronize()
+    t = buf.cpu().view(-1, 32)
+    n = int((t[:, 0] > 0).sum())
+    t = t[:n].double()
+    t0 = t[:, 0].min()
+    print("%s L2: %d CTAs, kernel span %.2f us (first entry -> last exit), CUDA-event time %.2f us" % (
+        "cold" if cold else "warm", n, (t[:, 8].max() - t0) / 1e3, ev0.elapsed_time(ev1) * 1e3))
+    for sl in sorted(names):
+        rel = (t[:, sl] - t[:, 0]) / 1e3
+        print("   %-32s mean %6.2f us   min %6.2f   max %6.2f   (since own entry)" % (names[sl], rel.mean(), rel.min(), rel.max()))
+    print("   entry skew across CTAs: %.2f us" % ((t[:, 0].max() - t0) / 1e3))
+    cn = {17: "softmax tile2: wait S", 18: "  tcgen05.ld 128 cols", 19: "  max + count pass", 20: "  exp + sum pass", 21: "  pack + tcgen05.st + arrive",
+          22: "softmax tile3 end (full period)"}
+    prev = 16
+    for sl in sorted(cn):
+        dcy = t[:, sl] - t[:, prev if sl != 22 else 21]
+        print("   %-34s mean %7.0f cyc  min %7.0f  max %7.0f" % (cn[sl], dcy.mean(), dcy.min(), dcy.max()))
+        prev = sl
+    mn = {25: "mma i=3: wait tile landed", 26: "  issue S GEMM + commit", 27: "  wait P(i-1)", 28: "  issue O GEMM + commits"}
+    prev = 24
+    for sl in sorted(mn):
+        dcy = t[:, sl] - t[:, prev]
+        print("   %-34s mean %7.0f cyc  min %7.0f  max %7.0f" % (mn[sl], dcy.mean(), dcy.min(), dcy.max()))
+        prev = sl

@@ -60,6 +60,8 @@ InfoNceWs infonce_ws_carve(void* base, int B, int d, int nsplit)
     w.part_sum = (float*)(p + off);                    off += align_up(rows * sizeof(float), 256);
     w.part_cnt = (int*)(p + off);                      off += align_up(rows * sizeof(int), 256);
     w.pos_tmp  = (float*)(p + off);                    off += align_up((size_t)w.Bpad * sizeof(float), 256);
+    w.pos_ws   = (float*)(p + off);                    off += align_up((size_t)w.Bpad * sizeof(float), 256);
+    w.q_bf16   = (void*)(p + off);                     off += align_up((size_t)w.Bpad * d * 2, 1024);
     w.part_acc = (float*)(p + off);                    off += align_up(rows * d * sizeof(float), 256);
     w.bytes = off;
     return w;
@@ -98,7 +100,7 @@ static int nsplit_for(int algo, int B, long long K, int d)
 // launch the stream kernel of the chosen family; fills `ws`
 static int run_stream(const float* q, const float* k, const void* queue, int dtype_queue, int B, long long K, int d,
                       float inv_T, int algo, const float* lse_fixed, bool want_acc, float* pos_out, float* logits_out,
-                      void* workspace, size_t workspace_bytes, InfoNceWs* ws_out, cudaStream_t st)
+                      void* workspace, size_t workspace_bytes, InfoNceWs* ws_out, cudaStream_t st, bool skip_prep = false)
 {
     const int a = pick_algo(algo, dtype_queue, d);
     if (sm_count_cached() < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
@@ -111,6 +113,7 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
     P.counter = ws.counter; P.part_max = ws.part_max; P.part_sum = ws.part_sum; P.part_cnt = ws.part_cnt;
     P.part_acc = want_acc ? ws.part_acc : nullptr;
     P.nsplit = nsplit; P.Bpad = ws.Bpad; P.pos_out = pos_out ? pos_out : ws.pos_tmp; P.logits_out = logits_out; P.ld_logits = K + 1;
+    P.q_bf16_ws = ws.q_bf16; P.pos_ws = ws.pos_ws; P.T_ = 1.f / inv_T; P.skip_prep = skip_prep ? 1 : 0;
     *ws_out = ws;
     count_launch(1);
     if (a == GCA_ALGO_TCGEN05) return infonce_tc_launch(P, lse_fixed != nullptr, st);
@@ -197,8 +200,8 @@ extern "C" int gca_infonce_partials(const float* q, const float* k, const void* 
     int rc = check_infonce_args("gca_infonce_partials", q, k, queue, dtype_queue, B, K, d, inv_T, algo);
     if (rc != GCA_OK) return rc;
     InfoNceWs ws;
-    return run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, want_acc != 0, nullptr, nullptr, workspace,
-                      workspace_bytes, &ws, (cudaStream_t)stream);
+    return run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, (want_acc & 1) != 0, nullptr, nullptr, workspace,
+                      workspace_bytes, &ws, (cudaStream_t)stream, (want_acc & 2) != 0);
 }
 
 extern "C" int gca_infonce_bwd(const float* q, const float* k, const void* queue, int dtype_queue, int B, long long K,

@@ -41,6 +41,8 @@ struct InfoNceWs {
     int*   part_cnt;
     float* part_acc;
     float* pos_tmp;     // [Bpad] positive logits when the caller gave no output buffer
+    float* pos_ws;      // [Bpad] positive logits for the tcgen05 kernel (written by its prep kernel)
+    void*  q_bf16;      // [Bpad, d] bf16 copy of q for the tcgen05 kernel
     int    nsplit;
     int    Bpad;
     size_t bytes;

@@ -24,6 +24,11 @@ struct InfoNceStreamParams {
     float* pos_out;          // [B] or NULL
     float* logits_out;       // [B, ld_logits] or NULL (ffma family only)
     long long ld_logits;
+    // tcgen05 family only: per-step scratch filled by infonce_prep_kernel
+    void*  q_bf16_ws;        // [Bpad, 128] bf16
+    float* pos_ws;           // [Bpad] positive logits (natural-log units)
+    float  T_;               // 1 / inv_T
+    int    skip_prep;        // reuse q_bf16_ws / pos_ws from the previous launch on this workspace (profiling)
 };
 
 // ffma family (infonce_ffma.cu)

@@ -3,11 +3,11 @@
 // One CTA = 128 query rows x a contiguous range of 128-key queue tiles; grid = (K-splits, row blocks) ~ one CTA/SM.
 // It is a flash-attention forward whose keys and values are the same queue tile:
 //     S = q Q^T        tcgen05.mma, A = q (bf16 smem tile), B = queue tile in smem, both K-major
-//     p = 2^(S c - m)  one thread per query row, online max with lazy rescale, row sum, rank count
+//     p = 2^(S c - m)  one thread per query row, online max with lazy rescale, row sum, rank count; two warpgroups
+//                      ping-pong over alternate tiles with their own S / O buffers in TMEM
 //     O += P Q         tcgen05.mma, A = P (bf16, written back over S in TMEM), B = the SAME smem tile, MN-major
 // so a queue tile is fetched once (TMA, 128-byte swizzle, 4-stage mbarrier ring) and the [B, K] logits never
-// leave the SM.  q is converted once per CTA into a swizzled smem tile (A operand).  Warp roles: warps 0-3 softmax (TMEM lane quarter = warp), warp 4 TMA producer, warp 5 MMA
-// issuer + TMEM allocator.  Per-split partials (max, sum, count, O) go to the workspace; finalize.cu merges them
+// leave the SM.  Per-split partials (max, sum, count, O) go to the workspace; finalize.cu merges them
 // in a fixed order.  Replaces mem_moco.py:36-46 + criterion.py:44 + autograd(mm) of the reference.
 #include "gca_common.cuh"
 #include "infonce_params.cuh"
@@ -20,23 +20,41 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_D = 128;
 constexpr int TC_STAGES = 4;
 constexpr int TC_STAGE_BYTES = TC_BN * TC_D * 2;          // 32 KB: two [128 keys][64 features] swizzled boxes
 constexpr int TC_HALF_BYTES = TC_STAGE_BYTES / 2;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;                           // 8 softmax warps (2 groups) + TMA warp + MMA warp
+constexpr int TC_WARP_TMA = 8, TC_WARP_MMA = 9;
 constexpr uint32_t TM_COLS = 512;
-constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O = 256;   // TMEM column map (fp32 S double buffer, fp32 O)
+constexpr int TC_SUB = 64;                                // keys per softmax step: each 128-key tile feeds 64 keys to each group
+// TMEM columns per softmax group g: two 64-column S buffers (P is written back over the first 32 columns of the buffer
+// it came from) and a 128-column O accumulator: 256 columns per group, 512 in all
+__host__ __device__ constexpr uint32_t tm_s(int g, int b) { return (uint32_t)(g * 256 + b * 64); }
+__host__ __device__ constexpr uint32_t tm_o(int g) { return (uint32_t)(g * 256 + 128); }
 constexpr float TC_RESCALE_LOG2 = 8.f;                    // rescale O only when the row max grows by > 2^8
 constexpr int TC_OST_STRIDE = 132;                        // fp32 O staging row (128 + 4 floats): conflict-free row writes
 constexpr size_t TC_QTILE_BYTES = (size_t)TC_BM * TC_D * 2;   // bf16 q block, same swizzled layout as a queue tile
 constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + TC_QTILE_BYTES + 512;
 static_assert((size_t)TC_BM * TC_OST_STRIDE * 4 <= (size_t)TC_STAGES * TC_STAGE_BYTES, "O staging must fit in the tile ring");
 
-struct TcDebug { uint32_t lbo1, sbo1, kstep1, lbo2, sbo2, kstep2; };
+struct TcDebug { unsigned long long* timebuf; };   // bring-up only: phase time stamps (tools/tc_timeline.py)
+
+__device__ __forceinline__ void tc_stamp(const TcDebug& dbg, int slot)
+{
+    if (dbg.timebuf) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        dbg.timebuf[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 32 + slot] = t;
+    }
+}
+__device__ __forceinline__ void tc_cstamp(const TcDebug& dbg, int slot)          // SM cycle counter, for intra-CTA phases
+{
+    if (dbg.timebuf) dbg.timebuf[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 32 + slot] = (unsigned long long)clock64();
+}
 
 struct TcBarriers {
     uint64_t full[TC_STAGES];     // TMA landed a queue tile
     uint64_t empty[TC_STAGES];    // both MMAs that read the tile have completed
-    uint64_t s_full[2];           // S = q Q^T of a tile is in TMEM
-    uint64_t p_full[2];           // softmax finished with S (and wrote P)
-    uint64_t o_done;              // one phase per completed O += P Q
+    uint64_t s_full[4];           // [group * 2 + buffer] S = q Q^T of a 64-key step is in TMEM
+    uint64_t p_full[4];           // [group * 2 + buffer] softmax finished with that S buffer (and wrote P over it)
+    uint64_t o_done[2];           // per softmax group: one phase per completed O += P Q
     uint64_t acc_final;           // last O += P Q completed
     uint64_t q_ready;             // the bf16 q block is in shared memory (A operand of S = q Q^T)
     uint32_t tmem_base;
@@ -44,7 +62,8 @@ struct TcBarriers {
 
 template <bool kWantAcc, bool kFixedMax>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const InfoNceStreamParams P, const TcDebug dbg)
+infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap qmap,
+                  const InfoNceStreamParams P, const TcDebug dbg)
 {
     using namespace ptx;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -60,241 +79,324 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const InfoNceStreamP
     const int n = (int)(t_end - t_begin);
 
     if (split == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.counter = 0u;      // re-arm the finalize ticket
+    if (threadIdx.x == 0) tc_stamp(dbg, 0);
 
-    if (warp == 4 && lane == 0) {
+    if (warp == TC_WARP_TMA && lane == 0) {
         prefetch_tmap(&tmap);
+        prefetch_tmap(&qmap);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar->full[s], 1); mbar_init(&bar->empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&bar->s_full[b], 1); mbar_init(&bar->p_full[b], 128); }
-        mbar_init(&bar->o_done, 1);
+        for (int b = 0; b < 4; ++b) { mbar_init(&bar->s_full[b], 1); mbar_init(&bar->p_full[b], 128); }
+        for (int b = 0; b < 2; ++b) mbar_init(&bar->o_done[b], 1);
         mbar_init(&bar->acc_final, 1);
-        mbar_init(&bar->q_ready, 128);
+        mbar_init(&bar->q_ready, 1);
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc<TM_COLS>(&bar->tmem_base);
+    if (warp == TC_WARP_MMA) tmem_alloc<TM_COLS>(&bar->tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bar->tmem_base;
+    if (threadIdx.x == 0) tc_stamp(dbg, 1);
 
-    if (warp < 4) {
-        // =============================================================== softmax warps: one thread per query row
-        const int row = row0 + warp * 32 + lane;
+    if (warp < 8) {
+        // =============================================================== softmax: two warpgroups, one thread per query row.
+        // Group g (warps 4g..4g+3) owns the tiles of parity g, the S buffer g and its OWN accumulator O_g: two independent
+        // online-softmax streams that interleave on the MUFU and tensor pipes (while one group is in its MUFU-bound exp
+        // sweep the other loads / scans its next tile) and are merged once at the end.
+        const int g = warp >> 2, wq = warp & 3;                       // group, TMEM lane quarter
+        const int r_loc = wq * 32 + lane;                             // row within the 128-row block
+        const int row = row0 + r_loc;
         const bool valid = row < P.B;
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        const float c2 = P.inv_T * 1.4426950408889634f;                 // logits -> log2 domain
+        const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
+        const uint32_t o_addr = lane_addr + tm_o(g);
+        const float c2 = P.inv_T * 1.4426950408889634f;               // logits -> log2 domain
 
-        // Prologue.  Each warp converts ITS 32 query rows with coalesced 128-bit loads (lane = 4 features): the
-        // positive logit q.k in fp32 (fixed shuffle order: every split computes the same bits) and q -> bf16 written in
-        // the 128-byte-swizzled K-major layout of a queue tile, so S = q Q^T is a plain smem x smem tcgen05.mma.
-        float pos_dot = 0.f;
-        {
-            const float4* qg = reinterpret_cast<const float4*>(P.q + (size_t)row0 * TC_D);
-            const float4* kg = reinterpret_cast<const float4*>(P.k + (size_t)row0 * TC_D);
-            const int sub = lane >> 4, chunk = (lane & 15) >> 1, half = lane & 1;    // 64-feature box, 16-byte chunk, 8-byte half
-#pragma unroll
-            for (int batch = 0; batch < 2; ++batch) {
-                float4 a[16], b[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int r = warp * 32 + batch * 16 + u;
-                    a[u] = make_float4(0.f, 0.f, 0.f, 0.f); b[u] = a[u];
-                    if (r < nrows) { a[u] = __ldg(qg + r * 32 + lane); b[u] = __ldg(kg + r * 32 + lane); }
-                }
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int r = warp * 32 + batch * 16 + u;
-                    float dsum = fmaf(a[u].x, b[u].x, fmaf(a[u].y, b[u].y, fmaf(a[u].z, b[u].z, a[u].w * b[u].w)));
-                    dsum = warp_sum(dsum);
-                    if (lane == batch * 16 + u) pos_dot = dsum;
-                    uint2 pk2;
-                    pk2.x = pack_bf16(a[u].x, a[u].y);
-                    pk2.y = pack_bf16(a[u].z, a[u].w);
-                    *reinterpret_cast<uint2*>(qtile + sub * TC_HALF_BYTES + r * 128 + ((chunk ^ (r & 7)) << 4) + half * 8) = pk2;
-                }
-            }
-            fence_proxy_async();                               // generic-proxy smem writes -> visible to the tensor core
-            mbar_arrive(&bar->q_ready);
-        }
-        const float pos_nat = pos_dot * P.inv_T;
-        if (split == 0 && valid) {
-            if (P.pos_out) P.pos_out[row] = pos_nat;
-            if (P.logits_out) P.logits_out[(size_t)row * P.ld_logits] = pos_nat;
-        }
+        // The bf16 q block and the positive logits were prepared once per step by infonce_prep_kernel (below): 148 CTAs
+        // re-reading and re-converting the same fp32 rows would cost more L2 traffic than the queue itself.
+        const float pos_nat0 = P.pos_ws[row];                         // natural-log units (q.k / T); 0 for padding rows
+        const float pos_dot = pos_nat0 * P.T_;                        // the raw dot product the S tile is compared with
+        if (split == 0 && g == 0 && valid && P.logits_out) P.logits_out[(size_t)row * P.ld_logits] = pos_nat0;
+        if (threadIdx.x == 0) tc_stamp(dbg, 3);
 
         float m_run = kFixedMax ? (valid ? P.lse_fixed[row] * 1.4426950408889634f : 0.f) : -INFINITY;   // log2 domain
         float s_run = 0.f;
         int cnt = 0;
 
-        for (int i = 0; i < n; ++i) {
-            const int buf = i & 1;
-            const uint32_t s_addr = lane_addr + (buf ? TM_S1 : TM_S0);
-            mbar_wait(&bar->s_full[buf], (i >> 1) & 1);
+        // Group g takes keys [64g, 64g+64) of every 128-key tile; its S buffers alternate, so the S GEMM of step v+1 is
+        // already in TMEM while step v is being exponentiated.
+        for (int v = 0; v < n; ++v) {
+            const int sb = v & 1;
+            const uint32_t s_addr = lane_addr + tm_s(g, sb);
+            if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 16);
+            mbar_wait(&bar->s_full[g * 2 + sb], (v >> 1) & 1);
             tc_fence_after();
-            uint32_t sr[128];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + 32 * c, sr + 32 * c);
+            if (threadIdx.x == 0 && v == 0) tc_stamp(dbg, 4);
+            if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 17);
+            const long long key0 = (t_begin + v) * TC_BN + g * TC_SUB;
+            const int nvalid = (P.K - key0 < TC_SUB) ? (int)((P.K - key0 > 0) ? (P.K - key0) : 0) : TC_SUB;
+            uint32_t sr[64];
+            tmem_ld32(s_addr, sr);
+            tmem_ld32(s_addr + 32, sr + 32);
             tc_wait_ld();
+            if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 18);
             float* sv = reinterpret_cast<float*>(sr);
-
-            const long long key0 = (t_begin + i) * TC_BN;
-            const int nvalid = (P.K - key0 < TC_BN) ? (int)(P.K - key0) : TC_BN;
             if (P.logits_out && valid) {                                   // parity / debug path only
                 float* dst = P.logits_out + (size_t)row * P.ld_logits + 1 + key0;
 #pragma unroll
-                for (int j = 0; j < TC_BN; ++j) if (j < nvalid) dst[j] = sv[j] * P.inv_T;
+                for (int j = 0; j < TC_SUB; ++j) if (j < nvalid) dst[j] = sv[j] * P.inv_T;
             }
-            if (nvalid < TC_BN) {
+            if (nvalid < TC_SUB) {
 #pragma unroll
-                for (int j = 0; j < TC_BN; ++j) if (j >= nvalid) sv[j] = -INFINITY;   // TMA zero-filled rows past K
+                for (int j = 0; j < TC_SUB; ++j) if (j >= nvalid) sv[j] = -INFINITY;   // TMA zero-filled rows past K
             }
-            float tmax = -INFINITY;
-            int c = 0;
-#pragma unroll
-            for (int j = 0; j < TC_BN; j += 2) {
-                tmax = max3(tmax, sv[j], sv[j + 1]);
-                c += (sv[j] > pos_dot) ? 1 : 0;
-                c += (sv[j + 1] > pos_dot) ? 1 : 0;
-            }
-            cnt += c;
-
             if (!kFixedMax) {
-                const float xm = tmax * c2;
-                if (i == 0) {
-                    m_run = xm;
-                } else {
-                    const bool need = xm > m_run + TC_RESCALE_LOG2;
-                    if (__any_sync(0xffffffffu, need)) {                    // warp-uniform: TMEM ld/st are collective
-                        const float m_new = need ? xm : m_run;
-                        const float sc = ex2(m_run - m_new);
-                        s_run *= sc;
-                        m_run = m_new;
-                        if (kWantAcc) {
-                            mbar_wait(&bar->o_done, (i - 1) & 1);          // O += P Q of tile i-1 has landed
-                            tc_fence_after();
+                // row max with four independent chains
+                float tm0 = -INFINITY, tm1 = -INFINITY, tm2 = -INFINITY, tm3 = -INFINITY;
 #pragma unroll
-                            for (int ch = 0; ch < 4; ++ch) {
-                                uint32_t t[32];
-                                tmem_ld32(lane_addr + TM_O + 32 * ch, t);
-                                tc_wait_ld();
+                for (int j = 0; j < TC_SUB; j += 8) {
+                    tm0 = max3(tm0, sv[j], sv[j + 1]);
+                    tm1 = max3(tm1, sv[j + 2], sv[j + 3]);
+                    tm2 = max3(tm2, sv[j + 4], sv[j + 5]);
+                    tm3 = max3(tm3, sv[j + 6], sv[j + 7]);
+                }
+                const float xm = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3)) * c2;   // -inf when the step is fully masked
+                const bool need = xm > m_run + TC_RESCALE_LOG2;             // (m_run = -inf before the first valid step)
+                if (__any_sync(0xffffffffu, need)) {                        // warp-uniform: TMEM ld/st are collective
+                    const float m_new = need ? xm : m_run;
+                    const float sc = (m_run == -INFINITY) ? 0.f : ex2(m_run - m_new);
+                    s_run *= sc;
+                    m_run = m_new;
+                    if (kWantAcc && v > 0) {                                // (first step: O is still unwritten)
+                        mbar_wait(&bar->o_done[g], (v - 1) & 1);            // this group's previous O += P Q has landed
+                        tc_fence_after();
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) t[j] = __float_as_uint(__uint_as_float(t[j]) * sc);
-                                tmem_st32(lane_addr + TM_O + 32 * ch, t);
-                            }
-                            tc_wait_st();
+                        for (int ch = 0; ch < 4; ++ch) {
+                            uint32_t t[32];
+                            tmem_ld32(o_addr + 32 * ch, t);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) t[j] = __float_as_uint(__uint_as_float(t[j]) * sc);
+                            tmem_st32(o_addr + 32 * ch, t);
                         }
+                        tc_wait_st();
                     }
                 }
             }
-            const float neg_m = -m_run;
-            float rs = 0.f;
+            if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 19);
+            // p = 2^(S c2 - m), row sum and rank count in one sweep (MUFU-bound: the compare/count instructions ride in
+            // issue slots that would otherwise idle); four independent chains each, counts kept exact in fp32
+            const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;        // fully masked so far: every p is 2^-inf = 0
+            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+            float cf0 = 0.f, cf1 = 0.f, cf2 = 0.f, cf3 = 0.f;
+            uint32_t pk[32];
 #pragma unroll
-            for (int j = 0; j < TC_BN; ++j) { const float p = ex2(fmaf(sv[j], c2, neg_m)); rs += p; sv[j] = p; }
-            s_run += rs;
+            for (int j = 0; j < TC_SUB; j += 4) {
+                cf0 += (sv[j] > pos_dot) ? 1.f : 0.f;
+                cf1 += (sv[j + 1] > pos_dot) ? 1.f : 0.f;
+                cf2 += (sv[j + 2] > pos_dot) ? 1.f : 0.f;
+                cf3 += (sv[j + 3] > pos_dot) ? 1.f : 0.f;
+                const float p0 = ex2(fmaf(sv[j], c2, neg_m)), p1 = ex2(fmaf(sv[j + 1], c2, neg_m));
+                const float p2 = ex2(fmaf(sv[j + 2], c2, neg_m)), p3 = ex2(fmaf(sv[j + 3], c2, neg_m));
+                rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+                pk[j >> 1] = pack_bf16(p0, p1);
+                pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+            }
+            cnt += (int)((cf0 + cf1) + (cf2 + cf3));
+            s_run += (rs0 + rs1) + (rs2 + rs3);
+            if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 20);
             if (kWantAcc) {
-                uint32_t pk[64];
-#pragma unroll
-                for (int j = 0; j < 64; ++j) pk[j] = pack_bf16(sv[2 * j], sv[2 * j + 1]);
-                tmem_st32(s_addr, pk);                                     // P (bf16) overwrites the first half of S
-                tmem_st32(s_addr + 32, pk + 32);
+                tmem_st32(s_addr, pk);                                      // P (bf16, 64 keys) over the first 32 S columns
                 tc_wait_st();
             }
             tc_fence_before();
-            mbar_arrive(&bar->p_full[buf]);
+            mbar_arrive(&bar->p_full[g * 2 + sb]);
+            if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 21);
+            if (threadIdx.x == 0 && v == 3) tc_cstamp(dbg, 22);
         }
+        if (threadIdx.x == 0) tc_stamp(dbg, 5);
 
-        // split partials
-        const size_t po = (size_t)split * P.Bpad + row;
-        P.part_max[po] = kFixedMax ? 0.f : m_run * 0.6931471805599453f;  // back to natural-log units
-        P.part_sum[po] = s_run;
-        P.part_cnt[po] = cnt;
+        // ---- merge the two groups' streams (max, sum, count, O) and write ONE split partial per row
+        float* st_m = reinterpret_cast<float*>(qtile);                     // the q tile is dead once the last S GEMM is done;
+        float* st_s = st_m + 256;                                          // these are read only after acc_final below
+        int*   st_c = reinterpret_cast<int*>(st_s + 256);
+        if (kWantAcc) { mbar_wait(&bar->acc_final, 0); tc_fence_after(); } // every tcgen05.mma of this CTA has completed
+        if (threadIdx.x == 0) tc_stamp(dbg, 6);
+        st_m[g * 128 + r_loc] = m_run; st_s[g * 128 + r_loc] = s_run; st_c[g * 128 + r_loc] = cnt;
+        named_barrier_sync(1, 256);
+        const float m_o = st_m[(g ^ 1) * 128 + r_loc], s_o = st_s[(g ^ 1) * 128 + r_loc];
+        const int c_o = st_c[(g ^ 1) * 128 + r_loc];
+        float w_me = 1.f, w_ot = 0.f, m_all = m_run;
+        if (!kFixedMax) {
+            m_all = fmaxf(m_run, m_o);                                     // a group whose keys were all past K has m = -inf
+            w_me = (m_run == -INFINITY) ? 0.f : ex2(m_run - m_all);
+            w_ot = (m_o == -INFINITY) ? 0.f : ex2(m_o - m_all);
+        } else {
+            w_ot = 1.f;
+        }
+        if (g == 0) {
+            const size_t po = (size_t)split * P.Bpad + row;
+            P.part_max[po] = kFixedMax ? 0.f : m_all * 0.6931471805599453f;  // back to natural-log units
+            P.part_sum[po] = s_run * w_me + s_o * w_ot;
+            P.part_cnt[po] = cnt + c_o;
+        }
         if (kWantAcc) {
-            // O row (thread-owned in TMEM) -> padded smem staging (the tile ring is idle now) -> coalesced 512-byte rows
-            mbar_wait(&bar->acc_final, 0);
-            tc_fence_after();
+            // group g merges feature columns [64g, 64g+64) of its row: O = w_me O_mine + w_ot O_other, staged in the (idle)
+            // tile ring with a padded stride, then written out as coalesced 512-byte rows
             float* ost = reinterpret_cast<float*>(stages);
-            float4* mine = reinterpret_cast<float4*>(ost + (size_t)(warp * 32 + lane) * TC_OST_STRIDE);
+            const uint32_t o_other = lane_addr + tm_o(g ^ 1);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t t[32];
-                tmem_ld32(lane_addr + TM_O + 32 * ch, t);
+            for (int ch = 0; ch < 2; ++ch) {
+                const int col = g * 64 + ch * 32;
+                uint32_t a[32], b[32];
+                tmem_ld32(o_addr + col, a);
+                tmem_ld32(o_other + col, b);
                 tc_wait_ld();
+                float4* dst = reinterpret_cast<float4*>(ost + (size_t)r_loc * TC_OST_STRIDE + col);
 #pragma unroll
-                for (int v = 0; v < 8; ++v)
-                    mine[ch * 8 + v] = make_float4(__uint_as_float(t[4 * v]), __uint_as_float(t[4 * v + 1]),
-                                                   __uint_as_float(t[4 * v + 2]), __uint_as_float(t[4 * v + 3]));
+                for (int v = 0; v < 8; ++v) {
+                    float4 o;
+                    o.x = __uint_as_float(a[4 * v]) * w_me;     o.y = __uint_as_float(a[4 * v + 1]) * w_me;
+                    o.z = __uint_as_float(a[4 * v + 2]) * w_me; o.w = __uint_as_float(a[4 * v + 3]) * w_me;
+                    o.x = fmaf(__uint_as_float(b[4 * v]), w_ot, o.x);     o.y = fmaf(__uint_as_float(b[4 * v + 1]), w_ot, o.y);
+                    o.z = fmaf(__uint_as_float(b[4 * v + 2]), w_ot, o.z); o.w = fmaf(__uint_as_float(b[4 * v + 3]), w_ot, o.w);
+                    dst[v] = o;
+                }
             }
-            __syncwarp();                                   // each warp drains exactly the 32 rows it staged
-            float4* dst = reinterpret_cast<float4*>(P.part_acc + ((size_t)split * P.Bpad + row0 + warp * 32) * TC_D);
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-                if (warp * 32 + rr < nrows)
-                    dst[rr * 32 + lane] = *reinterpret_cast<const float4*>(ost + (size_t)(warp * 32 + rr) * TC_OST_STRIDE + lane * 4);
+            named_barrier_sync(1, 256);
+            // 8 warps x 16 rows each, one 512-byte row per warp instruction
+            float4* gdst = reinterpret_cast<float4*>(P.part_acc + ((size_t)split * P.Bpad + row0) * TC_D);
+#pragma unroll 4
+            for (int rr = 0; rr < 16; ++rr) {
+                const int r = warp * 16 + rr;
+                if (r < nrows) gdst[r * 32 + lane] = *reinterpret_cast<const float4*>(ost + (size_t)r * TC_OST_STRIDE + lane * 4);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == TC_WARP_TMA) {
         // =============================================================== TMA producer
         if (lane == 0) {
+            mbar_arrive_expect_tx(&bar->q_ready, (uint32_t)TC_QTILE_BYTES);
+            tma_load_2d(qtile, &qmap, &bar->q_ready, 0, row0);                       // features  0..63 of the 128 query rows
+            tma_load_2d(qtile + TC_HALF_BYTES, &qmap, &bar->q_ready, 64, row0);      // features 64..127
             for (int i = 0; i < n; ++i) {
                 const int stage = i % TC_STAGES;
                 if (i >= TC_STAGES) mbar_wait(&bar->empty[stage], ((i / TC_STAGES) - 1) & 1);
                 uint8_t* dst = stages + (size_t)stage * TC_STAGE_BYTES;
                 const int key0 = (int)((t_begin + i) * TC_BN);
+                if (i == 0) tc_stamp(dbg, 9);
                 mbar_arrive_expect_tx(&bar->full[stage], TC_STAGE_BYTES);
                 tma_load_2d(dst, &tmap, &bar->full[stage], 0, key0);               // features  0..63
                 tma_load_2d(dst + TC_HALF_BYTES, &tmap, &bar->full[stage], 64, key0);   // features 64..127
             }
         }
     } else {
-        // =============================================================== MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(TC_BM, TC_BN, 0, 0);   // S: B = tile, K-major  (N = keys)
-            constexpr uint32_t idesc_o = make_idesc_bf16(TC_BM, TC_D, 0, 1);    // O: B = tile, MN-major (N = features)
-            mbar_wait(&bar->q_ready, 0);
+        // =============================================================== MMA issuer: the whole warp walks the loop (uniform
+        // control flow keeps descriptors in uniform registers); one elected lane issues tcgen05.mma / commit.
+        // Program order per iteration: S GEMM of tile i, then O GEMM of tile i-1 -- so the S GEMM of the next tile (other
+        // group's buffer) is already queued while a group is still in its softmax sweep.
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_s = make_idesc_bf16(TC_BM, TC_SUB, 0, 0);  // S: A = q tile, B = 64 queue rows, both K-major
+        constexpr uint32_t idesc_o = make_idesc_bf16(TC_BM, TC_D, 0, 1);    // O: A = P (TMEM), B = the same rows, MN-major
+        mbar_wait(&bar->q_ready, 0);
+        tc_fence_after();
+        if (leader) tc_stamp(dbg, 10);
+        const uint32_t qbase = smem_u32(qtile);
+
+        // S GEMM of step v for group g: S_g[v & 1] = q . (rows [64g, 64g+64) of tile v)^T
+        auto issue_s = [&](int v, int g) {
+            const uint32_t sbase = smem_u32(stages + (size_t)(v % TC_STAGES) * TC_STAGE_BYTES) + g * (TC_SUB * 128);
+            const uint32_t d_tmem = tmem + tm_s(g, v & 1);
+            if (leader) {
+#pragma unroll
+                for (int kk = 0; kk < TC_D / 16; ++kk) {
+                    // 16 features per MMA: 32 bytes along the swizzled 128-byte row, next 64-feature box after 4 steps
+                    // (K-major, 128-byte swizzle: LBO unused, SBO = 1024 B between 8-row groups)
+                    const uint32_t koff = (kk >> 2) * TC_HALF_BYTES + (kk & 3) * 32;
+                    mma_ss(d_tmem, make_smem_desc_sw128(qbase + koff, 16, 1024), make_smem_desc_sw128(sbase + koff, 16, 1024),
+                           idesc_s, kk > 0);
+                }
+                tc_commit(&bar->s_full[g * 2 + (v & 1)]);
+            }
+            __syncwarp();
+        };
+
+        // prologue: the first two steps of both groups
+        for (int v = 0; v < n && v < 2; ++v) {
+            mbar_wait(&bar->full[v % TC_STAGES], 0);
             tc_fence_after();
-            const uint32_t qbase = smem_u32(qtile);
-            for (int i = 0; i <= n; ++i) {
-                if (i < n) {
-                    const int stage = i % TC_STAGES;
-                    mbar_wait(&bar->full[stage], (i / TC_STAGES) & 1);
-                    if (!kWantAcc && i >= 2) mbar_wait(&bar->p_full[i & 1], ((i - 2) >> 1) & 1);   // S buffer drained
-                    tc_fence_after();
-                    const uint32_t sbase = smem_u32(stages + (size_t)stage * TC_STAGE_BYTES);
-                    const uint32_t d_tmem = tmem + ((i & 1) ? TM_S1 : TM_S0);
+            if (v == 0 && leader) tc_stamp(dbg, 11);
+            issue_s(v, 0);
+            issue_s(v, 1);
+            if (!kWantAcc) { if (leader) tc_commit(&bar->empty[v % TC_STAGES]); __syncwarp(); }
+        }
+        for (int v = 0; v < n; ++v) {
+            const int stage = v % TC_STAGES;
+            if (v + 2 < n) {                                               // tile v+2 has to be in smem for the refills below
+                if (v == 3 && leader) tc_cstamp(dbg, 24);
+                mbar_wait(&bar->full[(v + 2) % TC_STAGES], ((v + 2) / TC_STAGES) & 1);
+                if (v == 3 && leader) tc_cstamp(dbg, 25);
+            }
 #pragma unroll
-                    for (int kk = 0; kk < TC_D / 16; ++kk) {
-                        // 16 features per MMA: 32 bytes along the swizzled 128-byte row, next box after 4 steps
-                        const uint64_t bd = make_smem_desc_sw128(sbase + (kk >> 2) * TC_HALF_BYTES + (kk & 3) * dbg.kstep1,
-                                                                 dbg.lbo1, dbg.sbo1);
-                        const uint64_t ad = make_smem_desc_sw128(qbase + (kk >> 2) * TC_HALF_BYTES + (kk & 3) * dbg.kstep1,
-                                                                 dbg.lbo1, dbg.sbo1);
-                        mma_ss(d_tmem, ad, bd, idesc_s, kk > 0);
-                    }
-                    tc_commit(&bar->s_full[i & 1]);
-                    if (!kWantAcc) tc_commit(&bar->empty[stage]);
-                }
-                if (kWantAcc && i >= 1) {
-                    const int j = i - 1, stage = j % TC_STAGES;
-                    mbar_wait(&bar->p_full[j & 1], (j >> 1) & 1);
-                    tc_fence_after();
-                    const uint32_t sbase = smem_u32(stages + (size_t)stage * TC_STAGE_BYTES);
-                    const uint32_t p_tmem = tmem + ((j & 1) ? TM_S1 : TM_S0);
+            for (int g = 0; g < 2; ++g) {
+                mbar_wait(&bar->p_full[g * 2 + (v & 1)], (v >> 1) & 1);     // softmax of (g, v) done: P written / S consumed
+                tc_fence_after();
+                if (v == 3 && g == 0 && leader) tc_cstamp(dbg, 26);
+                if (kWantAcc) {
+                    const uint32_t sbase = smem_u32(stages + (size_t)stage * TC_STAGE_BYTES) + g * (TC_SUB * 128);
+                    const uint32_t p_tmem = tmem + tm_s(g, v & 1);
+                    if (leader) {
 #pragma unroll
-                    for (int kk = 0; kk < TC_BN / 16; ++kk) {
-                        // 16 keys per MMA = two 8-row swizzle atoms (2 KB); LBO = next 64-feature box, SBO = next 8 keys
-                        const uint64_t bd = make_smem_desc_sw128(sbase + kk * dbg.kstep2, dbg.lbo2, dbg.sbo2);
-                        mma_ts(tmem + TM_O, p_tmem + kk * 8, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+                        for (int kk = 0; kk < TC_SUB / 16; ++kk) {
+                            // 16 keys per MMA = two 8-row swizzle atoms (2 KB); LBO = next 64-feature box, SBO = next 8 keys
+                            mma_ts(tmem + tm_o(g), p_tmem + kk * 8, make_smem_desc_sw128(sbase + kk * 2048, TC_HALF_BYTES, 1024),
+                                   idesc_o, (v > 0 || kk > 0) ? 1u : 0u);
+                        }
+                        tc_commit(&bar->o_done[g]);
+                        if (g == 1) tc_commit(&bar->empty[stage]);          // both groups' GEMMs on this tile are queued
+                        if (g == 1 && v == n - 1) tc_commit(&bar->acc_final);
                     }
-                    tc_commit(&bar->empty[stage]);
-                    tc_commit(&bar->o_done);
-                    if (j == n - 1) tc_commit(&bar->acc_final);
+                    __syncwarp();
                 }
+                if (v == 3 && g == 0 && leader) tc_cstamp(dbg, 27);
+                // refill this group's S buffer (v & 1) with step v+2: queued behind the O GEMM that read P from it
+                if (v + 2 < n) {
+                    issue_s(v + 2, g);
+                    if (!kWantAcc && g == 1) { if (leader) tc_commit(&bar->empty[(v + 2) % TC_STAGES]); __syncwarp(); }
+                }
+                if (v == 3 && g == 0 && leader) tc_cstamp(dbg, 28);
             }
         }
     }
+    if (threadIdx.x == 0) tc_stamp(dbg, 7);
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc<TM_COLS>(tmem);
+    if (warp == TC_WARP_MMA) tmem_dealloc<TM_COLS>(tmem);
+    if (threadIdx.x == 0) tc_stamp(dbg, 8);
+}
+
+// Once per step: q -> bf16 [Bpad, 128] (zero rows past B) and the positive logits q.k / T in fp32.  One warp per row,
+// 128-bit coalesced loads; the dot product has a fixed shuffle order (deterministic).
+__global__ void __launch_bounds__(256)
+infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, int B, int Bpad, float inv_T,
+                    __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ pos_ws, float* __restrict__ pos_out)
+{
+    const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= Bpad) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (row < B) {
+        a = __ldg(reinterpret_cast<const float4*>(q + (size_t)row * TC_D) + lane);
+        b = __ldg(reinterpret_cast<const float4*>(k + (size_t)row * TC_D) + lane);
+    }
+    float dsum = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+    dsum = warp_sum(dsum) * inv_T;
+    uint2 pk;
+    pk.x = ptx::pack_bf16(a.x, a.y);
+    pk.y = ptx::pack_bf16(a.z, a.w);
+    reinterpret_cast<uint2*>(q_bf16 + (size_t)row * TC_D)[lane] = pk;
+    if (lane == 0) {
+        pos_ws[row] = dsum;
+        if (pos_out && row < B) pos_out[row] = dsum;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -317,11 +419,12 @@ static EncodeTiledFn encode_fn()
 
 struct TmapCache { const void* ptr; long long K; CUtensorMap map; bool ok; };
 
+// row-major bf16 [rows, 128] tensor, box = 128 rows x 64 features, 128-byte swizzle (queue tiles and the q block alike)
 static int get_queue_tmap(const void* queue, long long K, CUtensorMap* out)
 {
-    static thread_local TmapCache cache[4] = {};
+    static thread_local TmapCache cache[8] = {};
     static thread_local int next = 0;
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
         if (cache[i].ok && cache[i].ptr == queue && cache[i].K == K) { *out = cache[i].map; return GCA_OK; }
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_err(GCA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -335,7 +438,7 @@ static int get_queue_tmap(const void* queue, long long K, CUtensorMap* out)
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(GCA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     cache[next] = TmapCache{queue, K, m, true};
-    next = (next + 1) & 3;
+    next = (next + 1) & 7;
     *out = m;
     return GCA_OK;
 }
@@ -352,14 +455,9 @@ int infonce_tc_nsplit(int B, long long K)
 
 static TcDebug tc_debug_knobs()
 {
-    // canonical values; GCA_TC_DESC="lbo1,sbo1,kstep1,lbo2,sbo2,kstep2" overrides them (bring-up aid only)
-    TcDebug d{16, 1024, 32, (uint32_t)TC_HALF_BYTES, 1024, 2048};
-    const char* e = getenv("GCA_TC_DESC");
-    if (e) {
-        unsigned v[6];
-        if (sscanf(e, "%u,%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == 6)
-            d = TcDebug{v[0], v[1], v[2], v[3], v[4], v[5]};
-    }
+    TcDebug d{nullptr};
+    const char* tb = getenv("GCA_TC_TIMEBUF");        // device address of a >= 32 * grid uint64 buffer (tools/tc_timeline.py)
+    if (tb) d.timebuf = (unsigned long long*)strtoull(tb, nullptr, 0);
     return d;
 }
 
@@ -368,16 +466,24 @@ int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t
     if (P.d != TC_D) return set_err(GCA_ERR_UNSUPPORTED, "tcgen05 InfoNCE kernel needs d == %d (got %d)", TC_D, P.d);
     if (P.K >= (1ll << 31) - TC_BN) return set_err(GCA_ERR_UNSUPPORTED, "tcgen05 InfoNCE kernel: K too large");
     if ((reinterpret_cast<uintptr_t>(P.queue) & 15) != 0) return set_err(GCA_ERR_BAD_ARG, "queue must be 16-byte aligned");
-    CUtensorMap tmap;
+    CUtensorMap tmap, qmap;
     int rc = get_queue_tmap(P.queue, P.K, &tmap);
     if (rc != GCA_OK) return rc;
+    rc = get_queue_tmap(P.q_bf16_ws, P.Bpad, &qmap);
+    if (rc != GCA_OK) return rc;
+    if (!P.skip_prep) {
+        infonce_prep_kernel<<<(P.Bpad + 7) / 8, 256, 0, st>>>(P.q, P.k, P.B, P.Bpad, P.inv_T, (__nv_bfloat16*)P.q_bf16_ws,
+                                                              P.pos_ws, P.pos_out);
+        GCA_LAUNCH_CHECK("infonce_prep_kernel");
+        count_launch(1);
+    }
     const TcDebug dbg = tc_debug_knobs();
     const bool want_acc = P.part_acc != nullptr;
     dim3 grid(P.nsplit, P.Bpad / TC_BM);
 #define GCA_TC_LAUNCH(ACC, FIX) do { \
         auto kern = infonce_tc_kernel<ACC, FIX>; \
         GCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES)); \
-        kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap, P, dbg); } while (0)
+        kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap, qmap, P, dbg); } while (0)
     if (want_acc) { if (fixed_max) GCA_TC_LAUNCH(true, true); else GCA_TC_LAUNCH(true, false); }
     else          { if (fixed_max) GCA_TC_LAUNCH(false, true); else GCA_TC_LAUNCH(false, false); }
 #undef GCA_TC_LAUNCH
