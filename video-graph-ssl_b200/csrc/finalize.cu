@@ -6,10 +6,12 @@
 
 namespace gca {
 
-constexpr int FIN_THREADS = 512;
+constexpr int FIN_THREADS = 256;
 constexpr int FIN_COLS = 128;                 // feature columns per slab
 constexpr int FIN_GROUPS = FIN_THREADS / FIN_COLS;
 constexpr int FIN_MAX_SPLITS = 1024;
+constexpr int FIN_STAT = 5;                   // split statistics a lane of warp 0 keeps in registers (<= 160 splits)
+constexpr int FIN_CHUNK = 40;                 // gradient partials a thread keeps in flight at once
 
 // last-block ticket: returns true in exactly one block, after every other block's global writes are visible
 __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigned int nblocks, int* flag_smem)
@@ -81,10 +83,16 @@ infonce_finalize_kernel(const FinalizeParams F)
 {
     __shared__ float w_s[FIN_MAX_SPLITS];
     __shared__ float red[FIN_THREADS / 32];
-    __shared__ int   cnt_s[FIN_THREADS / 32];
     __shared__ float colsum[FIN_GROUPS][FIN_COLS];
+    __shared__ float row_stat[2];                              // lse, pos of this row
     __shared__ int   flag;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (F.timebuf && tid == 0) {                              // bring-up only
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(F.timebuf + 32 * 1000 + 0, t);
+        F.timebuf[32 * 400 + 4 * blockIdx.x] = t;
+    }
     if (kMode == FIN_FULL && (int)blockIdx.x >= F.B) {        // fused enqueue CTAs
         if (F.enq_dtype == GCA_F32) enqueue_rows<float>(F, blockIdx.x - F.B, gridDim.x - F.B);
         else                        enqueue_rows<__nv_bfloat16>(F, blockIdx.x - F.B, gridDim.x - F.B);
@@ -92,74 +100,119 @@ infonce_finalize_kernel(const FinalizeParams F)
     }
     const int b = blockIdx.x;
     const int ns = F.nsplit;
+    float* out = (kMode == FIN_SHARD) ? F.out_acc : F.dq;
+    const bool want_acc = (out != nullptr && F.part_acc != nullptr);
+    const int grp = tid / FIN_COLS, col = tid % FIN_COLS;
+    const size_t stride = (size_t)F.Bpad * F.d;
 
-    float lse = 0.f, pos = 0.f;
-    if (kMode == FIN_BWD) {
-        lse = F.lse_in[b];
-        pos = F.pos ? F.pos[b] : 0.f;
-    } else {
-        // M = max over splits (and the positive), S = sum of rescaled split sums: fixed order
-        float m = -INFINITY;
-        for (int s = tid; s < ns; s += FIN_THREADS) m = fmaxf(m, F.part_max[(size_t)s * F.Bpad + b]);
-        m = warp_max(m);
-        if ((tid & 31) == 0) red[tid >> 5] = m;
-        __syncthreads();
-        m = red[0];
+    // Loads first, arithmetic later: warp 0 puts the split statistics of its row in flight (they head the memory queue),
+    // then every thread puts its share of the gradient partials in flight (raw values: the split weights are not needed to
+    // LOAD them) -- one L2 round trip for the whole block instead of a chain of dependent ones.
+    float st_m[FIN_STAT], st_s[FIN_STAT];
+    int st_c[FIN_STAT];
+    const bool stat_fast = (ns <= 32 * FIN_STAT);
+    if (warp == 0 && kMode != FIN_BWD && stat_fast) {
 #pragma unroll
-        for (int w = 1; w < FIN_THREADS / 32; ++w) m = fmaxf(m, red[w]);
-        __syncthreads();
-        if (kMode == FIN_FULL) { pos = F.pos[b]; m = fmaxf(m, pos); }
-        float part = 0.f;
-        int cnt = 0;
-        for (int s = tid; s < ns; s += FIN_THREADS) {
-            const size_t o = (size_t)s * F.Bpad + b;
-            const float pm = F.part_max[o];
-            const float e = (pm == -INFINITY) ? 0.f : __expf(pm - m);
-            w_s[s] = e;                                        // exp(part_max - M); turned into exp(. - lse) below
-            part += F.part_sum[o] * e;
-            cnt += F.part_cnt[o];
+        for (int i = 0; i < FIN_STAT; ++i) {
+            const int sp = lane + 32 * i;
+            const size_t o = (size_t)(sp < ns ? sp : 0) * F.Bpad + b;
+            st_m[i] = (sp < ns) ? __ldcg(F.part_max + o) : -INFINITY;
+            st_s[i] = (sp < ns) ? __ldcg(F.part_sum + o) : 0.f;
+            st_c[i] = (sp < ns) ? __ldcg(F.part_cnt + o) : 0;
         }
-        float S = block_sum<FIN_THREADS>(part, red);
-        cnt = warp_sum_i(cnt);
-        if ((tid & 31) == 0) cnt_s[tid >> 5] = cnt;
-        __syncthreads();
-        cnt = 0;
+    }
+    float v[FIN_CHUNK];
+    if (want_acc && col < F.d) {
+        const float* src = F.part_acc + (size_t)b * F.d + col;
 #pragma unroll
-        for (int w = 0; w < FIN_THREADS / 32; ++w) cnt += cnt_s[w];
-        if (kMode == FIN_FULL) {
-            S += __expf(pos - m);
-            lse = m + logf(S);
-            if (tid == 0) {
-                F.lse[b] = lse;
-                F.loss_rows[b] = lse - pos;
-                F.rank_gt[b] = cnt;
-            }
-            const float corr = __expf(m - lse);                // = 1 / S
-            for (int s = tid; s < ns; s += FIN_THREADS) w_s[s] *= corr;
-        } else {                                               // FIN_SHARD: keep the merged partial relative to m
-            if (tid == 0) { F.out_max[b] = m; F.out_sum[b] = S; F.out_cnt[b] = cnt; }
+        for (int i = 0; i < FIN_CHUNK; ++i) {
+            const int sp = grp + i * FIN_GROUPS;
+            v[i] = (sp < ns) ? __ldcg(src + sp * stride) : 0.f;
         }
-        __syncthreads();
     }
 
-    // Gradient accumulator.  FIN_GROUPS thread groups take interleaved splits of one column slab (many independent
-    // loads in flight), then the groups are added in a fixed order: deterministic for a given split count.
-    float* out = (kMode == FIN_SHARD) ? F.out_acc : F.dq;
-    if (out != nullptr && F.part_acc != nullptr) {
+    if (warp == 0) {
+        float lse = 0.f, pos = 0.f;
+        if (kMode == FIN_BWD) {
+            lse = F.lse_in[b];
+            pos = F.pos ? F.pos[b] : 0.f;
+        } else {
+            // M = max over splits (and the positive), S = sum of rescaled split sums: fixed order for a given split count
+            if (kMode == FIN_FULL) pos = F.pos[b];
+            float m = -INFINITY, part = 0.f;
+            int cnt = 0;
+            if (stat_fast) {
+#pragma unroll
+                for (int i = 0; i < FIN_STAT; ++i) m = fmaxf(m, st_m[i]);
+                m = warp_max(m);
+                if (kMode == FIN_FULL) m = fmaxf(m, pos);
+#pragma unroll
+                for (int i = 0; i < FIN_STAT; ++i) {
+                    const int sp = lane + 32 * i;
+                    const float e = (st_m[i] == -INFINITY) ? 0.f : __expf(st_m[i] - m);
+                    if (sp < ns) w_s[sp] = e;                  // exp(part_max - M); turned into exp(. - lse) below
+                    part += st_s[i] * e;
+                    cnt += st_c[i];
+                }
+            } else {                                           // many splits: two dependent passes over the statistics
+                for (int sp = lane; sp < ns; sp += 32) m = fmaxf(m, F.part_max[(size_t)sp * F.Bpad + b]);
+                m = warp_max(m);
+                if (kMode == FIN_FULL) m = fmaxf(m, pos);
+                for (int sp = lane; sp < ns; sp += 32) {
+                    const size_t o = (size_t)sp * F.Bpad + b;
+                    const float pm = F.part_max[o];
+                    const float e = (pm == -INFINITY) ? 0.f : __expf(pm - m);
+                    w_s[sp] = e;
+                    part += F.part_sum[o] * e;
+                    cnt += F.part_cnt[o];
+                }
+            }
+            float S = warp_sum(part);
+            cnt = warp_sum_i(cnt);
+            if (kMode == FIN_FULL) {
+                S += __expf(pos - m);
+                lse = m + logf(S);
+                if (lane == 0) {
+                    F.lse[b] = lse;
+                    F.loss_rows[b] = lse - pos;
+                    F.rank_gt[b] = cnt;
+                }
+                const float corr = __expf(m - lse);            // = 1 / S
+                for (int sp = lane; sp < ns; sp += 32) w_s[sp] *= corr;
+            } else if (lane == 0) {                            // FIN_SHARD: keep the merged partial relative to m
+                F.out_max[b] = m; F.out_sum[b] = S; F.out_cnt[b] = cnt;
+            }
+        }
+        if (lane == 0) { row_stat[0] = lse; row_stat[1] = pos; }
+    }
+    __syncthreads();
+    if (F.timebuf && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.timebuf[32 * 400 + 4 * blockIdx.x + 1] = t; }
+
+    // Gradient accumulator: each of the FIN_GROUPS thread groups sums its interleaved splits in order, then the groups are
+    // added in order: deterministic for a given split count.
+    if (want_acc) {
+        const float lse = row_stat[0], pos = row_stat[1];
         const float p0m1 = (kMode == FIN_SHARD) ? 0.f : (__expf(pos - lse) - 1.f);
         const float scale = (kMode == FIN_FULL) ? F.inv_T / (float)F.B
                           : (kMode == FIN_BWD)  ? F.inv_T * F.grad_scale : 1.f;
-        const int grp = tid / FIN_COLS, col = tid % FIN_COLS;
-        const size_t stride = (size_t)F.Bpad * F.d;
         for (int c0 = 0; c0 < F.d; c0 += FIN_COLS) {
             const int c = c0 + col;
             float a = 0.f;
             if (c < F.d) {
                 const float* src = F.part_acc + (size_t)b * F.d + c;
-#pragma unroll 8
-                for (int s = grp; s < ns; s += FIN_GROUPS) {
-                    const float v = __ldcg(src + s * stride);
-                    a = (kMode == FIN_BWD) ? a + v : fmaf(w_s[s], v, a);
+                for (int base = 0; base < ns; base += FIN_CHUNK * FIN_GROUPS) {
+                    if (c0 > 0 || base > 0) {                  // beyond what was preloaded above
+#pragma unroll
+                        for (int i = 0; i < FIN_CHUNK; ++i) {
+                            const int sp = base + grp + i * FIN_GROUPS;
+                            v[i] = (sp < ns) ? __ldcg(src + sp * stride) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < FIN_CHUNK; ++i) {
+                        const int sp = base + grp + i * FIN_GROUPS;
+                        if (sp < ns) a = (kMode == FIN_BWD) ? a + v[i] : fmaf(w_s[sp], v[i], a);
+                    }
                 }
             }
             colsum[grp][col] = a;
@@ -175,14 +228,16 @@ infonce_finalize_kernel(const FinalizeParams F)
         }
     }
 
+    if (F.timebuf && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.timebuf[32 * 400 + 4 * blockIdx.x + 2] = t; }
     if (kMode == FIN_FULL && (F.loss_mean != nullptr || F.top_hits != nullptr)) {
         if (last_block_ticket(F.counter, (unsigned int)F.B, &flag)) {
+            if (F.timebuf && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.timebuf[32 * 1000 + 6] = t; }
             const float mean = block_mean_fixed(F.loss_rows, F.B, red);
             int h1 = 0, h5 = 0;                                   // integer counts: exact, order-independent
             for (int i = tid; i < F.B; i += FIN_THREADS) { const int r = __ldcg(F.rank_gt + i); h1 += (r < 1); h5 += (r < 5); }
             h1 = warp_sum_i(h1); h5 = warp_sum_i(h5);
             __shared__ int hit_s[2][FIN_THREADS / 32];
-            if ((tid & 31) == 0) { hit_s[0][tid >> 5] = h1; hit_s[1][tid >> 5] = h5; }
+            if (lane == 0) { hit_s[0][warp] = h1; hit_s[1][warp] = h5; }
             __syncthreads();
             if (tid == 0) {
                 int t1 = 0, t5 = 0;
@@ -190,13 +245,20 @@ infonce_finalize_kernel(const FinalizeParams F)
                 if (F.loss_mean) *F.loss_mean = mean;
                 if (F.top_hits) { F.top_hits[0] = t1; F.top_hits[1] = t5; }
                 *F.counter = 0u;
+                if (F.timebuf) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    F.timebuf[32 * 1000 + 1] = t;
+                }
             }
         }
     }
 }
 
-int infonce_finalize_launch(const FinalizeParams& F, int mode, cudaStream_t st)
+int infonce_finalize_launch(const FinalizeParams& F_, int mode, cudaStream_t st)
 {
+    FinalizeParams F = F_;
+    F.timebuf = debug_timebuf();
     if (F.nsplit > FIN_MAX_SPLITS) return set_err(GCA_ERR_UNSUPPORTED, "finalize: %d splits > %d", F.nsplit, FIN_MAX_SPLITS);
     int enq_blocks = 0;
     if (mode == FIN_FULL && F.enq_queue != nullptr && F.enq_N > 0) {

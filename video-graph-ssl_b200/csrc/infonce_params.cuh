@@ -57,7 +57,9 @@ struct FinalizeParams {
     // optional fused enqueue (FIN_FULL): keys [enq_N, d] into the full ring queue [enq_K, d]
     void* enq_queue; int enq_dtype; long long enq_K; const float* enq_keys; int enq_N;
     long long enq_index; long long* enq_state;
+    unsigned long long* timebuf;   // bring-up only (tools/tc_timeline.py): entry / exit time stamps
 };
 int infonce_finalize_launch(const FinalizeParams& F, int mode, cudaStream_t st);
+unsigned long long* debug_timebuf();   // GCA_TC_TIMEBUF env (bring-up only), nullptr normally
 
 }  // namespace gca

@@ -378,9 +378,15 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 // 128-bit coalesced loads; the dot product has a fixed shuffle order (deterministic).
 __global__ void __launch_bounds__(256)
 infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, int B, int Bpad, float inv_T,
-                    __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ pos_ws, float* __restrict__ pos_out)
+                    __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ pos_ws, float* __restrict__ pos_out,
+                    unsigned long long* timebuf)
 {
     const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (timebuf && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(timebuf + 32 * 1000 + 2, t);
+    }
     if (row >= Bpad) return;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (row < B) {
@@ -453,13 +459,13 @@ int infonce_tc_nsplit(int B, long long K)
     return ns;
 }
 
-static TcDebug tc_debug_knobs()
+unsigned long long* debug_timebuf()
 {
-    TcDebug d{nullptr};
-    const char* tb = getenv("GCA_TC_TIMEBUF");        // device address of a >= 32 * grid uint64 buffer (tools/tc_timeline.py)
-    if (tb) d.timebuf = (unsigned long long*)strtoull(tb, nullptr, 0);
-    return d;
+    const char* tb = getenv("GCA_TC_TIMEBUF");        // device address of a 32 * 1024 uint64 buffer (tools/tc_timeline.py)
+    return tb ? (unsigned long long*)strtoull(tb, nullptr, 0) : nullptr;
 }
+
+static TcDebug tc_debug_knobs() { return TcDebug{debug_timebuf()}; }
 
 int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t st)
 {
@@ -473,7 +479,7 @@ int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t
     if (rc != GCA_OK) return rc;
     if (!P.skip_prep) {
         infonce_prep_kernel<<<(P.Bpad + 7) / 8, 256, 0, st>>>(P.q, P.k, P.B, P.Bpad, P.inv_T, (__nv_bfloat16*)P.q_bf16_ws,
-                                                              P.pos_ws, P.pos_out);
+                                                              P.pos_ws, P.pos_out, debug_timebuf());
         GCA_LAUNCH_CHECK("infonce_prep_kernel");
         count_launch(1);
     }
