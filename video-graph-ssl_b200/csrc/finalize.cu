@@ -87,6 +87,9 @@ infonce_finalize_kernel(const FinalizeParams F)
     __shared__ float row_stat[2];                              // lse, pos of this row
     __shared__ int   flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // launched with a programmatic dependency on the stream kernel: everything below reads its partials (or, for the
+    // enqueue CTAs, overwrites queue rows it may still be reading)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (F.timebuf && tid == 0) {                              // bring-up only
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -265,9 +268,15 @@ int infonce_finalize_launch(const FinalizeParams& F_, int mode, cudaStream_t st)
         enq_blocks = (int)(((long long)F.enq_N * (F.d / 4) + FIN_THREADS - 1) / FIN_THREADS);
         if (enq_blocks > 64) enq_blocks = 64;
     }
-    if (mode == FIN_FULL)       infonce_finalize_kernel<FIN_FULL><<<F.B + enq_blocks, FIN_THREADS, 0, st>>>(F);
-    else if (mode == FIN_SHARD) infonce_finalize_kernel<FIN_SHARD><<<F.B, FIN_THREADS, 0, st>>>(F);
-    else                        infonce_finalize_kernel<FIN_BWD><<<F.B, FIN_THREADS, 0, st>>>(F);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(F.B + enq_blocks); cfg.blockDim = dim3(FIN_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;    // PDL: be resident when the stream kernel drains
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    if (mode == FIN_FULL)       GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_finalize_kernel<FIN_FULL>, F));
+    else if (mode == FIN_SHARD) GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_finalize_kernel<FIN_SHARD>, F));
+    else                        GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_finalize_kernel<FIN_BWD>, F));
     GCA_LAUNCH_CHECK("infonce_finalize_kernel");
     count_launch(1);
     return GCA_OK;

@@ -60,6 +60,7 @@ struct FinalizeParams {
     unsigned long long* timebuf;   // bring-up only (tools/tc_timeline.py): entry / exit time stamps
 };
 int infonce_finalize_launch(const FinalizeParams& F, int mode, cudaStream_t st);
+bool pdl_enabled();                    // programmatic dependent launch between prep -> stream -> finalize (default on)
 unsigned long long* debug_timebuf();   // GCA_TC_TIMEBUF env (bring-up only), nullptr normally
 
 }  // namespace gca

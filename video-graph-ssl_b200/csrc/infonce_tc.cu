@@ -78,8 +78,8 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const long long t_begin = ntiles * split / P.nsplit, t_end = ntiles * (split + 1) / P.nsplit;
     const int n = (int)(t_end - t_begin);
 
-    if (split == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.counter = 0u;      // re-arm the finalize ticket
     if (threadIdx.x == 0) tc_stamp(dbg, 0);
+    pdl_launch_dependents();                 // the finalize kernel may begin its (independent) prologue
 
     if (warp == TC_WARP_TMA && lane == 0) {
         prefetch_tmap(&tmap);
@@ -113,8 +113,10 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 
         // The bf16 q block and the positive logits were prepared once per step by infonce_prep_kernel (below): 148 CTAs
         // re-reading and re-converting the same fp32 rows would cost more L2 traffic than the queue itself.
+        pdl_wait();                                                   // prep kernel results (pos_ws) are visible from here
         const float pos_nat0 = P.pos_ws[row];                         // natural-log units (q.k / T); 0 for padding rows
         const float pos_dot = pos_nat0 * P.T_;                        // the raw dot product the S tile is compared with
+        if (split == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.counter = 0u;      // re-arm the finalize ticket
         if (split == 0 && g == 0 && valid && P.logits_out) P.logits_out[(size_t)row * P.ld_logits] = pos_nat0;
         if (threadIdx.x == 0) tc_stamp(dbg, 3);
 
@@ -274,15 +276,25 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     } else if (warp == TC_WARP_TMA) {
         // =============================================================== TMA producer
         if (lane == 0) {
+            // queue tiles do not depend on the prep kernel: get the first ones moving before waiting for it
+            const int pre = n < TC_STAGES ? n : TC_STAGES;
+            for (int i = 0; i < pre; ++i) {
+                uint8_t* dst = stages + (size_t)i * TC_STAGE_BYTES;
+                const int key0 = (int)((t_begin + i) * TC_BN);
+                if (i == 0) tc_stamp(dbg, 9);
+                mbar_arrive_expect_tx(&bar->full[i], TC_STAGE_BYTES);
+                tma_load_2d(dst, &tmap, &bar->full[i], 0, key0);
+                tma_load_2d(dst + TC_HALF_BYTES, &tmap, &bar->full[i], 64, key0);
+            }
+            pdl_wait();                                                              // q_bf16 comes from the prep kernel
             mbar_arrive_expect_tx(&bar->q_ready, (uint32_t)TC_QTILE_BYTES);
             tma_load_2d(qtile, &qmap, &bar->q_ready, 0, row0);                       // features  0..63 of the 128 query rows
             tma_load_2d(qtile + TC_HALF_BYTES, &qmap, &bar->q_ready, 64, row0);      // features 64..127
-            for (int i = 0; i < n; ++i) {
+            for (int i = pre; i < n; ++i) {
                 const int stage = i % TC_STAGES;
-                if (i >= TC_STAGES) mbar_wait(&bar->empty[stage], ((i / TC_STAGES) - 1) & 1);
+                mbar_wait(&bar->empty[stage], ((i / TC_STAGES) - 1) & 1);
                 uint8_t* dst = stages + (size_t)stage * TC_STAGE_BYTES;
                 const int key0 = (int)((t_begin + i) * TC_BN);
-                if (i == 0) tc_stamp(dbg, 9);
                 mbar_arrive_expect_tx(&bar->full[stage], TC_STAGE_BYTES);
                 tma_load_2d(dst, &tmap, &bar->full[stage], 0, key0);               // features  0..63
                 tma_load_2d(dst + TC_HALF_BYTES, &tmap, &bar->full[stage], 64, key0);   // features 64..127
@@ -381,6 +393,7 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
                     __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ pos_ws, float* __restrict__ pos_out,
                     unsigned long long* timebuf)
 {
+    ptx::pdl_launch_dependents();            // the streaming kernel may start its setup and its first queue-tile loads
     const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (timebuf && threadIdx.x == 0) {
         unsigned long long t;
@@ -459,6 +472,13 @@ int infonce_tc_nsplit(int B, long long K)
     return ns;
 }
 
+bool pdl_enabled()
+{
+    static int on = -1;                               // GCA_NO_PDL=1 turns programmatic dependent launch off (A/B timing)
+    if (on < 0) { const char* e = getenv("GCA_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
+    return on != 0;
+}
+
 unsigned long long* debug_timebuf()
 {
     const char* tb = getenv("GCA_TC_TIMEBUF");        // device address of a 32 * 1024 uint64 buffer (tools/tc_timeline.py)
@@ -486,10 +506,16 @@ int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t
     const TcDebug dbg = tc_debug_knobs();
     const bool want_acc = P.part_acc != nullptr;
     dim3 grid(P.nsplit, P.Bpad / TC_BM);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;    // PDL: overlap this kernel's setup with the prep kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
 #define GCA_TC_LAUNCH(ACC, FIX) do { \
         auto kern = infonce_tc_kernel<ACC, FIX>; \
         GCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES)); \
-        kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap, qmap, P, dbg); } while (0)
+        GCA_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, qmap, P, dbg)); } while (0)
     if (want_acc) { if (fixed_max) GCA_TC_LAUNCH(true, true); else GCA_TC_LAUNCH(true, false); }
     else          { if (fixed_max) GCA_TC_LAUNCH(false, true); else GCA_TC_LAUNCH(false, false); }
 #undef GCA_TC_LAUNCH
