@@ -42,38 +42,63 @@ def peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line): started before the warm-up so the first
+    samples exist when the timed region begins; only samples whose timestamp falls inside [mark_start, mark_end] count."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
+    def wait_first_sample(self, timeout=5.0):
+        t = time.time()
+        while self.p is not None and time.time() - t < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.02)
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        rows = [[c.strip() for c in r.split(",")] for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 9]
         os.unlink(self.f.name)
         if not rows:
             return out
-        sm = sorted(float(r[1]) for r in rows)
+
+        def ts(r):
+            try:
+                return datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                return None
+        inside = [r for r in rows if self.t0 is not None and ts(r) is not None and self.t0 - 0.02 <= ts(r) <= self.t1 + 0.02]
+        use = inside if inside else rows
+        sm = sorted(float(r[2]) for r in use)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any("Active" == r[5 + i].strip() and "Not" not in r[5 + i] for r in rows)]
-        out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(rows[0][2]), reasons=reasons, samples=len(rows),
-                   power_w_max=max(float(r[3]) for r in rows))
+        reasons = [n for i, n in enumerate(names) if any(r[6 + i] == "Active" for r in use)]
+        out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(use[0][3]), reasons=reasons, samples=len(use),
+                   samples_in_timed_region=len(inside), power_w_max=max(float(r[4]) for r in use))
         return out
 
 
@@ -173,12 +198,13 @@ def run_single(args):
     def one(i):
         steps_g[i % POOL].step()
 
+    sampler = ClockSampler(0)
     for i in range(args.warmup):
         flush.fill_(i & 1)
         one(i)
-    sampler = ClockSampler(0)
-    launches0 = 0
+    sampler.wait_first_sample()
     torch.cuda.synchronize()
+    sampler.mark_start()
     t0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 1)                                 # L2 flush between timed iterations (not inside the events)
@@ -187,6 +213,7 @@ def run_single(args):
         ev[i][1].record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    sampler.mark_end()
     clocks = sampler.stop()
     dev_ms = sorted(a.elapsed_time(b) for a, b in ev)
     ms_per_step = sum(dev_ms) / len(dev_ms)
@@ -198,7 +225,8 @@ def run_single(args):
     g0 = steps_g[0]
     host_out = torch.empty_like(g0.outputs, device="cpu").pin_memory()
     e2e_t = []
-    for i in range(args.warmup + args.steps):
+    e2e_steps = min(args.steps, 2000)
+    for i in range(args.warmup + e2e_steps):
         flush.fill_(i & 1)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
@@ -272,101 +300,178 @@ def run_single(args):
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm, N > 1
-def run_sharded(args, rank, world, local_rank):
-    """Weak scaling: 256 rows per GPU, the 65536-row queue sharded along K; per-shard partials merged with NCCL."""
+def run_multi(args, rank, world, local_rank):
+    """Weak scaling, the reference's own data parallelism: every GPU scores its 256 rows against a replicated 65536-row
+    queue; the keys of all ranks are all-gathered (NCCL over NVLink, overlapped with the queue sweep) and enqueued on every
+    replica.  value = n_gpus x steps/s.  The K-sharded variant (queue 2^20 x 128 split over the ranks, BASELINE config 4) is
+    timed in the same run and reported under "sharded_k1m"."""
     import torch
     import torch.distributed as dist
     import gca_b200
     from gca_b200 import _lib
-    from gca_b200.dist import ShardedRGBMoCo
+    from gca_b200.graphed import GraphedReplicaStep
     lib = _lib.load()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(1)
-    moco = ShardedRGBMoCo(D, K=K, T=T, queue_dtype="bf16", device=dev)
-    crit = gca_b200.NCESoftmaxLoss()
-    batches = synthetic_batches(100 + rank, POOL, B, 0, device=dev)
+    torch.manual_seed(1)                                     # identical queue on every replica (upstream: broadcast from rank 0)
+    moco = gca_b200.RGBMoCo(D, K=K, T=T, queue_dtype="bf16").to(dev)
+    dist.broadcast(moco.memory, 0)
+    pool = 4
+    batches = synthetic_batches(100 + rank, pool, B, 0, device=dev)
+    state = torch.tensor([0, 0], dtype=torch.int64, device=dev)
+    steps_g = []
+    for i in range(pool):
+        s = GraphedReplicaStep(moco, B, state=state)
+        s.inputs[:2 * B].copy_(batches[i])
+        steps_g.append(s)
+    graphed = True
+    try:
+        for s in steps_g:
+            s.capture()
+    except Exception as e:                                   # NCCL capture unavailable: run the same work eagerly
+        graphed = False
+        if rank == 0:
+            print("CUDA-graph capture of the NCCL step failed (%s); running eagerly" % e, file=sys.stderr)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def one(i):
-        pk = batches[i % POOL]
-        q = pk[:B].clone().requires_grad_(True)
-        out, labels = moco(q, pk[B:2 * B])
-        loss = crit(out)
-        loss.backward()
-        hits = ((out.rank < 1).sum(), (out.rank < 5).sum())
-        return loss, q.grad, hits
+        s = steps_g[i % pool]
+        if graphed:
+            s.step()
+        else:
+            s._enqueue_work(st)
+            moco.index = (moco.index + s.N) % K
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for i in range(args.warmup):
         flush.fill_(i & 1)
         one(i)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_first_sample()
     n0 = lib.gca_launch_count()
     torch.cuda.synchronize()
     dist.barrier()
+    if sampler:
+        sampler.mark_start()
     t0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 1)
         ev[i][0].record()
-        loss, _, _ = one(args.warmup + i)
+        one(args.warmup + i)
         ev[i][1].record()
     torch.cuda.synchronize()
     dist.barrier()
     wall = time.perf_counter() - t0
-    launches = int(lib.gca_launch_count() - n0)
+    if sampler:
+        sampler.mark_end()
     clocks = sampler.stop() if sampler else None
+    launches = (steps_g[0].launches_per_step * args.steps) if graphed else int(lib.gca_launch_count() - n0)
     tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev)
     dist.all_reduce(tot, op=dist.ReduceOp.MAX)              # max over ranks of the device-timed total
     ms_per_step = float(tot) / args.steps
-    # end to end: host q, k per rank -> H2D -> step -> D2H loss + dq, synchronised per step
-    host_in = synthetic_batches(200 + rank, POOL, B, 0, pin=True)
-    dev_in = torch.empty_like(batches[0])
+    loss_last = float(steps_g[(args.warmup + args.steps - 1) % pool].loss)
+    # replicas must stay bit-identical: compare a checksum of the queue and the ring pointer across ranks
+    chk = torch.stack([moco.memory.float().sum().double(), state[0].double()])
+    chk_all = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(chk_all, chk)
+    consistent = all(torch.equal(c, chk_all[0]) for c in chk_all)
+
+    # end to end: pinned host q|k per rank -> H2D -> step -> D2H loss|hits|dq, synchronised per step
+    host_in = synthetic_batches(200 + rank, pool, B, 0, pin=True)
+    g0 = steps_g[0]
+    host_out = torch.empty_like(g0.outputs, device="cpu").pin_memory()
     e2e_t = []
-    for i in range(args.warmup + args.steps):
+    e2e_steps = min(args.steps, 1000)
+    for i in range(args.warmup + e2e_steps):
         flush.fill_(i & 1)
         torch.cuda.synchronize()
         dist.barrier()
         t1 = time.perf_counter()
-        dev_in.copy_(host_in[i % POOL], non_blocking=True)
-        q = dev_in[:B].clone().requires_grad_(True)
-        out, _ = moco(q, dev_in[B:2 * B])
-        l = crit(out)
-        l.backward()
-        res = (l.detach().cpu(), q.grad.cpu())
+        g0.inputs[:2 * B].copy_(host_in[i % pool], non_blocking=True)
+        if graphed:
+            g0.step()
+        else:
+            g0._enqueue_work(st)
+        host_out.copy_(g0.outputs, non_blocking=True)
         torch.cuda.synchronize()
         if i >= args.warmup:
             e2e_t.append(time.perf_counter() - t1)
     e2e = torch.tensor([sum(e2e_t) / len(e2e_t) * 1e3], device=dev)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+
+    sharded = time_sharded_k1m(rank, world, dev, flush) if not args.no_sharded else None
     if rank == 0:
         line = {
             "metric": METRIC, "value": world * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "moco_head_B256perGPU_K65536sharded_d128", "B_per_gpu": B, "B_global": B * world, "K": K, "d": D,
-                       "T": T, "queue_dtype": "bf16", "parallelism": "queue sharded along K over %d ranks; NCCL all-gather of q,k and "
-                       "of the (max,sum,count) partials, reduce-scatter of the gradient accumulator" % world,
-                       "cuda_graph": False, "l2": "flushed between timed iterations (256 MiB write, outside the per-step events)",
+            "config": {"workload": "moco_head_B256perGPU_K65536_d128_replicas", "B_per_gpu": B, "B_global": B * world, "K": K, "d": D,
+                       "T": T, "queue_dtype": "bf16", "enqueued_rows_per_step": B * world,
+                       "parallelism": "dp%d: replicated queue (the reference's scheme); NCCL all-gather of the keys overlapped with "
+                                      "the queue sweep; every replica enqueues all %d keys" % (world, B * world),
+                       "cuda_graph": graphed, "l2": "flushed between timed iterations (256 MiB write, outside the per-step events)",
                        "timing": "per-step CUDA events, total = max over ranks; value = n_gpus * 1000 / ms_per_step "
                                  "(each global step processes n_gpus x 256 rows)"},
-            "wall_s_total": wall, "loss_last": float(loss), "clocks": clocks,
-            "e2e": {"value": world * 1e3 / float(e2e), "unit": UNIT, "h2d_bytes_per_step": 2 * B * D * 4, "d2h_bytes_per_step": B * D * 4 + 4,
-                    "ms_per_step": float(e2e)},
+            "wall_s_total": wall, "loss_last": loss_last, "replicas_consistent": consistent, "clocks": clocks,
+            "e2e": {"value": world * 1e3 / float(e2e), "unit": UNIT, "h2d_bytes_per_step": 2 * B * D * 4,
+                    "d2h_bytes_per_step": g0.outputs.numel() * 4, "ms_per_step": float(e2e)},
             "gpu_launches": launches,
+            "sharded_k1m": sharded,
         }
         print(json.dumps(line), flush=True)
-    dist.destroy_process_group()
+    # Leave without tearing the communicator down: destroy_process_group() after NCCL work was captured into CUDA graphs
+    # has been seen to block forever (round 1, 2 GPUs); every rank is past its last collective here.
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
+def time_sharded_k1m(rank, world, dev, flush, steps=30, warmup=5):
+    """BASELINE config 4: queue 2^20 x 128 (bf16) split along K over the ranks, 256 rows per GPU; per-shard online-softmax
+    partials merged with NCCL (gca_b200.dist.ShardedRGBMoCo).  Eager (not graph-captured); device time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import gca_b200
+    from gca_b200.dist import ShardedRGBMoCo
+    K1 = 1 << 20
+    torch.manual_seed(1)
+    moco = ShardedRGBMoCo(D, K=K1, T=T, queue_dtype="bf16", device=dev)
+    crit = gca_b200.NCESoftmaxLoss()
+    batches = synthetic_batches(300 + rank, 2, B, 0, device=dev)
+    ev = []
+    for i in range(warmup + steps):
+        flush.fill_(i & 1)
+        pk = batches[i % 2]
+        q = pk[:B].clone().requires_grad_(True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out, _ = moco(q, pk[B:2 * B])
+        crit(out).backward()
+        b.record()
+        if i >= warmup:
+            ev.append((a, b))
+    torch.cuda.synchronize()
+    tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev)
+    dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms = float(tot) / steps
+    flops = 4.0 * (B * world) * (K1 / world) * D
+    return {"K": K1, "rows_per_gpu": B, "rows_global": B * world, "shard_rows": K1 // world, "ms_per_step": ms,
+            "global_rows_per_s": B * world / ms * 1e3, "per_gpu_tflops": flops / (ms * 1e-3) / 1e12, "cuda_graph": False}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the extra K-sharded 2^20-row measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -375,7 +480,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
     if world > 1:
-        return run_sharded(args, rank, world, local_rank)
+        return run_multi(args, rank, world, local_rank)
     if args.gpus > 1:
         print("bench.py --gpus %d must be launched with torch.distributed.run (one rank per GPU)" % args.gpus, file=sys.stderr)
         sys.exit(2)

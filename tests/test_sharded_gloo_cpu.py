@@ -1,0 +1,107 @@
+"""CPU, world_size 2 (gloo): the host-side orchestration of the K-sharded queue (gca_b200.dist.ShardedRGBMoCo):
+gather of q / k, all-gather of the per-shard partials, combine, reduce-scatter, finish, sharded enqueue ownership and the
+replicated ring pointer.  The four compute steps are injected from the oracle here (the product binds them to the CUDA
+library); the same module runs over NCCL on the GPU box (bench.py --gpus N)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN, PKG, ROOT
+
+
+class OracleCompute(object):
+    """Drop-in for gca_b200.dist.ShardCompute computing on CPU tensors with the oracle (TEST ONLY)."""
+
+    def shard_fwd(self, q_all, k_all, shard, T, algo, want_grad):
+        import oracle
+        pos = (q_all * k_all).sum(1) / T
+        m, s, cnt = oracle.lse_partials(q_all, shard, T, pos)
+        stats = torch.stack([m, s, cnt.to(torch.int32).view(torch.float32)])          # count travels as raw bits
+        lg = (q_all @ shard.float().t()) / T
+        acc = torch.exp(lg - m[:, None]) @ shard.float() if want_grad else None
+        return pos, stats, acc
+
+    def shard_combine(self, all_stats, rank_id, pos, acc):
+        import oracle
+        ms, ss = all_stats[:, 0], all_stats[:, 1]
+        cnt = all_stats[:, 2].contiguous().view(torch.int32).sum(0).to(torch.int32)
+        lse = oracle.merge_partials(ms, ss, pos)
+        if acc is not None:
+            acc.mul_(torch.exp(ms[rank_id] - lse)[:, None])
+        return lse, lse - pos, cnt
+
+    def shard_finish(self, acc_loc, k_loc, pos_loc, lse_loc, loss_rows_loc, T):
+        B = pos_loc.shape[0]
+        dq = None
+        if acc_loc is not None:
+            dq = ((torch.exp(pos_loc - lse_loc) - 1)[:, None] * k_loc + acc_loc) / (T * B)
+        return dq, loss_rows_loc.mean()
+
+    def enqueue(self, shard, keys, index, K, k_begin):
+        from oracle.ring import enqueue_sharded
+        return enqueue_sharded(shard, keys, index, K, k_begin)
+
+
+def _worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from gca_b200.dist import ShardedRGBMoCo
+    from gca_b200.memory.losses import NCESoftmaxLoss
+    g = dict(np.load(os.path.join(GOLDEN, "infonce_small.npz")))
+    K, d, T = 256, 128, float(g["T"])
+    torch.manual_seed(100 + rank)                     # ranks draw DIFFERENT queues; rank 0's must win (train...:233-242)
+    moco = ShardedRGBMoCo(d, K=K, T=T, compute=OracleCompute())
+    torch.manual_seed(100)
+    full0 = torch.nn.functional.normalize(torch.randn(K, d))
+    Ks = K // world
+    assert torch.equal(moco.memory, full0[rank * Ks:(rank + 1) * Ks])
+    # replace the queue by the golden one so the reference's own numbers apply
+    moco.memory.copy_(torch.from_numpy(g["memory_before"])[rank * Ks:(rank + 1) * Ks])
+    ref_mem = torch.from_numpy(g["memory_before"]).clone()
+    ref_idx = 0
+    crit = NCESoftmaxLoss()
+    B_loc = 8 // world
+    for st in range(int(g["steps"])):
+        q_all, k_all = torch.from_numpy(g[f"q{st}"]), torch.from_numpy(g[f"k{st}"])
+        q = q_all[rank * B_loc:(rank + 1) * B_loc].clone().requires_grad_(True)
+        k = k_all[rank * B_loc:(rank + 1) * B_loc]
+        out, labels = moco(q, k)                                   # local rows in, keys gathered inside
+        loss = crit(out)
+        loss.backward()
+        # what ONE replica of the reference computes for its local rows against the full (replicated) queue
+        o = oracle.infonce_step(q.detach(), k, ref_mem.clone(), 0, T)
+        assert abs(float(loss) - float(o["loss"])) <= 1e-5 * abs(float(o["loss"])), (float(loss), float(o["loss"]))
+        assert torch.allclose(q.grad, o["dq"], rtol=1e-4, atol=1e-8)
+        assert torch.equal(out.rank.long(), o["rank"])
+        assert labels.shape == (B_loc,) and out.shape == (B_loc, K + 1)
+        ref_idx = oracle.enqueue(ref_mem, k_all, ref_idx)           # every replica enqueues the gathered keys
+        assert moco.index == ref_idx == int(g[f"index_after{st}"])
+        assert torch.equal(moco.memory, ref_mem[rank * Ks:(rank + 1) * Ks])     # each rank wrote exactly the slots it owns
+    full = moco.gather_full_queue()
+    assert torch.equal(full, torch.from_numpy(g["memory_after"]))
+    # wrap-around with pre-gathered keys passed by the caller (all_k=...), pointer near the end of the ring
+    moco.index = ref_idx = K - 5
+    keys = torch.nn.functional.normalize(torch.randn(12, d, generator=torch.Generator().manual_seed(7)))
+    q = torch.from_numpy(g["q0"])[rank * B_loc:(rank + 1) * B_loc].clone().requires_grad_(True)
+    k = torch.from_numpy(g["k0"])[rank * B_loc:(rank + 1) * B_loc]
+    with pytest.raises(ValueError):
+        moco(q, k, all_k=keys[:3])                                  # gathered keys must cover every rank's rows
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_sharded_moco_world2(tmp_path):
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))

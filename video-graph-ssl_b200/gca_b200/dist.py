@@ -148,6 +148,8 @@ class ShardedRGBMoCo(nn.Module):
 
     def forward(self, q, k, all_k=None):
         k = k.detach()
+        if all_k is not None and all_k.shape[0] != self.world * q.shape[0]:
+            raise ValueError("all_k must hold the keys of every rank (%d rows), got %d" % (self.world * q.shape[0], all_k.shape[0]))
         src = all_k.detach() if all_k is not None else k
         loss, loss_rows, lse, pos, rank_gt, k_all = _ShardedInfoNCE.apply(q, src, self.memory, self)
         with torch.no_grad():

@@ -98,3 +98,34 @@ class GraphedMoCoStep(object):
         self.graph.replay()
         self.moco.index = (self.moco.index + self.N) % self.K
         return self.loss
+
+
+class GraphedReplicaStep(GraphedMoCoStep):
+    """The same captured step for data-parallel replicas (the reference's own parallelisation: a replicated queue that
+    every rank updates with the keys of ALL ranks, train_video_contrast_dis.py:222 + mem_moco.py:81-83).
+
+    The key all-gather (NCCL over NVLink) is captured on a side stream and overlaps the queue-streaming kernel, which
+    only needs the LOCAL keys for its positives; the gathered keys are first needed by the enqueue at the end of the step.
+    Every rank must hold an identical queue and ring pointer (same seed or a broadcast, as upstream)."""
+
+    def __init__(self, moco, batch, group=None, algo=None, state=None):
+        import torch.distributed as dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        super(GraphedReplicaStep, self).__init__(moco, batch, n_enqueue=batch * self.world, algo=algo, state=state)
+        self.side = torch.cuda.Stream(moco.memory.device)
+
+    def _enqueue_work(self, stream):
+        import torch.distributed as dist
+        m = self.moco
+        dev = m.memory.device
+        main = torch.cuda.current_stream(dev)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            dist.all_gather_into_tensor(self.all_k, self.k, group=self.group)
+        _lib.call("gca_infonce_fwd", ptr(self.q), ptr(self.k), ptr(m.memory), self.qd, self.B, self.K, self.d, 1.0 / m.T,
+                  _lib.ALGO[self.algo], ptr(self.loss), ptr(self.loss_rows), ptr(self.lse), ptr(self.pos), ptr(self.rank),
+                  ptr(self.hits), ptr(self.dq), None, ptr(self.ws), self.ws.numel(), stream)
+        main.wait_stream(self.side)
+        _lib.call("gca_enqueue_devptr", ptr(m.memory), self.qd, self.K, 0, self.K, self.d, ptr(self.all_k), self.N,
+                  ptr(self.state), stream)
