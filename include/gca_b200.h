@@ -160,14 +160,14 @@ int gca_infonce_shard_finish(const float* acc, const float* k, const float* pos_
  * --------------------------------------------------------------------------------------------------------- */
 int gca_graph_fwd(const float* gq, const float* gk, int Cq, int S, const float* support, int C, int HW,
                   int T, int B, const float* u, float alpha, int max_hop, float temperature, unsigned flags,
-                  float* sim, float* adj, float* s, float* y, void* stream);
+                  float* sim, float* adj, float* s, float* y, void* workspace, size_t workspace_bytes, void* stream);
 
 int gca_graph_bwd(const float* gq, const float* gk, int Cq, int S, const float* support, int C, int HW,
                   int T, int B, const float* sim, const float* adj, const float* s, const float* dy,
                   float alpha, int max_hop, float temperature, unsigned flags,
                   float* d_gq, float* d_gk, float* d_support,
                   void* workspace, size_t workspace_bytes, void* stream);
-/* scratch for gca_graph_bwd ([B, T, T] fp32 d_logit; only touched for large feature maps) */
+/* scratch for gca_graph_fwd / gca_graph_bwd (d_logit + per-chunk pair-dot partials; only touched for large feature maps) */
 size_t gca_graph_workspace_bytes(int B, int T);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -65,7 +65,7 @@ def test_argument_validation_without_gpu(lib):
     args[7] = 0.0
     assert lib.gca_infonce_fwd(*args) == -1                                         # inv_T
     # graph: T range and flags
-    g = [one, one, 4, 1, one, 8, 1, 40, 2, one, 0.5, 3, 1.0, 0, one, one, one, one, null]
+    g = [one, one, 4, 1, one, 8, 1, 40, 2, one, 0.5, 3, 1.0, 0, one, one, one, one, one, 1 << 20, null]
     assert lib.gca_graph_fwd(*g) == -1
     g[7] = 4
     g[13] = 5
@@ -79,7 +79,7 @@ def test_argument_validation_without_gpu(lib):
 def test_workspace_sizes(lib):
     assert lib.gca_infonce_workspace_bytes(256, 65536, 128, 1, 0) >= 74 * 256 * 128 * 4
     assert lib.gca_infonce_workspace_bytes(0, 65536, 128, 1, 0) == 0
-    assert lib.gca_graph_workspace_bytes(128, 8) == 128 * 64 * 4
+    assert lib.gca_graph_workspace_bytes(128, 8) >= 128 * 64 * 4
     assert lib.gca_negcos_workspace_bytes(128, 1024) >= 128 * 4
     assert lib.gca_sim_topk_workspace_bytes(10, 20, 8, 5) >= 10 * 20 * 4
 

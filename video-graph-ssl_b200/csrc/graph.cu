@@ -127,12 +127,14 @@ static int check_graph_args(const char* fn, int Cq, int S, int C, int HW, int T,
 
 extern "C" size_t gca_graph_workspace_bytes(int B, int T)
 {
-    return (B > 0 && T > 0) ? (size_t)B * T * T * sizeof(float) : 0;
+    // [B, T, T] d_logit + the per-chunk pair-dot partials of the split path
+    return (B > 0 && T > 0) ? ((size_t)B * T * T + gca::graph_split_scratch_floats(B, T)) * sizeof(float) : 0;
 }
 
 extern "C" int gca_graph_fwd(const float* gq, const float* gk, int Cq, int S, const float* support, int C, int HW,
                              int T, int B, const float* u, float alpha, int max_hop, float temperature, unsigned flags,
-                             float* sim, float* adj, float* s, float* y, void* stream)
+                             float* sim, float* adj, float* s, float* y, void* workspace, size_t workspace_bytes,
+                             void* stream)
 {
     using namespace gca;
     GCA_CHECK_ARG(gq && gk && support && u && sim && adj && s && y, "gca_graph_fwd: null pointer");
@@ -144,7 +146,9 @@ extern "C" int gca_graph_fwd(const float* gq, const float* gk, int Cq, int S, co
     fill_theta(a.th, alpha, max_hop);
     cudaStream_t st = (cudaStream_t)stream;
     if (use_fused(a)) return graph_fwd_adj_launch(a, true, st);
-    rc = graph_fwd_adj_launch(a, false, st);
+    if (!workspace || workspace_bytes < gca_graph_workspace_bytes(B, T))
+        return set_err(GCA_ERR_WORKSPACE, "gca_graph_fwd: workspace of %zu bytes needed", gca_graph_workspace_bytes(B, T));
+    rc = graph_split_adj_launch(a, false, (float*)workspace + (size_t)B * T * T, st);
     if (rc != GCA_OK) return rc;
     AggJobs jobs{};
     jobs.T = T;
@@ -173,7 +177,7 @@ extern "C" int gca_graph_bwd(const float* gq, const float* gk, int Cq, int S, co
     if (!workspace || workspace_bytes < gca_graph_workspace_bytes(B, T))
         return set_err(GCA_ERR_WORKSPACE, "gca_graph_bwd: workspace of %zu bytes needed", gca_graph_workspace_bytes(B, T));
     a.dl = (float*)workspace;
-    rc = graph_bwd_adj_launch(a, false, st);
+    rc = graph_split_adj_launch(a, true, (float*)workspace + (size_t)B * T * T, st);
     if (rc != GCA_OK) return rc;
     AggJobs jobs{};
     jobs.T = T;

@@ -210,5 +210,7 @@ static inline int pick_tmax(int T) { return T <= 4 ? 4 : T <= 8 ? 8 : T <= 16 ? 
 void fill_theta(GraphTheta& th, float alpha, int max_hop);
 int graph_agg_launch(const AggJobs& jobs, int njobs, int B, cudaStream_t st);   // graph.cu
 int graph_bwd_adj_launch(const GraphArgs& a, bool fused, cudaStream_t st);   // graph_bwd.cu
+size_t graph_split_scratch_floats(int B, int T);                              // graph_split.cu
+int graph_split_adj_launch(const GraphArgs& a, bool bwd, float* scratch, cudaStream_t st);
 
 }  // namespace gca

@@ -55,7 +55,8 @@ SIGNATURES = {
     "gca_infonce_shard_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                          c_void_p, c_void_p, c_void_p]),
     "gca_graph_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                              c_float, c_int, c_float, c_uint, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                              c_float, c_int, c_float, c_uint, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                              c_void_p]),
     "gca_graph_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_float, c_uint,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -161,8 +161,9 @@ class _GraphCore(torch.autograd.Function):
         adj = torch.empty_like(sim)
         s = torch.empty_like(sim)
         y = torch.empty_like(support)
+        ws = workspace(dev, int(_lib.load().gca_graph_workspace_bytes(B, T)), "graph")
         _lib.call("gca_graph_fwd", ptr(gq), ptr(gk), Cq, S, ptr(support), C, HW, T, B, ptr(u), float(alpha), int(max_hop),
-                  float(temperature), 0, ptr(sim), ptr(adj), ptr(s), ptr(y), _stream(gq))
+                  float(temperature), 0, ptr(sim), ptr(adj), ptr(s), ptr(y), ptr(ws), ws.numel(), _stream(gq))
         ctx.save_for_backward(gq, gk, support, sim, adj, s)
         ctx.cfg = (float(alpha), int(max_hop), float(temperature))
         ctx.mark_non_differentiable(sim, adj, s)
