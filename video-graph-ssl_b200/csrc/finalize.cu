@@ -232,27 +232,29 @@ infonce_finalize_kernel(const FinalizeParams F)
     }
 
     if (F.timebuf && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.timebuf[32 * 400 + 4 * blockIdx.x + 2] = t; }
-    if (kMode == FIN_FULL && (F.loss_mean != nullptr || F.top_hits != nullptr)) {
-        if (last_block_ticket(F.counter, (unsigned int)F.B, &flag)) {
-            if (F.timebuf && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.timebuf[32 * 1000 + 6] = t; }
-            const float mean = block_mean_fixed(F.loss_rows, F.B, red);
-            int h1 = 0, h5 = 0;                                   // integer counts: exact, order-independent
-            for (int i = tid; i < F.B; i += FIN_THREADS) { const int r = __ldcg(F.rank_gt + i); h1 += (r < 1); h5 += (r < 5); }
-            h1 = warp_sum_i(h1); h5 = warp_sum_i(h5);
-            __shared__ int hit_s[2][FIN_THREADS / 32];
-            if (lane == 0) { hit_s[0][warp] = h1; hit_s[1][warp] = h5; }
-            __syncthreads();
-            if (tid == 0) {
-                int t1 = 0, t5 = 0;
-                for (int w = 0; w < FIN_THREADS / 32; ++w) { t1 += hit_s[0][w]; t5 += hit_s[1][w]; }
-                if (F.loss_mean) *F.loss_mean = mean;
-                if (F.top_hits) { F.top_hits[0] = t1; F.top_hits[1] = t5; }
-                *F.counter = 0u;
-                if (F.timebuf) {
-                    unsigned long long t;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                    F.timebuf[32 * 1000 + 1] = t;
-                }
+    // Mean loss and top-k hit counts without a second pass over the rows: every row block adds its loss as a 64-bit
+    // fixed-point integer (2^-36 resolution; integer addition is associative, so the sum is exact and order-independent --
+    // deterministic) and its two hit bits to accumulators in the control block, then takes a ticket; the last ticket holder
+    // converts and re-arms.  counter layout (gca_common.cuh): [0] ticket, [2..3] loss accumulator, [4] top-1, [5] top-5.
+    if (kMode == FIN_FULL && (F.loss_mean != nullptr || F.top_hits != nullptr) && tid == 0) {
+        const float lrow = row_stat[0] - row_stat[1];                      // lse - pos of this row
+        unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(F.counter + 2);
+        atomicAdd(acc64, (unsigned long long)__double2ll_rn((double)lrow * 68719476736.0));   // exact: ulp(lrow) >= 2^-36
+        const int r = F.rank_gt[b];
+        if (r < 1) atomicAdd(F.counter + 4, 1u);
+        if (r < 5) atomicAdd(F.counter + 5, 1u);
+        __threadfence();
+        const unsigned int t = atomicAdd(F.counter, 1u);
+        if (t == (unsigned int)F.B - 1) {
+            __threadfence();
+            const long long tot = (long long)atomicAdd(acc64, 0ull);
+            if (F.loss_mean) *F.loss_mean = (float)((double)tot / 68719476736.0 / (double)F.B);
+            if (F.top_hits) { F.top_hits[0] = (int)atomicAdd(F.counter + 4, 0u); F.top_hits[1] = (int)atomicAdd(F.counter + 5, 0u); }
+            F.counter[0] = 0u; F.counter[2] = 0u; F.counter[3] = 0u; F.counter[4] = 0u; F.counter[5] = 0u;
+            if (F.timebuf) {
+                unsigned long long tt;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+                F.timebuf[32 * 1000 + 1] = tt;
             }
         }
     }

@@ -43,7 +43,7 @@ infonce_ffma_kernel(const InfoNceStreamParams P)
     const int split = blockIdx.x, row0 = blockIdx.y * BM;
     const bool want_acc = (P.part_acc != nullptr);
 
-    if (split == 0 && blockIdx.y == 0 && tid == 0) *P.counter = 0u;     // re-arm the finalize ticket
+    if (split == 0 && blockIdx.y == 0 && tid == 0) { for (int w = 0; w < 6; ++w) P.counter[w] = 0u; }     // re-arm the finalize control block
 
     // positive logit of each row, fp32, fixed summation order (identical in every split)
     for (int r = warp; r < BM; r += 8) {

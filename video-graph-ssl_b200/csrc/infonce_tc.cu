@@ -24,10 +24,10 @@ constexpr int TC_THREADS = 320;                           // 8 softmax warps (2 
 constexpr int TC_WARP_TMA = 8, TC_WARP_MMA = 9;
 constexpr uint32_t TM_COLS = 512;
 constexpr int TC_SUB = 64;                                // keys per softmax step: each 128-key tile feeds 64 keys to each group
-// TMEM columns per softmax group g: two 64-column S buffers (P is written back over the first 32 columns of the buffer
-// it came from) and a 128-column O accumulator: 256 columns per group, 512 in all
-__host__ __device__ constexpr uint32_t tm_s(int g, int b) { return (uint32_t)(g * 256 + b * 64); }
-__host__ __device__ constexpr uint32_t tm_o(int g) { return (uint32_t)(g * 256 + 128); }
+// TMEM columns: two 128-column S buffers (one 128-key tile each; group g reads columns [64g, 64g+64) and writes its P back
+// over the first 32 of them) and one 128-column O accumulator per softmax group: 512 columns in all
+__host__ __device__ constexpr uint32_t tm_s(int g, int b) { return (uint32_t)(b * 128 + g * 64); }
+__host__ __device__ constexpr uint32_t tm_o(int g) { return (uint32_t)(256 + g * 128); }
 constexpr float TC_RESCALE_LOG2 = 8.f;                    // rescale O only when the row max grows by > 2^8
 constexpr int TC_OST_STRIDE = 132;                        // fp32 O staging row (128 + 4 floats): conflict-free row writes
 constexpr size_t TC_QTILE_BYTES = (size_t)TC_BM * TC_D * 2;   // bf16 q block, same swizzled layout as a queue tile
@@ -52,7 +52,7 @@ __device__ __forceinline__ void tc_cstamp(const TcDebug& dbg, int slot)         
 struct TcBarriers {
     uint64_t full[TC_STAGES];     // TMA landed a queue tile
     uint64_t empty[TC_STAGES];    // both MMAs that read the tile have completed
-    uint64_t s_full[4];           // [group * 2 + buffer] S = q Q^T of a 64-key step is in TMEM
+    uint64_t s_full[2];           // [buffer] S = q Q^T of a 128-key tile is in TMEM (both groups wait on it)
     uint64_t p_full[4];           // [group * 2 + buffer] softmax finished with that S buffer (and wrote P over it)
     uint64_t o_done[2];           // per softmax group: one phase per completed O += P Q
     uint64_t acc_final;           // last O += P Q completed
@@ -85,8 +85,8 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         prefetch_tmap(&tmap);
         prefetch_tmap(&qmap);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar->full[s], 1); mbar_init(&bar->empty[s], 1); }
-        for (int b = 0; b < 4; ++b) { mbar_init(&bar->s_full[b], 1); mbar_init(&bar->p_full[b], 128); }
-        for (int b = 0; b < 2; ++b) mbar_init(&bar->o_done[b], 1);
+        for (int b = 0; b < 4; ++b) mbar_init(&bar->p_full[b], 128);
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar->s_full[b], 1); mbar_init(&bar->o_done[b], 1); }
         mbar_init(&bar->acc_final, 1);
         mbar_init(&bar->q_ready, 1);
         fence_barrier_init();
@@ -116,7 +116,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         pdl_wait();                                                   // prep kernel results (pos_ws) are visible from here
         const float pos_nat0 = P.pos_ws[row];                         // natural-log units (q.k / T); 0 for padding rows
         const float pos_dot = pos_nat0 * P.T_;                        // the raw dot product the S tile is compared with
-        if (split == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.counter = 0u;      // re-arm the finalize ticket
+        if (split == 0 && blockIdx.y == 0 && threadIdx.x == 0) { for (int w = 0; w < 6; ++w) P.counter[w] = 0u; }      // re-arm the finalize control block
         if (split == 0 && g == 0 && valid && P.logits_out) P.logits_out[(size_t)row * P.ld_logits] = pos_nat0;
         if (threadIdx.x == 0) tc_stamp(dbg, 3);
 
@@ -130,7 +130,8 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             const int sb = v & 1;
             const uint32_t s_addr = lane_addr + tm_s(g, sb);
             if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 16);
-            mbar_wait(&bar->s_full[g * 2 + sb], (v >> 1) & 1);
+            if (v == 0 && g == 1) named_barrier_sync(2, 256);
+            mbar_wait(&bar->s_full[sb], (v >> 1) & 1);
             tc_fence_after();
             if (threadIdx.x == 0 && v == 0) tc_stamp(dbg, 4);
             if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 17);
@@ -184,6 +185,9 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     }
                 }
             }
+            // Stagger the two groups by about half a step: group 1 starts only when group 0 is through its first scan, so one
+            // group's MUFU-bound exp sweep runs against the other's load / max phases instead of both colliding on the MUFU
+            if (v == 0) { if (g == 0) named_barrier_arrive(2, 256); }
             if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 19);
             // p = 2^(S c2 - m), row sum and rank count in one sweep (MUFU-bound: the compare/count instructions ride in
             // issue slots that would otherwise idle); four independent chains each, counts kept exact in fp32
@@ -276,28 +280,26 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     } else if (warp == TC_WARP_TMA) {
         // =============================================================== TMA producer
         if (lane == 0) {
-            // queue tiles do not depend on the prep kernel: get the first ones moving before waiting for it
+            // queue tiles do not depend on the prep kernel: get the first one moving before waiting for it
             const int pre = n < TC_STAGES ? n : TC_STAGES;
-            for (int i = 0; i < pre; ++i) {
-                uint8_t* dst = stages + (size_t)i * TC_STAGE_BYTES;
+            auto load_tile = [&](int i) {
+                const int stage = i % TC_STAGES;
+                uint8_t* dst = stages + (size_t)stage * TC_STAGE_BYTES;
                 const int key0 = (int)((t_begin + i) * TC_BN);
-                if (i == 0) tc_stamp(dbg, 9);
-                mbar_arrive_expect_tx(&bar->full[i], TC_STAGE_BYTES);
-                tma_load_2d(dst, &tmap, &bar->full[i], 0, key0);
-                tma_load_2d(dst + TC_HALF_BYTES, &tmap, &bar->full[i], 64, key0);
-            }
+                mbar_arrive_expect_tx(&bar->full[stage], TC_STAGE_BYTES);
+                tma_load_2d(dst, &tmap, &bar->full[stage], 0, key0);                     // features  0..63
+                tma_load_2d(dst + TC_HALF_BYTES, &tmap, &bar->full[stage], 64, key0);    // features 64..127
+            };
+            tc_stamp(dbg, 9);
+            load_tile(0);
             pdl_wait();                                                              // q_bf16 comes from the prep kernel
             mbar_arrive_expect_tx(&bar->q_ready, (uint32_t)TC_QTILE_BYTES);
             tma_load_2d(qtile, &qmap, &bar->q_ready, 0, row0);                       // features  0..63 of the 128 query rows
             tma_load_2d(qtile + TC_HALF_BYTES, &qmap, &bar->q_ready, 64, row0);      // features 64..127
+            for (int i = 1; i < pre; ++i) load_tile(i);
             for (int i = pre; i < n; ++i) {
-                const int stage = i % TC_STAGES;
-                mbar_wait(&bar->empty[stage], ((i / TC_STAGES) - 1) & 1);
-                uint8_t* dst = stages + (size_t)stage * TC_STAGE_BYTES;
-                const int key0 = (int)((t_begin + i) * TC_BN);
-                mbar_arrive_expect_tx(&bar->full[stage], TC_STAGE_BYTES);
-                tma_load_2d(dst, &tmap, &bar->full[stage], 0, key0);               // features  0..63
-                tma_load_2d(dst + TC_HALF_BYTES, &tmap, &bar->full[stage], 64, key0);   // features 64..127
+                mbar_wait(&bar->empty[i % TC_STAGES], ((i / TC_STAGES) - 1) & 1);
+                load_tile(i);
             }
         }
     } else {
@@ -306,17 +308,18 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         // Program order per iteration: S GEMM of tile i, then O GEMM of tile i-1 -- so the S GEMM of the next tile (other
         // group's buffer) is already queued while a group is still in its softmax sweep.
         const bool leader = elect_one();
-        constexpr uint32_t idesc_s = make_idesc_bf16(TC_BM, TC_SUB, 0, 0);  // S: A = q tile, B = 64 queue rows, both K-major
-        constexpr uint32_t idesc_o = make_idesc_bf16(TC_BM, TC_D, 0, 1);    // O: A = P (TMEM), B = the same rows, MN-major
+        constexpr uint32_t idesc_s = make_idesc_bf16(TC_BM, TC_BN, 0, 0);   // S: A = q tile, B = 128 queue rows, both K-major
+        constexpr uint32_t idesc_o = make_idesc_bf16(TC_BM, TC_D, 0, 1);    // O: A = P (TMEM), B = 64 of those rows, MN-major
         mbar_wait(&bar->q_ready, 0);
         tc_fence_after();
         if (leader) tc_stamp(dbg, 10);
         const uint32_t qbase = smem_u32(qtile);
 
-        // S GEMM of step v for group g: S_g[v & 1] = q . (rows [64g, 64g+64) of tile v)^T
-        auto issue_s = [&](int v, int g) {
-            const uint32_t sbase = smem_u32(stages + (size_t)(v % TC_STAGES) * TC_STAGE_BYTES) + g * (TC_SUB * 128);
-            const uint32_t d_tmem = tmem + tm_s(g, v & 1);
+        // S GEMM of tile v: S[v & 1] = q . tile^T, one 128 x 128 x 128 product for both softmax groups (a 64-key product
+        // per group would re-read the q tile from shared memory twice as often, and SS-mode MMAs are smem-bandwidth-bound)
+        auto issue_s = [&](int v) {
+            const uint32_t sbase = smem_u32(stages + (size_t)(v % TC_STAGES) * TC_STAGE_BYTES);
+            const uint32_t d_tmem = tmem + tm_s(0, v & 1);
             if (leader) {
 #pragma unroll
                 for (int kk = 0; kk < TC_D / 16; ++kk) {
@@ -326,29 +329,24 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     mma_ss(d_tmem, make_smem_desc_sw128(qbase + koff, 16, 1024), make_smem_desc_sw128(sbase + koff, 16, 1024),
                            idesc_s, kk > 0);
                 }
-                tc_commit(&bar->s_full[g * 2 + (v & 1)]);
+                tc_commit(&bar->s_full[v & 1]);
+                if (!kWantAcc) tc_commit(&bar->empty[v % TC_STAGES]);       // forward only: the tile is not needed again
             }
             __syncwarp();
         };
 
-        // prologue: the first two steps of both groups
+        // prologue: the first two tiles
         for (int v = 0; v < n && v < 2; ++v) {
             mbar_wait(&bar->full[v % TC_STAGES], 0);
             tc_fence_after();
             if (v == 0 && leader) tc_stamp(dbg, 11);
-            issue_s(v, 0);
-            issue_s(v, 1);
-            if (!kWantAcc) { if (leader) tc_commit(&bar->empty[v % TC_STAGES]); __syncwarp(); }
+            issue_s(v);
         }
         for (int v = 0; v < n; ++v) {
             const int stage = v % TC_STAGES;
-            if (v + 2 < n) {                                               // tile v+2 has to be in smem for the refills below
-                if (v == 3 && leader) tc_cstamp(dbg, 24);
-                mbar_wait(&bar->full[(v + 2) % TC_STAGES], ((v + 2) / TC_STAGES) & 1);
-                if (v == 3 && leader) tc_cstamp(dbg, 25);
-            }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
+                if (v == 3 && g == 0 && leader) tc_cstamp(dbg, 25);
                 mbar_wait(&bar->p_full[g * 2 + (v & 1)], (v >> 1) & 1);     // softmax of (g, v) done: P written / S consumed
                 tc_fence_after();
                 if (v == 3 && g == 0 && leader) tc_cstamp(dbg, 26);
@@ -369,13 +367,14 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     __syncwarp();
                 }
                 if (v == 3 && g == 0 && leader) tc_cstamp(dbg, 27);
-                // refill this group's S buffer (v & 1) with step v+2: queued behind the O GEMM that read P from it
-                if (v + 2 < n) {
-                    issue_s(v + 2, g);
-                    if (!kWantAcc && g == 1) { if (leader) tc_commit(&bar->empty[(v + 2) % TC_STAGES]); __syncwarp(); }
-                }
-                if (v == 3 && g == 0 && leader) tc_cstamp(dbg, 28);
             }
+            // refill S buffer (v & 1) with tile v+2: queued behind the two O GEMMs that read P from it
+            if (v + 2 < n) {
+                mbar_wait(&bar->full[(v + 2) % TC_STAGES], ((v + 2) / TC_STAGES) & 1);
+                tc_fence_after();
+                issue_s(v + 2);
+            }
+            if (v == 3 && leader) tc_cstamp(dbg, 28);
         }
     }
     if (threadIdx.x == 0) tc_stamp(dbg, 7);

@@ -50,6 +50,10 @@ __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ void named_barrier_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
