@@ -101,6 +101,8 @@ int gca_infonce_fwd(const float* q, const float* k, const void* queue, int dtype
  * caller advances its copy); `state` != NULL -> device-resident {pointer, ticket} as in gca_enqueue_devptr. */
 int gca_moco_step(const float* q, const float* k, void* queue, int dtype_queue, int B, long long K, int d, float inv_T,
                   int algo, const float* enqueue_keys, int N, long long index, long long* state,
+                  void* keys_ready_event /* cudaEvent_t or NULL: the stream waits on it before the enqueue launch, so a
+                                            key all-gather on another stream can overlap the queue sweep */,
                   float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt, int* top_hits,
                   float* dq_unit, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -143,7 +143,7 @@ extern "C" size_t gca_infonce_workspace_bytes(int B, long long K, int d, int dty
 static int infonce_fwd_impl(const char* fn, const float* q, const float* k, const void* queue, int dtype_queue, int B,
                             long long K, int d, float inv_T, int algo, float* loss_mean, float* loss_rows, float* lse,
                             float* pos_logit, int* rank_gt, int* top_hits, float* dq_unit, float* logits_out,
-                            const float* enq_keys, int enq_N, long long enq_index, long long* enq_state,
+                            const float* enq_keys, int enq_N, long long enq_index, long long* enq_state, void* keys_ready_event,
                             void* workspace, size_t workspace_bytes, void* stream)
 {
     using namespace gca;
@@ -164,6 +164,7 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
     F.part_acc = dq_unit ? ws.part_acc : nullptr;
     F.nsplit = ws.nsplit; F.Bpad = ws.Bpad; F.B = B; F.d = d; F.inv_T = inv_T; F.k = k; F.pos = pos_logit;
     F.lse = lse; F.loss_rows = loss_rows; F.rank_gt = rank_gt; F.dq = dq_unit; F.loss_mean = loss_mean; F.top_hits = top_hits;
+    if (keys_ready_event) GCA_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)keys_ready_event, 0));
     if (enq_keys) {
         F.enq_queue = const_cast<void*>(queue); F.enq_dtype = dtype_queue; F.enq_K = K; F.enq_keys = enq_keys; F.enq_N = enq_N;
         F.enq_index = enq_index; F.enq_state = enq_state;
@@ -177,19 +178,19 @@ extern "C" int gca_infonce_fwd(const float* q, const float* k, const void* queue
                                size_t workspace_bytes, void* stream)
 {
     return infonce_fwd_impl("gca_infonce_fwd", q, k, queue, dtype_queue, B, K, d, inv_T, algo, loss_mean, loss_rows, lse,
-                            pos_logit, rank_gt, top_hits, dq_unit, logits_out, nullptr, 0, 0, nullptr, workspace,
+                            pos_logit, rank_gt, top_hits, dq_unit, logits_out, nullptr, 0, 0, nullptr, nullptr, workspace,
                             workspace_bytes, stream);
 }
 
 extern "C" int gca_moco_step(const float* q, const float* k, void* queue, int dtype_queue, int B, long long K, int d,
                              float inv_T, int algo, const float* enqueue_keys, int N, long long index, long long* state,
-                             float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt, int* top_hits,
+                             void* keys_ready_event, float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt, int* top_hits,
                              float* dq_unit, void* workspace, size_t workspace_bytes, void* stream)
 {
     GCA_CHECK_ARG(enqueue_keys, "gca_moco_step: enqueue_keys is required");
     return infonce_fwd_impl("gca_moco_step", q, k, queue, dtype_queue, B, K, d, inv_T, algo, loss_mean, loss_rows, lse,
-                            pos_logit, rank_gt, top_hits, dq_unit, nullptr, enqueue_keys, N, index, state, workspace,
-                            workspace_bytes, stream);
+                            pos_logit, rank_gt, top_hits, dq_unit, nullptr, enqueue_keys, N, index, state, keys_ready_event,
+                            workspace, workspace_bytes, stream);
 }
 
 extern "C" int gca_infonce_partials(const float* q, const float* k, const void* queue, int dtype_queue, int B,

@@ -145,6 +145,7 @@ extern "C" int gca_graph_fwd(const float* gq, const float* gk, int Cq, int S, co
     a.max_hop = max_hop; a.inv_temp = 1.f / temperature; a.sim = sim; a.adj = adj; a.s = s; a.y = y;
     fill_theta(a.th, alpha, max_hop);
     cudaStream_t st = (cudaStream_t)stream;
+    if (graph_smem_fits(a, false)) return graph_smem_launch(a, false, st);
     if (use_fused(a)) return graph_fwd_adj_launch(a, true, st);
     if (!workspace || workspace_bytes < gca_graph_workspace_bytes(B, T))
         return set_err(GCA_ERR_WORKSPACE, "gca_graph_fwd: workspace of %zu bytes needed", gca_graph_workspace_bytes(B, T));
@@ -173,6 +174,7 @@ extern "C" int gca_graph_bwd(const float* gq, const float* gk, int Cq, int S, co
     a.dy = dy; a.d_gq = d_gq; a.d_gk = d_gk; a.d_support = d_support;
     fill_theta(a.th, alpha, max_hop);
     cudaStream_t st = (cudaStream_t)stream;
+    if (graph_smem_fits(a, true)) return graph_smem_launch(a, true, st);
     if (use_fused(a)) return graph_bwd_adj_launch(a, true, st);
     if (!workspace || workspace_bytes < gca_graph_workspace_bytes(B, T))
         return set_err(GCA_ERR_WORKSPACE, "gca_graph_bwd: workspace of %zu bytes needed", gca_graph_workspace_bytes(B, T));

@@ -90,7 +90,7 @@ __device__ __forceinline__ float edge_w(const GraphTheta& th, int i, int j, int 
 }
 
 // forward T x T element work: logits (smem) -> sim, adj, s (smem + global)
-__device__ static void adj_forward(float* lg /*in: logits, out: s*/, float* sim_s, float* adj_s, const float* __restrict__ u,
+__device__ static void adj_forward(float* lg /*in: logits, out: s*/, float* sim_s, float* adj_s, const float* u,
                             const GraphTheta& th, int T, int max_hop, float inv_temp,
                             float* sim_g, float* adj_g, float* s_g)
 {
@@ -105,7 +105,7 @@ __device__ static void adj_forward(float* lg /*in: logits, out: s*/, float* sim_
             const float sim = e / sum;                                  // F.softmax(dim=-1), :176
             const float adj = sim * edge_w(th, i, lane, max_hop);       // :204-210
             const float p  = fminf(fmaxf(adj, G_EPS), 1.f - G_EPS);     // clamp_probs
-            const float uc = fminf(fmaxf(__ldg(u + o), G_EPS), 1.f - G_EPS);
+            const float uc = fminf(fmaxf(u[o], G_EPS), 1.f - G_EPS);          // (u may live in shared memory)
             const float z = (logf(uc) - log1pf(-uc) + logf(p) - log1pf(-p)) * inv_temp;   // LogitRelaxedBernoulli.rsample
             const float s = 1.f / (1.f + expf(-z));                     // SigmoidTransform
             sim_s[o] = sim; adj_s[o] = adj; lg[o] = s;
@@ -140,7 +140,7 @@ __device__ static void adj_backward(float* ds, const float* __restrict__ sim_g, 
 // ------------------------------------------------------------------------------------------------------------
 // aggregate: items [item_begin, item_end) step item_stride of one video; item = (channel, VEC-wide column group)
 // ------------------------------------------------------------------------------------------------------------
-template <int TMAX, int VEC>
+template <int TMAX, int VEC, bool kSmemIn = false>
 __device__ __forceinline__ void aggregate_items(const float* __restrict__ in, float* __restrict__ out, const float* M,
                                                 bool transpose, bool skip, int Cn, int T, int S,
                                                 int item_begin, int item_stride)
@@ -155,10 +155,11 @@ __device__ __forceinline__ void aggregate_items(const float* __restrict__ in, fl
         for (int j = 0; j < TMAX; ++j) {
             if (j < T) {
                 if constexpr (VEC == 4) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(in + base + (size_t)j * S));
+                    const float4* src = reinterpret_cast<const float4*>(in + base + (size_t)j * S);
+                    const float4 v = kSmemIn ? *src : __ldg(src);          // (__ldg is a global-memory load)
                     x[j][0] = v.x; x[j][1] = v.y; x[j][2] = v.z; x[j][3] = v.w;
                 } else {
-                    x[j][0] = __ldg(in + base + (size_t)j * S);
+                    x[j][0] = kSmemIn ? in[base + (size_t)j * S] : __ldg(in + base + (size_t)j * S);
                 }
             }
         }
@@ -212,5 +213,7 @@ int graph_agg_launch(const AggJobs& jobs, int njobs, int B, cudaStream_t st);   
 int graph_bwd_adj_launch(const GraphArgs& a, bool fused, cudaStream_t st);   // graph_bwd.cu
 size_t graph_split_scratch_floats(int B, int T);                              // graph_split.cu
 int graph_split_adj_launch(const GraphArgs& a, bool bwd, float* scratch, cudaStream_t st);
+bool graph_smem_fits(const GraphArgs& a, bool bwd);                           // graph_smem.cu
+int graph_smem_launch(const GraphArgs& a, bool bwd, cudaStream_t st);
 
 }  // namespace gca

@@ -54,7 +54,7 @@ class GraphedMoCoStep(object):
     def _enqueue_work(self, stream):
         m = self.moco
         _lib.call("gca_moco_step", ptr(self.q), ptr(self.k), ptr(m.memory), self.qd, self.B, self.K, self.d, 1.0 / m.T,
-                  _lib.ALGO[self.algo], ptr(self.all_k), self.N, 0, ptr(self.state),
+                  _lib.ALGO[self.algo], ptr(self.all_k), self.N, 0, ptr(self.state), None,
                   ptr(self.loss), ptr(self.loss_rows), ptr(self.lse), ptr(self.pos), ptr(self.rank), ptr(self.hits),
                   ptr(self.dq), ptr(self.ws), self.ws.numel(), stream)
 
@@ -114,6 +114,7 @@ class GraphedReplicaStep(GraphedMoCoStep):
         self.world = dist.get_world_size(self.group)
         super(GraphedReplicaStep, self).__init__(moco, batch, n_enqueue=batch * self.world, algo=algo, state=state)
         self.side = torch.cuda.Stream(moco.memory.device)
+        self.keys_ready = torch.cuda.Event()
 
     def _enqueue_work(self, stream):
         import torch.distributed as dist
@@ -123,9 +124,10 @@ class GraphedReplicaStep(GraphedMoCoStep):
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             dist.all_gather_into_tensor(self.all_k, self.k, group=self.group)
-        _lib.call("gca_infonce_fwd", ptr(self.q), ptr(self.k), ptr(m.memory), self.qd, self.B, self.K, self.d, 1.0 / m.T,
-                  _lib.ALGO[self.algo], ptr(self.loss), ptr(self.loss_rows), ptr(self.lse), ptr(self.pos), ptr(self.rank),
-                  ptr(self.hits), ptr(self.dq), None, ptr(self.ws), self.ws.numel(), stream)
+            self.keys_ready.record(self.side)
+        # one C call: prep + queue sweep, then (after the event) finalize with the enqueue of the gathered keys riding in it
+        _lib.call("gca_moco_step", ptr(self.q), ptr(self.k), ptr(m.memory), self.qd, self.B, self.K, self.d, 1.0 / m.T,
+                  _lib.ALGO[self.algo], ptr(self.all_k), self.N, 0, ptr(self.state), ctypes.c_void_p(self.keys_ready.cuda_event),
+                  ptr(self.loss), ptr(self.loss_rows), ptr(self.lse), ptr(self.pos), ptr(self.rank), ptr(self.hits),
+                  ptr(self.dq), ptr(self.ws), self.ws.numel(), stream)
         main.wait_stream(self.side)
-        _lib.call("gca_enqueue_devptr", ptr(m.memory), self.qd, self.K, 0, self.K, self.d, ptr(self.all_k), self.N,
-                  ptr(self.state), stream)
