@@ -33,7 +33,7 @@ graph_fwd_kernel(const GraphArgs a)
 
 // grid-parallel aggregation for large feature maps: grid = (chunks, B, jobs)
 template <int TMAX>
-__global__ void __launch_bounds__(G_THREADS)
+__global__ void __launch_bounds__(G_THREADS, (TMAX <= 8) ? 2 : 1)      // T <= 8: cap registers so 2 CTAs/SM keep enough loads in flight
 graph_agg_kernel(const AggJobs jobs)
 {
     __shared__ float M[G_TMAXMAX * G_TMAXMAX];
@@ -91,7 +91,7 @@ int graph_agg_launch(const AggJobs& jobs, int njobs, int B, cudaStream_t st)
     }
     int chunks = (int)((max_items + G_THREADS - 1) / G_THREADS);
     if (chunks < 1) chunks = 1;
-    if (chunks > 64) chunks = 64;
+    if (chunks > 256) chunks = 256;
     dim3 grid(chunks, B, njobs);
     switch (pick_tmax(jobs.T)) {
         case 4:  graph_agg_kernel<4><<<grid, G_THREADS, 0, st>>>(jobs); break;
