@@ -84,7 +84,8 @@ int gca_enqueue_devptr(void* queue, int dtype_queue, long long K_global, long lo
  *                                  accuracy(topk=(1,5)), train_video_contrast_dis.py:428); may be NULL
  *                 dq_unit[B, d]  = d loss_mean / d q (may be NULL: forward only)
  *                 logits_out     = [B, K+1] fp32 materialised logits (may be NULL; FFMA algo only)
- *   workspace   : gca_infonce_workspace_bytes(...) bytes of scratch
+ *   workspace   : gca_infonce_workspace_bytes(...) bytes of scratch, ZERO-FILLED ONCE by the caller before first use
+ *                 (its first 256 bytes hold self-resetting tickets and a grid-barrier generation counter)
  * Deterministic: partial results are merged in a fixed order (no floating-point atomics).
  * --------------------------------------------------------------------------------------------------------- */
 size_t gca_infonce_workspace_bytes(int B, long long K, int d, int dtype_queue, int algo);

@@ -517,7 +517,7 @@ def test_graphed_step_matches_oracle_over_a_lap(lib, queue_dtype, B, N, K):
     ref_mem = moco.memory.cpu().clone()
     idx = moco.index
     step = GraphedMoCoStep(moco, B, N).capture()
-    # bf16: prep + streaming kernel + finalize(with the enqueue riding in it); fp32 (ffma family): no prep launch
+    # bf16 (tcgen05): prep + streaming kernel + finalize (with the enqueue riding in it); fp32 (ffma family): no prep launch
     assert step.launches_per_step == (3 if queue_dtype == "bf16" else 2)
     for it in range(K // N + 3):
         q, k, all_k = unit_rows(B, 128, gen), unit_rows(B, 128, gen), unit_rows(N, 128, gen)

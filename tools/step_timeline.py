@@ -33,6 +33,11 @@ for cold in (True, False):
           "last-block exit %.2f (span %.2f)" % ("cold" if cold else "warm", a.elapsed_time(b) * 1e3, (s_in - p_in) / 1e3, (s_out - p_in) / 1e3,
           (s_out - s_in) / 1e3, (f_in - p_in) / 1e3, (f_out - p_in) / 1e3, (f_out - f_in) / 1e3))
 
+    if float(cta[:, 14].max()) > 0:      # fused finalize stamps (per CTA): 12 partial written, 13 past the grid barrier, 14 done
+        for sl, nm in ((5, "main loop done"), (6, "last MMA done"), (12, "partial written"), (13, "past grid barrier"), (14, "fused finalize done"), (8, "exit")):
+            rel = (cta[:, sl] - p_in) / 1e3
+            print("   %-22s mean %6.2f  min %6.2f  max %6.2f us since prep entry" % (nm, rel.mean(), rel.min(), rel.max()))
+        continue
     fb = t[32 * 400: 32 * 400 + 4 * 256].view(256, 4).double()
     e = (fb[:, 0] - p_in) / 1e3; st_ = (fb[:, 1] - p_in) / 1e3; ac = (fb[:, 2] - p_in) / 1e3
     print("   finalize row blocks: entry min %.2f max %.2f | stats+loads done min %.2f max %.2f | accumulate done min %.2f max %.2f | "

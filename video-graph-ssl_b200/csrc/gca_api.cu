@@ -100,7 +100,8 @@ static int nsplit_for(int algo, int B, long long K, int d)
 // launch the stream kernel of the chosen family; fills `ws`
 static int run_stream(const float* q, const float* k, const void* queue, int dtype_queue, int B, long long K, int d,
                       float inv_T, int algo, const float* lse_fixed, bool want_acc, float* pos_out, float* logits_out,
-                      void* workspace, size_t workspace_bytes, InfoNceWs* ws_out, cudaStream_t st, bool skip_prep = false)
+                      void* workspace, size_t workspace_bytes, InfoNceWs* ws_out, cudaStream_t st, bool skip_prep = false,
+                      FinalizeParams* fuse = nullptr)
 {
     const int a = pick_algo(algo, dtype_queue, d);
     if (sm_count_cached() < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
@@ -116,6 +117,11 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
     P.q_bf16_ws = ws.q_bf16; P.pos_ws = ws.pos_ws; P.T_ = 1.f / inv_T; P.skip_prep = skip_prep ? 1 : 0;
     *ws_out = ws;
     count_launch(1);
+    if (fuse) {                                         // single-launch path: the stream kernel finalizes (and enqueues) itself
+        fuse->counter = ws.counter; fuse->part_max = ws.part_max; fuse->part_sum = ws.part_sum; fuse->part_cnt = ws.part_cnt;
+        fuse->part_acc = ws.part_acc; fuse->nsplit = ws.nsplit; fuse->Bpad = ws.Bpad;
+        return infonce_tc_launch(P, false, st, fuse);
+    }
     if (a == GCA_ALGO_TCGEN05) return infonce_tc_launch(P, lse_fixed != nullptr, st);
     return infonce_ffma_launch(P, dtype_queue, lse_fixed != nullptr, st);
 }
@@ -156,19 +162,28 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
     }
     cudaStream_t st = (cudaStream_t)stream;
     InfoNceWs ws;
-    rc = run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, dq_unit != nullptr, pos_logit, logits_out,
-                    workspace, workspace_bytes, &ws, st);
-    if (rc != GCA_OK) return rc;
     FinalizeParams F{};
-    F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
-    F.part_acc = dq_unit ? ws.part_acc : nullptr;
-    F.nsplit = ws.nsplit; F.Bpad = ws.Bpad; F.B = B; F.d = d; F.inv_T = inv_T; F.k = k; F.pos = pos_logit;
+    F.B = B; F.d = d; F.inv_T = inv_T; F.k = k; F.pos = pos_logit;
     F.lse = lse; F.loss_rows = loss_rows; F.rank_gt = rank_gt; F.dq = dq_unit; F.loss_mean = loss_mean; F.top_hits = top_hits;
-    if (keys_ready_event) GCA_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)keys_ready_event, 0));
     if (enq_keys) {
         F.enq_queue = const_cast<void*>(queue); F.enq_dtype = dtype_queue; F.enq_K = K; F.enq_keys = enq_keys; F.enq_N = enq_N;
         F.enq_index = enq_index; F.enq_state = enq_state;
     }
+    // tcgen05 with gradient and no materialised logits: one launch does stream + finalize (+ enqueue) behind a grid barrier.
+    // (an enqueue that has to wait for an event on another stream keeps the two-kernel path: the wait sits between them)
+    const bool fused = pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05 && dq_unit != nullptr && logits_out == nullptr &&
+                       keys_ready_event == nullptr && infonce_tc_can_fuse(B, K);
+    if (fused) {
+        return run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, true, pos_logit, nullptr, workspace,
+                          workspace_bytes, &ws, st, false, &F);
+    }
+    rc = run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, dq_unit != nullptr, pos_logit, logits_out,
+                    workspace, workspace_bytes, &ws, st);
+    if (rc != GCA_OK) return rc;
+    F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
+    F.part_acc = dq_unit ? ws.part_acc : nullptr;
+    F.nsplit = ws.nsplit; F.Bpad = ws.Bpad;
+    if (keys_ready_event) GCA_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)keys_ready_event, 0));
     return infonce_finalize_launch(F, FIN_FULL, st);
 }
 
