@@ -1,0 +1,18 @@
+# Round-end evidence run (1 GPU): tests, smoke, bench, ncu launch list + full capture of the dominant kernel, secondary kernels
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "exit $?" >> gpurun_out/pytest_gpu.log; tail -n 3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit $?" >> gpurun_out/smoke.log; tail -n 2 gpurun_out/smoke.log
+timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"
+timeout 300 python bench.py --impl reference --steps 60 --warmup 3 > gpurun_out/bench_ref.json 2>> gpurun_out/bench_n1.err; echo "ref exit $?"
+timeout 300 python tools/bench_kernels.py > gpurun_out/kernels.jsonl 2>> gpurun_out/bench_n1.err; echo "kernels exit $?"
+timeout 120 python tools/step_timeline.py > gpurun_out/step_timeline.txt 2>&1
+timeout 120 python tools/tc_timeline.py 256 65536 > gpurun_out/tc_timeline.txt 2>&1
+timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu > gpurun_out/plain.log 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 30 --warmup 3 --no-cpu > gpurun_out/ncu_list.log 2>&1
+echo "ncu list exit $?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"infonce_tc|infonce_finalize|infonce_prep" -s 60 -c 6 -o gpurun_out/prof_r01 \
+    python bench.py --steps 30 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
+echo "ncu full exit $?"
+ls -la gpurun_out | head -30
