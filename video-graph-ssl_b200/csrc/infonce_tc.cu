@@ -325,9 +325,19 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 
         // Group g takes keys [64g, 64g+64) of every 128-key tile; its S buffers alternate, so the S GEMM of step v+1 is
         // already in TMEM while step v is being exponentiated.
+        // a warp whose 32 rows are all padding (B not a multiple of 128) only keeps the pipeline's barriers moving: its S rows
+        // are q = 0 and its P / O rows are never read (GEMM rows are independent), so it skips the load / exp / store work
+        const bool warp_has_rows = (row0 + wq * 32) < P.B;
         for (int v = 0; v < n; ++v) {
             const int sb = v & 1;
             const uint32_t s_addr = lane_addr + tm_s(g, sb);
+            if (!warp_has_rows) {
+                if (v == 0) { if (g == 0) named_barrier_arrive(2, 256); else named_barrier_sync(2, 256); }
+                mbar_wait(&bar->s_full[sb], (v >> 1) & 1);
+                tc_fence_before();
+                mbar_arrive(&bar->p_full[g * 2 + sb]);
+                continue;
+            }
             if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 16);
             if (v == 0 && g == 1) named_barrier_sync(2, 256);
             mbar_wait(&bar->s_full[sb], (v >> 1) & 1);
