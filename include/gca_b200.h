@@ -192,6 +192,16 @@ size_t gca_sim_topk_workspace_bytes(int Nq, int Ng, int d, int k);
 int gca_sim_topk(const float* queries, const float* gallery, int Nq, int Ng, int d, int k, int normalize,
                  int* idx_out, float* val_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Momentum (EMA) update of the key encoder in one multi-tensor launch.  Replaces Trainer._momentum_update
+ * (tools/train_video_contrast_dis.py:176-180, :440): for every parameter  p_ema = m * p_ema + (1 - m) * p.
+ *   chunk_table : DEVICE array of nchunks descriptors {float* ema; const float* src; long long n;}
+ *                 (gca_ema_chunk_bytes() each), built once per model by the caller; a descriptor covers at most
+ *                 a few thousand contiguous elements of one parameter tensor
+ * --------------------------------------------------------------------------------------------------------- */
+size_t gca_ema_chunk_bytes(void);
+int gca_ema_update(const void* chunk_table, int nchunks, float momentum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -534,3 +534,30 @@ def test_graphed_step_matches_oracle_over_a_lap(lib, queue_dtype, B, N, K):
     torch.cuda.synchronize()
     assert int(step.state[0]) == idx and int(step.state[1]) == 0           # device pointer == host pointer == oracle
     assert torch.equal(moco.memory.cpu(), ref_mem)                          # slot contents: exact
+
+
+# ============================================================================================ EMA (momentum encoder update)
+def test_momentum_update_matches_reference_loop(lib):
+    """One multi-tensor launch == the per-parameter mul_/add_ loop of Trainer._momentum_update (train...:176-180)."""
+    from gca_b200.ema import MomentumUpdater
+    torch.manual_seed(0)
+    def make():
+        return torch.nn.Sequential(torch.nn.Conv3d(3, 17, 3), torch.nn.BatchNorm3d(17), torch.nn.Linear(17, 33),
+                                   torch.nn.Linear(33, 5, bias=False), torch.nn.Conv3d(17, 64, (1, 3, 3))).cuda()
+    model, ema = make(), make()
+    ref = [p.detach().clone() for p in ema.parameters()]
+    up = MomentumUpdater(model, ema)
+    assert up.numel == sum(p.numel() for p in model.parameters())
+    for m in (0.999, 0.5, 0.0, 1.0):
+        up.step(m)
+        for r, p in zip(ref, model.parameters()):
+            r.mul_(m).add_(p.detach(), alpha=1 - m)                     # the reference's arithmetic
+        torch.cuda.synchronize()
+        for r, e in zip(ref, ema.parameters()):
+            assert rel_max(e, r) <= 1e-6
+    # m = 1 leaves the EMA weights bit-identical, m = 0 copies the online weights exactly
+    before = [p.detach().clone() for p in ema.parameters()]
+    up.step(1.0)
+    assert all(torch.equal(a, b) for a, b in zip(before, ema.parameters()))
+    up.step(0.0)
+    assert all(torch.equal(a, b) for a, b in zip(model.parameters(), ema.parameters()))

@@ -149,6 +149,20 @@ for Bq in (64, 256):
     report("infonce bf16 (tcgen05) fused fwd+grad+finalize B=%d K=2^20" % Bq,
            timeit(lambda: GF.infonce_forward(qb, kb, big, 0.07, algo="tcgen05"), n=10), K1 * 128 * 2, flops=4.0 * Bq * K1 * 128)
 
+# ---- EMA of an R3D-18-sized encoder (33.4 M fp32 parameters in 62 tensors)
+from gca_b200.ema import MomentumUpdater
+shapes = [(64, 3, 7, 7, 7)] + [(c, c, 3, 3, 3) for c in (64,) * 4 + (128,) * 4 + (256,) * 4 + (512,) * 4] + [(512, 512, 3, 3, 3)] * 2
+class Bag(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.ps = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(*sh, device="cuda") * 0.01) for sh in shapes])
+ma, mb = Bag(), Bag()
+upd = MomentumUpdater(ma, mb)
+def eager_ema():
+    for p1, p2 in zip(ma.parameters(), mb.parameters()):
+        p2.data.mul_(0.999).add_(p1.detach().data, alpha=0.001)
+report("ema update %.1f M params (1 launch)" % (upd.numel / 1e6), timeit(lambda: upd.step(0.999)), 12 * upd.numel, ref_us=timeit(eager_ema))
+
 # ---- retrieval (config 5)
 gal, qry = torch.randn(13320, 512, device="cuda"), torch.randn(3783, 512, device="cuda")
 report("sim_topk 3783x13320x512 k=50", timeit(lambda: GF.cosine_topk(qry, gal, 50), n=5, warm=2), flops=2.0 * 3783 * 13320 * 512,

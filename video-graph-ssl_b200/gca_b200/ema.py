@@ -1,0 +1,56 @@
+"""Momentum encoder update as one kernel launch (gca_ema_update).
+
+Mirror of `Trainer._momentum_update(model, model_ema, m)` (tools/train_video_contrast_dis.py:176-180):
+    for p1, p2 in zip(model.parameters(), model_ema.parameters()):  p2.data.mul_(m).add_(p1.detach().data, alpha=1 - m)
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ptr
+
+CHUNK = 16384          # elements per descriptor: 64 KB of fp32, one CTA's worth of work
+
+
+class MomentumUpdater(object):
+    """Built once for a (model, model_ema) pair; `step(m)` updates every parameter of model_ema in a single launch.
+    Parameters must be fp32, contiguous, on one CUDA device, and keep their storage (rebuild after re-allocation)."""
+
+    def __init__(self, model, model_ema):
+        pairs = list(zip(model.parameters(), model_ema.parameters()))
+        if not pairs:
+            raise ValueError("no parameters")
+        rec = []
+        dev = pairs[0][0].device
+        for p, e in pairs:
+            if not (p.is_cuda and e.is_cuda):
+                raise RuntimeError("MomentumUpdater needs CUDA parameters; there is no CPU path")
+            if p.dtype != torch.float32 or e.dtype != torch.float32 or p.shape != e.shape:
+                raise TypeError("MomentumUpdater handles matching fp32 parameters")
+            if not (p.is_contiguous() and e.is_contiguous()):
+                raise ValueError("parameters must be contiguous")
+            n = p.numel()
+            for off in range(0, n, CHUNK):
+                rec.append((e.data_ptr() + 4 * off, p.data_ptr() + 4 * off, min(CHUNK, n - off)))
+        assert int(_lib.load().gca_ema_chunk_bytes()) == 24
+        table = np.array(rec, dtype=np.int64).reshape(-1, 3)
+        self.table = torch.from_numpy(table).to(dev)                  # [nchunks, 3] int64 == {float*, const float*, long long}
+        self.nchunks = table.shape[0]
+        self.device = dev
+        self.numel = sum(p.numel() for p, _ in pairs)
+        self._keep = pairs                                            # keeps the storages (and their addresses) alive
+
+    def step(self, m):
+        _lib.call("gca_ema_update", ptr(self.table), self.nchunks, float(m),
+                  ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+
+
+def momentum_update(model, model_ema, m, _cache={}):
+    """Drop-in for `Trainer._momentum_update(model, model_ema, m)`; the descriptor table is cached per model pair."""
+    key = (id(model), id(model_ema))
+    up = _cache.get(key)
+    if up is None:
+        up = _cache[key] = MomentumUpdater(model, model_ema)
+    up.step(m)
