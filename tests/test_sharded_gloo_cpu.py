@@ -105,3 +105,45 @@ def test_sharded_moco_world2(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+def _shuffle_worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gca_b200.dist import ShuffleBN, shuffle_plan
+    from oracle.shuffle import shuffle_bn_all_ranks
+    bsz = 6
+    gen = torch.Generator().manual_seed(5)
+    xs = [torch.randn(bsz, 3, 2, 4, 4, generator=gen) for _ in range(world)]          # every rank can rebuild all clips
+    w = torch.randn(3 * 2 * 4 * 4, 16, generator=gen)
+
+    def encoder(x):                                   # batch-dependent on purpose (BN-like): the shuffle must be exact
+        f = x.reshape(x.shape[0], -1) @ w
+        return torch.nn.functional.normalize(f - f.mean(0, keepdim=True))
+
+    sbn = ShuffleBN()
+    for it in range(3):
+        torch.manual_seed(40 + it + 1000 * rank)      # ranks draw different permutations; rank 0's must win
+        k, all_k = sbn(xs[rank], encoder)
+        torch.manual_seed(40 + it)
+        ids0 = torch.randperm(bsz * world)
+        assert torch.equal(sbn.last_shuffle_ids, ids0)
+        ref_k, ref_all_k, ref_this = shuffle_bn_all_ranks(xs, encoder, ids0)
+        assert torch.equal(sbn.exchange(xs[rank], ids0), ref_this[rank])
+        assert torch.equal(all_k, ref_all_k)
+        assert torch.equal(k, ref_k[rank])
+        rows, sc, rc, place = shuffle_plan(ids0, bsz, world, rank)
+        assert sum(sc) == bsz and sum(rc) == bsz and sorted(place.tolist()) == list(range(bsz))
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shuffle_bn_matches_reference_indexing(tmp_path, world):
+    port = 31500 + (os.getpid() % 2000) + world
+    mp.spawn(_shuffle_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))

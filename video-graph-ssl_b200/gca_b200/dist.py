@@ -160,3 +160,80 @@ class ShardedRGBMoCo(nn.Module):
     def gather_full_queue(self):
         """The whole [K, d] queue in fp32 (checkpoint format of the reference, train...:278)."""
         return _all_gather_rows(self.memory.float(), self.group)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ShuffleBN clip exchange (train_video_contrast_dis.py:189-231)
+# ---------------------------------------------------------------------------------------------------------------
+
+def shuffle_plan(shuffle_ids, bsz, world, rank):
+    """Host-side routing tables for one rank of the ShuffleBN exchange.
+
+    The reference all-gathers every rank's clips and then indexes `node_x[shuffle_ids[rank*bsz:(rank+1)*bsz]]`
+    (train...:203-218), moving world x the payload.  Row g of `node_x` lives on rank g // bsz as local row g % bsz, so
+    only the rows a peer asks for need to travel.  Returns (all int64, CPU):
+      send_rows   local row numbers in send order: grouped by destination rank, inside a group in the order the
+                  destination's id list names them
+      send_counts rows per destination                     [world]
+      recv_counts rows per source                          [world]
+      recv_place  recv_place[j] = position in `this_x` of the j-th received row (receive order: by source rank)
+    """
+    ids = shuffle_ids.to("cpu", torch.int64).view(world, bsz)
+    src = torch.div(ids, bsz, rounding_mode="floor")
+    send_rows, send_counts = [], []
+    for dst in range(world):
+        mine = ids[dst][src[dst] == rank] - rank * bsz
+        send_rows.append(mine)
+        send_counts.append(int(mine.numel()))
+    order = torch.argsort(src[rank], stable=True)
+    recv_counts = torch.bincount(src[rank], minlength=world).tolist()
+    return torch.cat(send_rows), send_counts, recv_counts, order
+
+
+class ShuffleBN(object):
+    """`Trainer._shuffle_bn` (train_video_contrast_dis.py:189-231) with an all-to-all instead of gather-everything.
+
+    `__call__(x, model_ema)` returns `(k, all_k)` exactly like the reference: x is shuffled across the ranks of
+    `local_group` with a permutation drawn by `torch.randperm` on every rank and overwritten by rank 0's
+    (train...:208-211), the momentum encoder runs on the shuffled rows, the keys are gathered over `global_group`
+    and un-shuffled.  The permutation, its inverse and every row placement are integer work: bit-identical to
+    the reference for the same generator state.
+    """
+
+    def __init__(self, local_group=None, global_group=None, node_rank=0):
+        self.local_group = local_group if local_group is not None else dist.group.WORLD
+        self.global_group = global_group if global_group is not None else dist.group.WORLD
+        self.node_rank = node_rank
+        self.last_shuffle_ids = None
+
+    def exchange(self, x, shuffle_ids):
+        """Rows `shuffle_ids[rank*bsz:(rank+1)*bsz]` of the (virtual) concatenation of every rank's x."""
+        g = self.local_group
+        W, r = dist.get_world_size(g), dist.get_rank(g)
+        bsz = x.shape[0]
+        send_rows, send_counts, recv_counts, place = shuffle_plan(shuffle_ids, bsz, W, r)
+        x2 = x.contiguous().view(bsz, -1)
+        send = x2.index_select(0, send_rows.to(x.device))
+        recv = torch.empty_like(x2)
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=g)
+        out = torch.empty_like(x2)
+        out.index_copy_(0, place.to(x.device), recv)
+        return out.view(x.shape)
+
+    def __call__(self, x, model_ema):
+        g = self.local_group
+        W, r = dist.get_world_size(g), dist.get_rank(g)
+        bsz = x.shape[0]
+        shuffle_ids = torch.randperm(bsz * W).to(x.device)                 # train...:208 (CPU generator, as upstream)
+        reverse_ids = torch.argsort(shuffle_ids)
+        gg = self.global_group
+        root = 0 if gg is dist.group.WORLD else dist.get_global_rank(gg, 0)
+        dist.broadcast(shuffle_ids, root, group=gg)                         # rank 0's draw wins (train...:210-211)
+        dist.broadcast(reverse_ids, root, group=gg)
+        self.last_shuffle_ids = shuffle_ids
+        with torch.no_grad():
+            this_x = self.exchange(x, shuffle_ids)
+            k = model_ema(this_x)
+        all_k = _all_gather_rows(k.contiguous(), self.global_group)
+        node_k = all_k[self.node_rank * W * bsz:(self.node_rank + 1) * W * bsz]
+        return node_k[reverse_ids[r * bsz:(r + 1) * bsz]], all_k
