@@ -537,7 +537,8 @@ def test_graphed_step_matches_oracle_over_a_lap(lib, queue_dtype, B, N, K):
 
 
 # ============================================================================================ EMA (momentum encoder update)
-def test_momentum_update_matches_reference_loop(lib):
+@pytest.mark.parametrize("layout", ["contiguous", "channels_last_3d"])
+def test_momentum_update_matches_reference_loop(lib, layout):
     """One multi-tensor launch == the per-parameter mul_/add_ loop of Trainer._momentum_update (train...:176-180)."""
     from gca_b200.ema import MomentumUpdater
     torch.manual_seed(0)
@@ -545,6 +546,8 @@ def test_momentum_update_matches_reference_loop(lib):
         return torch.nn.Sequential(torch.nn.Conv3d(3, 17, 3), torch.nn.BatchNorm3d(17), torch.nn.Linear(17, 33),
                                    torch.nn.Linear(33, 5, bias=False), torch.nn.Conv3d(17, 64, (1, 3, 3))).cuda()
     model, ema = make(), make()
+    if layout == "channels_last_3d":                                    # permuted-dense conv weights, same on both sides
+        model, ema = model.to(memory_format=torch.channels_last_3d), ema.to(memory_format=torch.channels_last_3d)
     ref = [p.detach().clone() for p in ema.parameters()]
     up = MomentumUpdater(model, ema)
     assert up.numel == sum(p.numel() for p in model.parameters())
@@ -561,3 +564,5 @@ def test_momentum_update_matches_reference_loop(lib):
     assert all(torch.equal(a, b) for a, b in zip(before, ema.parameters()))
     up.step(0.0)
     assert all(torch.equal(a, b) for a, b in zip(model.parameters(), ema.parameters()))
+    with pytest.raises(ValueError):                                     # mismatched layouts are refused, not mis-indexed
+        MomentumUpdater(make(), make().to(memory_format=torch.channels_last_3d))

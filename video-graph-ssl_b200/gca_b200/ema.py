@@ -14,9 +14,19 @@ from ._lib import ptr
 CHUNK = 16384          # elements per descriptor: 64 KB of fp32, one CTA's worth of work
 
 
+def _dense(t):
+    """Every element of the storage span is used exactly once (any permutation of a contiguous layout)."""
+    expect = 1
+    for size, stride in sorted(((sz, st) for sz, st in zip(t.shape, t.stride()) if sz > 1), key=lambda x: x[1]):
+        if stride != expect:
+            return False
+        expect *= size
+    return True
+
+
 class MomentumUpdater(object):
     """Built once for a (model, model_ema) pair; `step(m)` updates every parameter of model_ema in a single launch.
-    Parameters must be fp32, contiguous, on one CUDA device, and keep their storage (rebuild after re-allocation)."""
+    Parameters must be fp32, dense with the same layout on both sides, on one CUDA device, and keep their storage (rebuild after re-allocation)."""
 
     def __init__(self, model, model_ema):
         pairs = list(zip(model.parameters(), model_ema.parameters()))
@@ -29,8 +39,8 @@ class MomentumUpdater(object):
                 raise RuntimeError("MomentumUpdater needs CUDA parameters; there is no CPU path")
             if p.dtype != torch.float32 or e.dtype != torch.float32 or p.shape != e.shape:
                 raise TypeError("MomentumUpdater handles matching fp32 parameters")
-            if not (p.is_contiguous() and e.is_contiguous()):
-                raise ValueError("parameters must be contiguous")
+            if p.stride() != e.stride() or not _dense(p):                 # channels_last(_3d) weights are fine
+                raise ValueError("parameter pairs must be dense and share one memory layout")
             n = p.numel()
             for off in range(0, n, CHUNK):
                 rec.append((e.data_ptr() + 4 * off, p.data_ptr() + 4 * off, min(CHUNK, n - off)))
