@@ -455,37 +455,61 @@ def run_multi(args, rank, world, local_rank):
     os._exit(0)
 
 
-def time_sharded_k1m(rank, world, dev, flush, steps=30, warmup=5):
+def time_sharded_k1m(rank, world, dev, flush, steps=200, warmup=10):
     """BASELINE config 4: queue 2^20 x 128 (bf16) split along K over the ranks, 256 rows per GPU; per-shard online-softmax
-    partials merged with NCCL (gca_b200.dist.ShardedRGBMoCo).  Eager (not graph-captured); device time, max over ranks."""
+    partials merged with NCCL.  One CUDA graph per step (gca_b200.graphed.GraphedShardedStep: 3 collectives + kernels);
+    the first step is cross-checked against the eager ShardedRGBMoCo path.  Per-step device time with an L2 flush
+    before every step, max over ranks."""
     import torch
     import torch.distributed as dist
     import gca_b200
     from gca_b200.dist import ShardedRGBMoCo
+    from gca_b200.graphed import GraphedShardedStep
     K1 = 1 << 20
     torch.manual_seed(1)
     moco = ShardedRGBMoCo(D, K=K1, T=T, queue_dtype="bf16", device=dev)
     crit = gca_b200.NCESoftmaxLoss()
     batches = synthetic_batches(300 + rank, 2, B, 0, device=dev)
+    # eager reference step on a copy of the shard
+    shard0 = moco.memory.clone()
+    q = batches[0][:B].clone().requires_grad_(True)
+    out, _ = moco(q, batches[0][B:2 * B])
+    loss_eager = crit(out)
+    loss_eager.backward()
+    torch.cuda.synchronize()
+    mem_eager = moco.memory.clone()
+    moco.memory.copy_(shard0)
+    moco.index = 0
+    del shard0
+    gs = GraphedShardedStep(moco, B).capture()
+    gs.step(batches[0][:B], batches[0][B:2 * B])
+    torch.cuda.synchronize()
+    same = bool(torch.equal(gs.loss, loss_eager.detach().reshape(1)) and torch.equal(gs.dq, q.grad)
+                and torch.equal(moco.memory, mem_eager))
+    del mem_eager
     ev = []
     for i in range(warmup + steps):
         flush.fill_(i & 1)
         pk = batches[i % 2]
-        q = pk[:B].clone().requires_grad_(True)
+        gs.q.copy_(pk[:B])
+        gs.k.copy_(pk[B:2 * B])
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        out, _ = moco(q, pk[B:2 * B])
-        crit(out).backward()
+        gs.step()
         b.record()
         if i >= warmup:
             ev.append((a, b))
     torch.cuda.synchronize()
     tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev)
     dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ok = torch.tensor([1 if same else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     ms = float(tot) / steps
     flops = 4.0 * (B * world) * (K1 / world) * D
     return {"K": K1, "rows_per_gpu": B, "rows_global": B * world, "shard_rows": K1 // world, "ms_per_step": ms,
-            "global_rows_per_s": B * world / ms * 1e3, "per_gpu_tflops": flops / (ms * 1e-3) / 1e12, "cuda_graph": False}
+            "global_rows_per_s": B * world / ms * 1e3, "per_gpu_tflops": flops / (ms * 1e-3) / 1e12, "cuda_graph": True,
+            "launches_per_step": gs.launches_per_step, "collectives_per_step": 3,
+            "graph_equals_eager_path": bool(int(ok))}
 
 
 def main():

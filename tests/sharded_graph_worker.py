@@ -1,0 +1,60 @@
+"""Worker for the GraphedShardedStep parity check (NCCL, one process per GPU; world size from the torchrun env, 1 when
+launched bare).  Runs the same steps through the eager ShardedRGBMoCo path and through the captured graph and compares
+every result bit for bit (both go through the same kernels in the same order).  Exits with os._exit: tearing down an
+NCCL communicator that was captured into a CUDA graph can block."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "video-graph-ssl_b200"))
+
+
+def main():
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", str(29400 + os.getpid() % 500))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from gca_b200.dist import ShardedRGBMoCo
+    from gca_b200.graphed import GraphedShardedStep
+    from gca_b200.memory.losses import NCESoftmaxLoss
+    K, d, T, Bl = 8192 * world, 128, 0.07, 128
+    for qdt in ("bf16", "fp32"):
+        torch.manual_seed(3)
+        a = ShardedRGBMoCo(d, K=K, T=T, queue_dtype=qdt, device=dev)
+        torch.manual_seed(3)
+        b = ShardedRGBMoCo(d, K=K, T=T, queue_dtype=qdt, device=dev)
+        assert torch.equal(a.memory, b.memory)
+        a.index = b.index = K - 3 * Bl * world + 64                  # the third step wraps around the ring
+        gs = GraphedShardedStep(b, Bl).capture()
+        assert torch.equal(a.memory, b.memory) and b.index == a.index   # capture leaves queue and pointer untouched
+        crit = NCESoftmaxLoss()
+        gen = torch.Generator().manual_seed(11 + rank)
+        for step in range(4):
+            q = torch.nn.functional.normalize(torch.randn(Bl, d, generator=gen)).to(dev)
+            k = torch.nn.functional.normalize(torch.randn(Bl, d, generator=gen)).to(dev)
+            qa = q.clone().requires_grad_(True)
+            out, _ = a(qa, k)
+            la = crit(out)
+            la.backward()
+            lb = gs.step(q, k)
+            torch.cuda.synchronize()
+            assert torch.equal(la.detach().reshape(1), lb), (step, float(la), float(lb))
+            assert torch.equal(qa.grad, gs.dq), step
+            assert torch.equal(out.rank, gs.rank) and torch.equal(out.lse, gs.lse), step
+            assert a.index == b.index and int(gs.state[0]) == b.index, step
+            assert torch.equal(a.memory, b.memory), step
+        assert gs.launches_per_step >= 5
+    dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        print("SHARDED_GRAPH_OK world=%d launches_per_step=%d" % (world, gs.launches_per_step), flush=True)
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()

@@ -2,6 +2,8 @@
 reference, on the same seeded inputs.  Integer and index work is compared bit-exactly; floating point within the
 tolerances BASELINE.json states: loss 1e-5 relative (fp32 mode) / 2e-3 (bf16 mode), gradients 1e-2 relative.
 Run with `pytest -m gpu` on a B200."""
+import os
+import sys
 import numpy as np
 import pytest
 import torch
@@ -566,3 +568,16 @@ def test_momentum_update_matches_reference_loop(lib, layout):
     assert all(torch.equal(a, b) for a, b in zip(model.parameters(), ema.parameters()))
     with pytest.raises(ValueError):                                     # mismatched layouts are refused, not mis-indexed
         MomentumUpdater(make(), make().to(memory_format=torch.channels_last_3d))
+
+
+def test_graphed_sharded_step_matches_eager_path():
+    """GraphedShardedStep (NCCL collectives + kernels in one CUDA graph) == the eager ShardedRGBMoCo path, bit for bit.
+    World size 1 here (the suite sees one GPU); `torchrun --nproc-per-node N tests/sharded_graph_worker.py` runs the
+    same check over N GPUs.  Separate process: see the worker's note on communicator teardown."""
+    import subprocess
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "sharded_graph_worker.py")],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "SHARDED_GRAPH_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
