@@ -344,9 +344,35 @@ def run_multi(args, rank, world, local_rank):
     pool = 4
     batches = synthetic_batches(100 + rank, pool, B, 0, device=dev)
     state = torch.tensor([0, 0], dtype=torch.int64, device=dev)
+    # key exchange: one peer-memory kernel per step (gca_keys_exchange over NVLink); NCCL all-gather if symmetric memory
+    # cannot be set up on this box (GCA_BENCH_EXCHANGE=nccl forces it).  All ranks agree on the mode.
+    exchange, why = None, "forced by GCA_BENCH_EXCHANGE"
+    xmode = os.environ.get("GCA_BENCH_EXCHANGE", "fused")          # fused | p2p (stand-alone kernel) | nccl
+    if xmode in ("fused", "p2p"):
+        try:
+            from gca_b200.peer import PeerKeyExchange
+            exchange = PeerKeyExchange(B, D, device=dev)
+            probe = batches[0][B:2 * B].contiguous()
+            got = torch.empty(world * B, D, device=dev)
+            want = torch.empty(world * B, D, device=dev)
+            exchange(probe, got)
+            dist.all_gather_into_tensor(want, probe)
+            torch.cuda.synchronize()
+            exchange.check()
+            if not torch.equal(got, want):
+                raise RuntimeError("peer exchange disagrees with NCCL all-gather")
+            okf = 1
+        except Exception as e:
+            okf, why = 0, "%s: %s" % (type(e).__name__, e)
+        agree = torch.tensor([okf], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree) == 0:
+            if rank == 0:
+                print("peer-memory key exchange unavailable (%s); using NCCL all-gather" % why, file=sys.stderr)
+            exchange = None
     steps_g = []
     for i in range(pool):
-        s = GraphedReplicaStep(moco, B, state=state)
+        s = GraphedReplicaStep(moco, B, state=state, exchange=exchange, fuse_exchange=(xmode == "fused"))
         s.inputs[:2 * B].copy_(batches[i])
         steps_g.append(s)
     graphed = True
@@ -426,6 +452,8 @@ def run_multi(args, rank, world, local_rank):
     e2e = torch.tensor([sum(e2e_t) / len(e2e_t) * 1e3], device=dev)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
 
+    if exchange is not None:
+        exchange.check()                                    # raises if any in-kernel wait for a peer ever timed out
     sharded = time_sharded_k1m(rank, world, dev, flush) if not args.no_sharded else None
     if rank == 0:
         line = {
@@ -434,8 +462,12 @@ def run_multi(args, rank, world, local_rank):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "moco_head_B256perGPU_K65536_d128_replicas", "B_per_gpu": B, "B_global": B * world, "K": K, "d": D,
                        "T": T, "queue_dtype": "bf16", "enqueued_rows_per_step": B * world,
-                       "parallelism": "dp%d: replicated queue (the reference's scheme); NCCL all-gather of the keys overlapped with "
-                                      "the queue sweep; every replica enqueues all %d keys" % (world, B * world),
+                       "parallelism": "dp%d: replicated queue (the reference's scheme); key all-gather (%s) overlapped with "
+                                      "the queue sweep; every replica enqueues all %d keys"
+                                      % (world, "NCCL" if exchange is None else
+                                         "NVLink peer-memory stores fused into the step's own launches" if xmode == "fused" else
+                                         "gca_keys_exchange: one NVLink peer-memory kernel per step", B * world),
+                       "key_exchange": "nccl" if exchange is None else ("fused_p2p" if xmode == "fused" else "p2p_kernel"),
                        "cuda_graph": graphed, "l2": "flushed between timed iterations (256 MiB write, outside the per-step events)",
                        "timing": "per-step CUDA events, total = max over ranks; value = n_gpus * 1000 / ms_per_step "
                                  "(each global step processes n_gpus x 256 rows)"},

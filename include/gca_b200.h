@@ -149,6 +149,34 @@ int gca_infonce_shard_finish(const float* acc, const float* k, const float* pos_
                              float* dq_unit, float* loss_mean, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Key all-gather over NVLink peer memory (replaces Trainer._global_gather, tools/train_video_contrast_dis.py:182-187,
+ * for the momentum keys every replica enqueues, train...:222).  One launch per step and rank, no NCCL call on the data
+ * path; safe to capture in a CUDA graph (the step counter is device-resident).
+ *   mailboxes : DEVICE array of W pointers; entry p is rank p's mailbox allocation as mapped into THIS process
+ *               (symmetric / IPC memory; entry `rank` is the local one).  Every mailbox is gca_keys_exchange_bytes()
+ *               long and zero-filled before the first step; all ranks call once per step, in the same order.
+ *   keys_local: [B, d] fp32 of this rank;  all_k: [W*B, d] fp32 out, rank-major rows (== torch.cat(all_gather)).
+ *   xstate    : 4 x int64 device words, zero-initialised: [0] step counter, [1] ticket, [2] raised to 1 if a peer did
+ *               not show up within timeout_ms (0 = wait for ever); all_k is then incomplete for that step.
+ * --------------------------------------------------------------------------------------------------------- */
+size_t gca_keys_exchange_bytes(int B, int d, int W);
+int gca_keys_exchange(const float* keys_local, int B, int d, int W, int rank, void* const* mailboxes,
+                      float* all_k, long long* xstate, int timeout_ms, void* stream);
+
+/* The data-parallel head step with the key gather fused in (RGBMoCo.forward with all_k = _global_gather(k),
+ * train...:222 + mem_moco.py:60-88): gca_moco_step whose enqueue rows are the keys of ALL W ranks, moved through the
+ * mailboxes above instead of an all_k buffer.  Extra CTAs of the first launch push this rank's k[B, d] to every peer
+ * while the queue is being swept; the enqueue CTAs of the last launch wait for the peers' flags and write the W*B
+ * gathered rows (rank-major, like torch.cat(all_gather)) straight from the local mailbox into the ring.  Same
+ * launches as gca_moco_step, no collective call, no side stream.  bf16 queue with d == 128 only (tcgen05 family);
+ * `state` (device ring pointer) is required; mailboxes / xstate / timeout_ms as for gca_keys_exchange (both entry
+ * points advance the same step counter, so they can share a mailbox if every rank issues the same call sequence). */
+int gca_moco_step_peer(const float* q, const float* k, void* queue, int dtype_queue, int B, long long K, int d, float inv_T,
+                       int algo, int W, int rank, void* const* mailboxes, long long* xstate, int timeout_ms,
+                       long long* state, float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt,
+                       int* top_hits, float* dq_unit, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Temporal clip-graph head.  Replaces, for one GCN layer (the shipped default), the part of
  * TemporalGraphAug.forward (lib/ops/module_wrappers/temporal_graph.py:227-239) between the 1x1x1 convolutions:
  * similarity + row softmax (:161-176), hop mask and theta(hop) weights (:25-36, :204-210), relaxed-Bernoulli

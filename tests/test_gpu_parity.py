@@ -581,3 +581,16 @@ def test_graphed_sharded_step_matches_eager_path():
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "sharded_graph_worker.py")],
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and "SHARDED_GRAPH_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+def test_peer_key_exchange_single_rank():
+    """gca_keys_exchange against NCCL all-gather, eager and graph-replayed (world size 1 inside the suite: the mailbox
+    protocol, parity double-buffering and the device-resident step counter; `torchrun --nproc-per-node N
+    tests/peer_exchange_worker.py` runs the same check across N GPUs over NVLink)."""
+    import subprocess
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "peer_exchange_worker.py")],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "PEER_EXCHANGE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])

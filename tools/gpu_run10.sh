@@ -2,6 +2,7 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 N=${1:-2}
 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 tests/sharded_graph_worker.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tail -n 12
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tests/peer_exchange_worker.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tail -n 25
 echo "worker exit ${PIPESTATUS[0]}"
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 1000 --warmup 20 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench n$N exit $?"
 python - $N <<'PY'

@@ -1,4 +1,16 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x -k "graph" > gpurun_out/pytest_graph.log 2>&1; echo "exit $?" >> gpurun_out/pytest_graph.log; tail -n 4 gpurun_out/pytest_graph.log
-timeout 600 python tools/bench_kernels.py 2>gpurun_out/kernels.err | head -n 8 | tee gpurun_out/kernels_graph.jsonl; tail -n 3 gpurun_out/kernels.err
+N=${1:-2}
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tests/peer_exchange_worker.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tail -n 25
+echo "worker exit ${PIPESTATUS[0]}"
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 1000 --warmup 20 --no-sharded > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench n$N exit $?"
+python - $N <<'PY'
+import json, sys
+n=sys.argv[1]
+try:
+    d=json.loads(open('gpurun_out/bench_n%s.json'%n).read().strip().splitlines()[-1])
+    for k in ('value','ms_per_step','replicas_consistent','gpu_launches'): print(k, d[k])
+    print('e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'graph', d['config']['cuda_graph'], d['config']['key_exchange'])
+except Exception as e: print('no json', e)
+PY
+grep -v "^\*\|OMP_NUM\|^$" gpurun_out/bench_n$N.err | tail -n 8

@@ -46,11 +46,22 @@ __device__ __forceinline__ void enqueue_rows(const FinalizeParams& F, int blk, i
     const int d4 = F.d / 4;
     const long long total = (long long)F.enq_N * d4;
     const float4* keys = reinterpret_cast<const float4*>(F.enq_keys);
+    const bool peer = F.xchg.mailboxes != nullptr;
+    unsigned long long xstep = 0;
+    if (peer) {
+        // the gathered keys are this rank's mailbox slots of the current parity: [W][B*d] == all_k, pushed by the peers'
+        // prep kernels while the queue was being swept.  Wait for every (rank, slice) flag, then read around L1.
+        xstep = *reinterpret_cast<volatile unsigned long long*>(F.xchg.xstate);
+        if ((int)threadIdx.x < F.xchg.W * XCHG_SLICES)
+            xchg_wait_slice(F.xchg, xstep, threadIdx.x / XCHG_SLICES, threadIdx.x % XCHG_SLICES);
+        __syncthreads();
+        keys = xchg_slot(F.xchg.mailboxes[F.xchg.rank], F.xchg, (int)(xstep & 1ull), 0);
+    }
     for (long long i = (long long)blk * FIN_THREADS + threadIdx.x; i < total; i += (long long)nblk * FIN_THREADS) {
         const int row = (int)(i / d4), c4 = (int)(i - (long long)row * d4);
         long long slot = index + row;
         if (slot >= F.enq_K) slot -= F.enq_K;
-        const float4 v = __ldg(keys + i);
+        const float4 v = peer ? ld_cg_f4(keys + i) : __ldg(keys + i);
         const long long off = slot * d4 + c4;
         if constexpr (sizeof(QT) == 4) {
             reinterpret_cast<float4*>(queue)[off] = v;
@@ -73,6 +84,7 @@ __device__ __forceinline__ void enqueue_rows(const FinalizeParams& F, int blk, i
             if (nx >= F.enq_K) nx -= F.enq_K;
             F.enq_state[0] = nx;
             F.enq_state[1] = 0;
+            if (peer) F.xchg.xstate[0] = xstep + 1;       // every enqueue CTA has read the step before taking its ticket
         }
     }
 }
@@ -266,6 +278,8 @@ int infonce_finalize_launch(const FinalizeParams& F_, int mode, cudaStream_t st)
     F.timebuf = debug_timebuf();
     if (F.nsplit > FIN_MAX_SPLITS) return set_err(GCA_ERR_UNSUPPORTED, "finalize: %d splits > %d", F.nsplit, FIN_MAX_SPLITS);
     int enq_blocks = 0;
+    if (F.xchg.mailboxes && F.xchg.W * XCHG_SLICES > FIN_THREADS)
+        return set_err(GCA_ERR_UNSUPPORTED, "finalize: peer exchange over %d ranks", F.xchg.W);
     if (mode == FIN_FULL && F.enq_queue != nullptr && F.enq_N > 0) {
         enq_blocks = (int)(((long long)F.enq_N * (F.d / 4) + FIN_THREADS - 1) / FIN_THREADS);
         if (enq_blocks > 64) enq_blocks = 64;

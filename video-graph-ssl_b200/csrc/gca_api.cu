@@ -101,7 +101,7 @@ static int nsplit_for(int algo, int B, long long K, int d)
 static int run_stream(const float* q, const float* k, const void* queue, int dtype_queue, int B, long long K, int d,
                       float inv_T, int algo, const float* lse_fixed, bool want_acc, float* pos_out, float* logits_out,
                       void* workspace, size_t workspace_bytes, InfoNceWs* ws_out, cudaStream_t st, bool skip_prep = false,
-                      FinalizeParams* fuse = nullptr)
+                      FinalizeParams* fuse = nullptr, const PeerXchg* px = nullptr)
 {
     const int a = pick_algo(algo, dtype_queue, d);
     if (sm_count_cached() < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
@@ -115,6 +115,11 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
     P.part_acc = want_acc ? ws.part_acc : nullptr;
     P.nsplit = nsplit; P.Bpad = ws.Bpad; P.pos_out = pos_out ? pos_out : ws.pos_tmp; P.logits_out = logits_out; P.ld_logits = K + 1;
     P.q_bf16_ws = ws.q_bf16; P.pos_ws = ws.pos_ws; P.T_ = 1.f / inv_T; P.skip_prep = skip_prep ? 1 : 0;
+    if (px) {
+        if (a != GCA_ALGO_TCGEN05)
+            return set_err(GCA_ERR_UNSUPPORTED, "the peer-fused step exists for the tcgen05 family only (bf16 queue, d == 128)");
+        P.xchg = *px;
+    }
     *ws_out = ws;
     count_launch(1);
     if (fuse) {                                         // single-launch path: the stream kernel finalizes (and enqueues) itself
@@ -150,7 +155,7 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
                             long long K, int d, float inv_T, int algo, float* loss_mean, float* loss_rows, float* lse,
                             float* pos_logit, int* rank_gt, int* top_hits, float* dq_unit, float* logits_out,
                             const float* enq_keys, int enq_N, long long enq_index, long long* enq_state, void* keys_ready_event,
-                            void* workspace, size_t workspace_bytes, void* stream)
+                            void* workspace, size_t workspace_bytes, void* stream, const gca::PeerXchg* px = nullptr)
 {
     using namespace gca;
     int rc = check_infonce_args(fn, q, k, queue, dtype_queue, B, K, d, inv_T, algo);
@@ -165,20 +170,21 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
     FinalizeParams F{};
     F.B = B; F.d = d; F.inv_T = inv_T; F.k = k; F.pos = pos_logit;
     F.lse = lse; F.loss_rows = loss_rows; F.rank_gt = rank_gt; F.dq = dq_unit; F.loss_mean = loss_mean; F.top_hits = top_hits;
-    if (enq_keys) {
+    if (enq_keys || px) {
         F.enq_queue = const_cast<void*>(queue); F.enq_dtype = dtype_queue; F.enq_K = K; F.enq_keys = enq_keys; F.enq_N = enq_N;
         F.enq_index = enq_index; F.enq_state = enq_state;
+        if (px) F.xchg = *px;
     }
     // tcgen05 with gradient and no materialised logits: one launch does stream + finalize (+ enqueue) behind a grid barrier.
     // (an enqueue that has to wait for an event on another stream keeps the two-kernel path: the wait sits between them)
     const bool fused = pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05 && dq_unit != nullptr && logits_out == nullptr &&
-                       keys_ready_event == nullptr && infonce_tc_can_fuse(B, K);
+                       keys_ready_event == nullptr && px == nullptr && infonce_tc_can_fuse(B, K);
     if (fused) {
         return run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, true, pos_logit, nullptr, workspace,
                           workspace_bytes, &ws, st, false, &F);
     }
     rc = run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, dq_unit != nullptr, pos_logit, logits_out,
-                    workspace, workspace_bytes, &ws, st);
+                    workspace, workspace_bytes, &ws, st, false, nullptr, px);
     if (rc != GCA_OK) return rc;
     F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
     F.part_acc = dq_unit ? ws.part_acc : nullptr;
@@ -206,6 +212,25 @@ extern "C" int gca_moco_step(const float* q, const float* k, void* queue, int dt
     return infonce_fwd_impl("gca_moco_step", q, k, queue, dtype_queue, B, K, d, inv_T, algo, loss_mean, loss_rows, lse,
                             pos_logit, rank_gt, top_hits, dq_unit, nullptr, enqueue_keys, N, index, state, keys_ready_event,
                             workspace, workspace_bytes, stream);
+}
+
+extern "C" int gca_moco_step_peer(const float* q, const float* k, void* queue, int dtype_queue, int B, long long K, int d,
+                                  float inv_T, int algo, int W, int rank, void* const* mailboxes, long long* xstate,
+                                  int timeout_ms, long long* state, float* loss_mean, float* loss_rows, float* lse,
+                                  float* pos_logit, int* rank_gt, int* top_hits, float* dq_unit, void* workspace,
+                                  size_t workspace_bytes, void* stream)
+{
+    using namespace gca;
+    GCA_CHECK_ARG(mailboxes && xstate && state, "gca_moco_step_peer: mailboxes, xstate and state are required");
+    GCA_CHECK_ARG(W >= 1 && W <= 64 && rank >= 0 && rank < W, "gca_moco_step_peer: bad rank %d of %d", rank, W);
+    GCA_CHECK_ARG(B >= 1 && (long long)W * B <= K, "gca_moco_step_peer: %d x %d rows do not fit a ring of %lld slots", W, B, K);
+    PeerXchg X{};
+    X.mailboxes = (char* const*)mailboxes; X.W = W; X.rank = rank; X.n4 = B * d / 4;
+    X.xstate = (unsigned long long*)xstate;
+    X.timeout_ns = timeout_ms > 0 ? (unsigned long long)timeout_ms * 1000000ull : 0ull;
+    return infonce_fwd_impl("gca_moco_step_peer", q, k, queue, dtype_queue, B, K, d, inv_T, algo, loss_mean, loss_rows, lse,
+                            pos_logit, rank_gt, top_hits, dq_unit, nullptr, nullptr, W * B, 0, state, nullptr,
+                            workspace, workspace_bytes, stream, &X);
 }
 
 extern "C" int gca_infonce_partials(const float* q, const float* k, const void* queue, int dtype_queue, int B,

@@ -48,6 +48,18 @@ struct InfoNceWs {
     size_t bytes;
 };
 
+// Key all-gather through peer "mailboxes" (exchange.cu has the protocol): either a stand-alone kernel
+// (gca_keys_exchange) or fused into the head step -- pushed by extra CTAs of the prep kernel, consumed directly by the
+// enqueue CTAs of the finalize kernel (gca_moco_step_peer).  mailboxes == nullptr: off.
+constexpr int XCHG_SLICES = 4;
+struct PeerXchg {
+    char* const* mailboxes;          // device array [W]: every rank's mailbox as mapped into this process
+    int W, rank;
+    int n4;                          // float4 per rank and step (B * d / 4)
+    unsigned long long* xstate;      // [0] step counter, [1] ticket, [2] timeout flag
+    unsigned long long timeout_ns;   // 0 = wait for ever
+};
+
 static inline int infonce_bpad(int B) { return (B + 127) / 128 * 128; }
 // upper bound on the number of K-splits any kernel family uses (2 CTAs worth per SM, at least 1)
 int infonce_max_splits(int B);
@@ -88,6 +100,60 @@ __device__ __forceinline__ float block_sum(float v, float* smem_red /* >= kThrea
     r = smem_red[0];
     __syncthreads();
     return r;
+}
+
+// ---- peer mailbox primitives (protocol: exchange.cu)
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float4* p) {       // L2 only: the line was written by a peer GPU
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ size_t xchg_flags_off(const PeerXchg& X) { return (size_t)2 * X.W * X.n4 * sizeof(float4); }
+__device__ __forceinline__ unsigned long long* xchg_flag(char* box, const PeerXchg& X, int par, int from, int slice) {
+    return reinterpret_cast<unsigned long long*>(box + xchg_flags_off(X)) + ((size_t)par * X.W + from) * XCHG_SLICES + slice;
+}
+__device__ __forceinline__ float4* xchg_slot(char* box, const PeerXchg& X, int par, int from) {
+    return reinterpret_cast<float4*>(box) + ((size_t)par * X.W + from) * (size_t)X.n4;
+}
+// One CTA: store slice `c` of this rank's keys into rank p's mailbox and publish it.  The bar.sync orders every thread's
+// stores before thread 0's release store (cumulativity), so one system-scope release per CTA is enough.
+__device__ __forceinline__ void xchg_push_slice(const PeerXchg& X, const float4* keys_local, unsigned long long step, int p, int c)
+{
+    const int par = (int)(step & 1ull);
+    const int per = (X.n4 + XCHG_SLICES - 1) / XCHG_SLICES;
+    const int lo = c * per, hi = min(X.n4, lo + per);
+    char* peer = X.mailboxes[p];
+    float4* dst = xchg_slot(peer, X, par, X.rank);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = __ldg(keys_local + i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys_u64(xchg_flag(peer, X, par, X.rank, c), step + 1);
+    }
+}
+// One thread: wait until slice c of rank p's keys for `step` has landed in my mailbox.  Returns false on timeout.
+__device__ __forceinline__ bool xchg_wait_slice(const PeerXchg& X, unsigned long long step, int p, int c)
+{
+    const unsigned long long* f = xchg_flag(X.mailboxes[X.rank], X, (int)(step & 1ull), p, c);
+    if (ld_acquire_sys_u64(f) >= step + 1) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys_u64(f) < step + 1) {
+        if (X.timeout_ns && globaltimer_ns() - t0 > X.timeout_ns) { atomicExch(X.xstate + 2, 1ull); return false; }
+    }
+    return true;
 }
 
 __device__ __forceinline__ float ld_queue(const float* p) { return *p; }

@@ -29,6 +29,7 @@ struct InfoNceStreamParams {
     float* pos_ws;           // [Bpad] positive logits (natural-log units)
     float  T_;               // 1 / inv_T
     int    skip_prep;        // reuse q_bf16_ws / pos_ws from the previous launch on this workspace (profiling)
+    PeerXchg xchg;           // tcgen05 family: extra CTAs of the prep kernel push k[B, d] to every peer's mailbox (off if null)
 };
 
 // ffma family (infonce_ffma.cu)
@@ -59,6 +60,7 @@ struct FinalizeParams {
     // optional fused enqueue (FIN_FULL): keys [enq_N, d] into the full ring queue [enq_K, d]
     void* enq_queue; int enq_dtype; long long enq_K; const float* enq_keys; int enq_N;
     long long enq_index; long long* enq_state;
+    PeerXchg xchg;                 // enq_keys == NULL and xchg on: the rows come from this rank's mailbox (all W*B of them)
     unsigned long long* timebuf;   // bring-up only (tools/tc_timeline.py): entry / exit time stamps
 };
 int infonce_finalize_launch(const FinalizeParams& F, int mode, cudaStream_t st);

@@ -603,9 +603,15 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 __global__ void __launch_bounds__(256)
 infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, int B, int Bpad, float inv_T,
                     __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ pos_ws, float* __restrict__ pos_out,
-                    unsigned long long* timebuf)
+                    unsigned long long* timebuf, const PeerXchg X, int nprep)
 {
     ptx::pdl_launch_dependents();            // the streaming kernel may start its setup and its first queue-tile loads
+    if ((int)blockIdx.x >= nprep) {          // key exchange riding in this launch: push slice c of k to rank p (exchange.cu)
+        const int e = blockIdx.x - nprep;
+        const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(X.xstate);
+        xchg_push_slice(X, reinterpret_cast<const float4*>(k), step, e / XCHG_SLICES, e % XCHG_SLICES);
+        return;
+    }
     const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (timebuf && threadIdx.x == 0) {
         unsigned long long t;
@@ -709,9 +715,12 @@ int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t
     if (rc != GCA_OK) return rc;
     rc = get_queue_tmap(P.q_bf16_ws, P.Bpad, &qmap);
     if (rc != GCA_OK) return rc;
+    if (P.skip_prep && P.xchg.mailboxes) return set_err(GCA_ERR_BAD_ARG, "the peer key exchange rides in the prep kernel");
     if (!P.skip_prep) {
-        infonce_prep_kernel<<<(P.Bpad + 7) / 8, 256, 0, st>>>(P.q, P.k, P.B, P.Bpad, P.inv_T, (__nv_bfloat16*)P.q_bf16_ws,
-                                                              P.pos_ws, P.pos_out, debug_timebuf());
+        const int nprep = (P.Bpad + 7) / 8;
+        const int npush = P.xchg.mailboxes ? P.xchg.W * XCHG_SLICES : 0;
+        infonce_prep_kernel<<<nprep + npush, 256, 0, st>>>(P.q, P.k, P.B, P.Bpad, P.inv_T, (__nv_bfloat16*)P.q_bf16_ws,
+                                                           P.pos_ws, P.pos_out, debug_timebuf(), P.xchg, nprep);
         GCA_LAUNCH_CHECK("infonce_prep_kernel");
         count_launch(1);
     }

@@ -66,6 +66,12 @@ SIGNATURES = {
     "gca_negcos_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gca_ema_chunk_bytes": (c_size_t, []),
     "gca_ema_update": (c_int, [c_void_p, c_int, c_float, c_void_p]),
+    "gca_keys_exchange_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gca_keys_exchange": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "gca_moco_step_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
+                                   c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_size_t, c_void_p]),
     "gca_sim_topk_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gca_sim_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_size_t, c_void_p]),

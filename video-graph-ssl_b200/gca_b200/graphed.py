@@ -108,22 +108,39 @@ class GraphedReplicaStep(GraphedMoCoStep):
     only needs the LOCAL keys for its positives; the gathered keys are first needed by the enqueue at the end of the step.
     Every rank must hold an identical queue and ring pointer (same seed or a broadcast, as upstream)."""
 
-    def __init__(self, moco, batch, group=None, algo=None, state=None):
+    def __init__(self, moco, batch, group=None, algo=None, state=None, exchange=None, fuse_exchange=True):
+        """`exchange`: None -> NCCL all-gather on a side stream.  A gca_b200.peer.PeerKeyExchange (shared by every
+        captured step of this process; the steps then must replay in the same order on all ranks) -> the keys travel
+        through peer memory: fused into the step's own launches (gca_moco_step_peer: pushed by the first launch,
+        enqueued straight from the mailbox by the last; `all_k` is not materialised) or, with fuse_exchange=False, as
+        one stand-alone exchange kernel on the side stream."""
         import torch.distributed as dist
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         super(GraphedReplicaStep, self).__init__(moco, batch, n_enqueue=batch * self.world, algo=algo, state=state)
         self.side = torch.cuda.Stream(moco.memory.device)
         self.keys_ready = torch.cuda.Event()
+        self.exchange = exchange
+        self.fuse_exchange = bool(fuse_exchange) and exchange is not None
 
     def _enqueue_work(self, stream):
         import torch.distributed as dist
         m = self.moco
         dev = m.memory.device
+        if self.fuse_exchange:
+            x = self.exchange
+            _lib.call("gca_moco_step_peer", ptr(self.q), ptr(self.k), ptr(m.memory), self.qd, self.B, self.K, self.d,
+                      1.0 / m.T, _lib.ALGO[self.algo], x.W, x.r, ptr(x.table), ptr(x.xstate), x.timeout_ms, ptr(self.state),
+                      ptr(self.loss), ptr(self.loss_rows), ptr(self.lse), ptr(self.pos), ptr(self.rank), ptr(self.hits),
+                      ptr(self.dq), ptr(self.ws), self.ws.numel(), stream)
+            return
         main = torch.cuda.current_stream(dev)
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            dist.all_gather_into_tensor(self.all_k, self.k, group=self.group)
+            if self.exchange is not None:
+                self.exchange(self.k, self.all_k, ctypes.c_void_p(self.side.cuda_stream))
+            else:
+                dist.all_gather_into_tensor(self.all_k, self.k, group=self.group)
             self.keys_ready.record(self.side)
         # one C call: prep + queue sweep, then (after the event) finalize with the enqueue of the gathered keys riding in it
         _lib.call("gca_moco_step", ptr(self.q), ptr(self.k), ptr(m.memory), self.qd, self.B, self.K, self.d, 1.0 / m.T,
