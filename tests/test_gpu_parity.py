@@ -486,6 +486,44 @@ def test_retrieval_config5_full_size(GF, golden):
     assert len(set(idx[0].cpu().tolist())) == 50
 
 
+@pytest.mark.parametrize("Nq,Ng,d,k", [(200, 1001, 64, 50), (129, 300, 128, 64), (5, 70, 192, 7), (384, 2048, 512, 50)])
+def test_retrieval_tensor_core_path_matches_oracle(GF, Nq, Ng, d, k):
+    """d % 64 == 0 takes the split-bf16 tcgen05 panel (ragged tile edges, panel rows padded to 16 bytes): indices equal
+    the fp32 oracle's stable argsort, similarities to fp32 rounding."""
+    rng = np.random.default_rng(Nq + Ng + d)
+    qry = rng.standard_normal((Nq, d)).astype(np.float32)
+    gal = rng.standard_normal((Ng, d)).astype(np.float32)
+    gal[Ng // 2] = gal[3]                                                  # an exact tie: the lower index must come first
+    idx, val = GF.cosine_topk(cu(T_(qry)), cu(T_(gal)), k)
+    oidx, oval = oracle.cosine_topk(qry, gal, k)
+    got, gv = idx.cpu().numpy(), val.cpu().numpy()
+    np.testing.assert_allclose(gv, oval, rtol=0, atol=3e-6)
+    mism = got != oidx
+    if mism.any():                                                         # only near-ties (below fp32 resolution) may swap
+        r, c = np.nonzero(mism)
+        assert np.all(np.abs(oval[r, c] - gv[r, c]) <= 3e-6) and mism.mean() < 0.002
+        for row in np.unique(r):
+            assert sorted(got[row].tolist()) == sorted(oidx[row].tolist()) or mism[row, -1]
+    three = np.nonzero((got == 3).any(1) & (got == Ng // 2).any(1))[0]
+    for row in three:                                                      # tie order: index 3 before its duplicate
+        assert list(got[row]).index(3) < list(got[row]).index(Ng // 2)
+
+
+def test_retrieval_massive_ties_take_the_fallback(GF):
+    """More candidates at the threshold than the shared list holds (1500 identical gallery rows): k rounds of arg-max."""
+    rng = np.random.default_rng(5)
+    gal = rng.standard_normal((1700, 64)).astype(np.float32)
+    gal[100:1600] = gal[100]
+    qry = np.stack([gal[100], -gal[100], gal[7]]).astype(np.float32)
+    idx, val = GF.cosine_topk(cu(T_(qry)), cu(T_(gal)), 20)
+    got = idx.cpu().numpy()
+    assert got[0].tolist() == list(range(100, 120))                       # all cosine 1: lowest indices first
+    assert got[2][0] == 7
+    oidx, _ = oracle.cosine_topk(qry, gal, 20)
+    assert got[2].tolist() == oidx[2].tolist()
+    assert bool((val[:, :-1] >= val[:, 1:]).all())
+
+
 # ============================================================================================ full-size properties
 def test_headline_shape_full_size(GF):
     """BASELINE metric shape (B=256, K=65536, d=128): both modes against the fp64 oracle, pointer wrap over a lap."""

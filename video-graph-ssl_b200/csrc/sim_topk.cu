@@ -1,7 +1,7 @@
 // K7: retrieval -- cosine similarity matrix + per-query top-k (k <= 64), replacing sklearn cosine_distances +
-// full-row np.argsort in tools/video_retrieval.py:174-186.  Three launches: row inverse norms, a register-tiled fp32 GEMM
-// that writes the [Nq, Ng] similarity panel into the workspace, and a per-row k-round arg-max selection with
-// ties going to the lower gallery index (== stable argsort of the distances).
+// full-row np.argsort in tools/video_retrieval.py:174-186.  The [Nq, Ng] similarity panel goes to the workspace, then a
+// per-row top-k with ties going to the lower gallery index (== stable argsort of the distances).  Panel: split-bf16
+// tcgen05 kernel when d % 64 == 0 (sim_tc.cu); this file keeps the API and the CUDA-core fp32 GEMMs for other widths.
 #include "gca_common.cuh"
 
 namespace gca {
@@ -29,7 +29,7 @@ row_inv_norm_kernel(const float* __restrict__ x, int n, int d, int normalize, fl
 constexpr int ST_BM = 128, ST_BN = 128, ST_BK = 16;
 __global__ void __launch_bounds__(256)
 sim_gemm_kernel(const float* __restrict__ Q, const float* __restrict__ G, int Nq, int Ng, int d,
-                const float* __restrict__ invq, const float* __restrict__ invg, float* __restrict__ C)
+                const float* __restrict__ invq, const float* __restrict__ invg, float* __restrict__ C, long long ldc)
 {
     __shared__ __align__(16) float As[2][ST_BK][ST_BM];
     __shared__ __align__(16) float Bs[2][ST_BK][ST_BN];
@@ -95,7 +95,7 @@ sim_gemm_kernel(const float* __restrict__ Q, const float* __restrict__ G, int Nq
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int cidx = j0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
-            if (cidx < Ng) C[(size_t)r * Ng + cidx] = acc[i][j] * sq * invg[cidx];
+            if (cidx < Ng) C[(size_t)r * ldc + cidx] = acc[i][j] * sq * invg[cidx];
         }
     }
 }
@@ -104,7 +104,7 @@ sim_gemm_kernel(const float* __restrict__ Q, const float* __restrict__ G, int Nq
 constexpr int SS_BM = 64, SS_BN = 64, SS_BK = 16;
 __global__ void __launch_bounds__(256)
 sim_gemm_small_kernel(const float* __restrict__ Q, const float* __restrict__ G, int Nq, int Ng, int d,
-                      const float* __restrict__ invq, const float* __restrict__ invg, float* __restrict__ C)
+                      const float* __restrict__ invq, const float* __restrict__ invg, float* __restrict__ C, long long ldc)
 {
     __shared__ float As[SS_BK][SS_BM + 1];
     __shared__ float Bs[SS_BK][SS_BN + 1];
@@ -138,60 +138,32 @@ sim_gemm_small_kernel(const float* __restrict__ Q, const float* __restrict__ G, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int cidx = j0 + tx * 4 + j;
-            if (cidx < Ng) C[(size_t)r * Ng + cidx] = acc[i][j] * sq * invg[cidx];
+            if (cidx < Ng) C[(size_t)r * ldc + cidx] = acc[i][j] * sq * invg[cidx];
         }
-    }
-}
-
-__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
-
-// one CTA per query row; k rounds of block arg-max with per-thread cached candidates
-__global__ void __launch_bounds__(256)
-row_topk_kernel(float* __restrict__ sim, int Ng, int k, int* __restrict__ idx_out, float* __restrict__ val_out)
-{
-    __shared__ float wv[8];
-    __shared__ int wi[8];
-    __shared__ int win_idx;
-    __shared__ float win_val;
-    float* row = sim + (size_t)blockIdx.x * Ng;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float bv = -INFINITY; int bi = 0x7fffffff;
-    for (int j = tid; j < Ng; j += 256) { const float v = row[j]; if (better(v, j, bv, bi)) { bv = v; bi = j; } }
-    for (int r = 0; r < k; ++r) {
-        float v = bv; int i = bi;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-            if (better(ov, oi, v, i)) { v = ov; i = oi; }
-        }
-        if (lane == 0) { wv[warp] = v; wi[warp] = i; }
-        __syncthreads();
-        if (tid == 0) {
-            float fv = wv[0]; int fi = wi[0];
-            for (int w = 1; w < 8; ++w) if (better(wv[w], wi[w], fv, fi)) { fv = wv[w]; fi = wi[w]; }
-            win_idx = fi; win_val = fv;
-            idx_out[(size_t)blockIdx.x * k + r] = (fi == 0x7fffffff) ? -1 : fi;
-            if (val_out) val_out[(size_t)blockIdx.x * k + r] = fv;
-        }
-        __syncthreads();
-        const int w = win_idx;
-        if (w != 0x7fffffff && (w & 255) == tid) {           // the owner retires the winner and rescans its elements
-            row[w] = -INFINITY;
-            bv = -INFINITY; bi = 0x7fffffff;
-            for (int j = tid; j < Ng; j += 256) { const float x = row[j]; if (better(x, j, bv, bi)) { bv = x; bi = j; } }
-        }
-        __syncthreads();
     }
 }
 
 }  // namespace gca
 
+namespace gca {
+// sim_tc.cu: split-bf16 tcgen05 panel + two-pass row top-k
+bool sim_tc_supported(int d);
+size_t sim_tc_pieces_bytes(int Nq, int Ng, int d);
+int sim_tc_panel(const float* queries, const float* gallery, int Nq, int Ng, int d, int normalize, float* S, long long ldS,
+                 void* pieces, cudaStream_t st);
+int sim_topk_rows(float* S, int Nq, int Ng, long long ldS, int k, int* idx_out, float* val_out, cudaStream_t st);
+}
+
+static long long sim_ld(int Ng) { return ((long long)Ng + 3) / 4 * 4; }       // panel rows stay 16-byte aligned
+
 extern "C" size_t gca_sim_topk_workspace_bytes(int Nq, int Ng, int d, int k)
 {
-    (void)d; (void)k;
-    if (Nq <= 0 || Ng <= 0) return 0;
-    return gca::align_up((size_t)Nq * Ng * sizeof(float), 256) + gca::align_up((size_t)(Nq + Ng) * sizeof(float), 256);
+    (void)k;
+    if (Nq <= 0 || Ng <= 0 || d <= 0) return 0;
+    const size_t panel = gca::align_up((size_t)Nq * sim_ld(Ng) * sizeof(float), 1024);
+    const size_t norms = gca::align_up((size_t)(Nq + Ng) * sizeof(float), 256);
+    const size_t pieces = gca::sim_tc_supported(d) ? gca::sim_tc_pieces_bytes(Nq, Ng, d) : 0;
+    return panel + (pieces > norms ? pieces : norms);
 }
 
 extern "C" int gca_sim_topk(const float* queries, const float* gallery, int Nq, int Ng, int d, int k, int normalize,
@@ -203,21 +175,29 @@ extern "C" int gca_sim_topk(const float* queries, const float* gallery, int Nq, 
     GCA_CHECK_ARG(k >= 1 && k <= 64 && k <= Ng, "gca_sim_topk: k=%d must be in [1, min(64, Ng)]", k);
     if (!workspace || workspace_bytes < gca_sim_topk_workspace_bytes(Nq, Ng, d, k))
         return set_err(GCA_ERR_WORKSPACE, "gca_sim_topk: workspace of %zu bytes needed", gca_sim_topk_workspace_bytes(Nq, Ng, d, k));
+    if (sm_count_cached() < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
     cudaStream_t st = (cudaStream_t)stream;
     float* sim = (float*)workspace;
-    float* invq = (float*)((char*)workspace + align_up((size_t)Nq * Ng * sizeof(float), 256));
+    const long long ld = sim_ld(Ng);
+    char* tail = (char*)workspace + align_up((size_t)Nq * ld * sizeof(float), 1024);
+    if (sim_tc_supported(d)) {
+        // tensor-core path: exact 3-way bf16 split of the normalised rows, 6 MMAs per product term (sim_tc.cu)
+        int rc = sim_tc_panel(queries, gallery, Nq, Ng, d, normalize, sim, ld, tail, st);
+        if (rc != GCA_OK) return rc;
+        return sim_topk_rows(sim, Nq, Ng, ld, k, idx_out, val_out, st);
+    }
+    float* invq = (float*)tail;
     float* invg = invq + Nq;
     row_inv_norm_kernel<<<(Nq + 3) / 4, 128, 0, st>>>(queries, Nq, d, normalize, invq);
     row_inv_norm_kernel<<<(Ng + 3) / 4, 128, 0, st>>>(gallery, Ng, d, normalize, invg);
     if (d % 4 == 0) {
         dim3 grid((Ng + ST_BN - 1) / ST_BN, (Nq + ST_BM - 1) / ST_BM);
-        sim_gemm_kernel<<<grid, 256, 0, st>>>(queries, gallery, Nq, Ng, d, invq, invg, sim);
+        sim_gemm_kernel<<<grid, 256, 0, st>>>(queries, gallery, Nq, Ng, d, invq, invg, sim, ld);
     } else {
         dim3 grid((Ng + SS_BN - 1) / SS_BN, (Nq + SS_BM - 1) / SS_BM);
-        sim_gemm_small_kernel<<<grid, 256, 0, st>>>(queries, gallery, Nq, Ng, d, invq, invg, sim);
+        sim_gemm_small_kernel<<<grid, 256, 0, st>>>(queries, gallery, Nq, Ng, d, invq, invg, sim, ld);
     }
-    row_topk_kernel<<<Nq, 256, 0, st>>>(sim, Ng, k, idx_out, val_out);
     GCA_LAUNCH_CHECK("sim_topk kernels");
-    count_launch(4);
-    return GCA_OK;
+    count_launch(3);
+    return sim_topk_rows(sim, Nq, Ng, ld, k, idx_out, val_out, st);
 }

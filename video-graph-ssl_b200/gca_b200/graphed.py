@@ -82,6 +82,31 @@ class GraphedMoCoStep(object):
         self.graph = g
         return self
 
+    def capture_host_io(self, host_in, host_out):
+        """A second graph for callers whose step inputs live in (pinned) host memory: H2D copy of `host_in` into the packed
+        input buffer -> the step -> D2H copy of the packed outputs (loss, top-1/top-5 hits, dq) into `host_out`, all in ONE
+        graph launch.  `host_in` / `host_out` are fixed pinned tensors shaped like .inputs / .outputs; `step_host_io()`
+        replays it (the caller synchronises the stream before reading host_out)."""
+        if self.graph is None:
+            self.capture()
+        if not (host_in.is_pinned() and host_out.is_pinned()):
+            raise ValueError("host buffers must be pinned")
+        if host_in.shape != self.inputs.shape or host_out.shape != self.outputs.shape:
+            raise ValueError("host buffers must match .inputs %r and .outputs %r" % (tuple(self.inputs.shape), tuple(self.outputs.shape)))
+        dev = self.moco.memory.device
+        self._host_io = (host_in, host_out)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.inputs.copy_(host_in, non_blocking=True)
+            self._enqueue_work(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            host_out.copy_(self.outputs, non_blocking=True)
+        self.graph_io = g
+        return self
+
+    def step_host_io(self):
+        self.graph_io.replay()
+        self.moco.index = (self.moco.index + self.N) % self.K
+
     def step(self, q=None, k=None, all_k=None):
         """Replay one step.  Tensors given here are copied into the static buffers first (device-side copies);
         results are in .loss, .hits (int32 [2]), .dq, .rank, .lse until the next replay."""
