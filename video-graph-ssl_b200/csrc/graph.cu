@@ -32,8 +32,126 @@ graph_fwd_kernel(const GraphArgs a)
 }
 
 // grid-parallel aggregation for large feature maps: grid = (chunks, B, jobs)
+// T <= 8 with 128-bit columns (the shipped shapes): a thread's T row loads do not depend on the mixing matrix, so they are
+// issued BEFORE the matrix is fetched and the block synchronises -- one memory round trip per CTA instead of two -- and the
+// register budget (64) lets 4 CTAs per SM keep ~128 KB of loads in flight.
 template <int TMAX>
-__global__ void __launch_bounds__(G_THREADS, (TMAX <= 8) ? 2 : 1)      // T <= 8: cap registers so 2 CTAs/SM keep enough loads in flight
+__global__ void __launch_bounds__(G_THREADS, 4)
+graph_agg_vec4_kernel(const AggJobs jobs)
+{
+    __shared__ float M[TMAX * TMAX];
+    const AggJob jb = jobs.j[blockIdx.z];
+    const int T = jobs.T, b = blockIdx.y, S = jb.S;
+    const size_t off = (size_t)b * jb.Cn * T * S;
+    const int stride = gridDim.x * G_THREADS;
+    const int SV = S / 4, n_items = jb.Cn * SV;
+    const float* in = jb.in + off;
+    float* out = jb.out + off;
+    float4 x[TMAX];
+    int item = blockIdx.x * G_THREADS + threadIdx.x;
+    size_t base = 0;
+    if (item < n_items) {
+        const int c = item / SV, sv = item - c * SV;
+        base = (size_t)c * T * S + (size_t)sv * 4;
+#pragma unroll
+        for (int j = 0; j < TMAX; ++j) if (j < T) x[j] = __ldg(reinterpret_cast<const float4*>(in + base + (size_t)j * S));
+    }
+    // M is stored [i][j] in shared memory already transposed if the job asks for it, padded to TMAX columns
+    for (int p = threadIdx.x; p < TMAX * TMAX; p += G_THREADS) {
+        const int i = p / TMAX, j = p - i * TMAX;
+        float m = 0.f;
+        if (i < T && j < T) m = __ldg(jb.M + (size_t)b * T * T + (jb.transpose ? j * T + i : i * T + j));
+        M[p] = m;
+    }
+    __syncthreads();
+    while (item < n_items) {
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i) {
+            if (i < T) {
+                float4 y = jb.skip ? x[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < TMAX; ++j) {
+                    if (j < T) {
+                        const float m = M[i * TMAX + j];
+                        y.x = fmaf(m, x[j].x, y.x); y.y = fmaf(m, x[j].y, y.y);
+                        y.z = fmaf(m, x[j].z, y.z); y.w = fmaf(m, x[j].w, y.w);
+                    }
+                }
+                *reinterpret_cast<float4*>(out + base + (size_t)i * S) = y;
+            }
+        }
+        item += stride;
+        if (item < n_items) {
+            const int c = item / SV, sv = item - c * SV;
+            base = (size_t)c * T * S + (size_t)sv * 4;
+#pragma unroll
+            for (int j = 0; j < TMAX; ++j) if (j < T) x[j] = __ldg(reinterpret_cast<const float4*>(in + base + (size_t)j * S));
+        }
+    }
+}
+
+// T <= 8, rows that are not 128-bit addressable (e.g. the 7x7 projections): scalar columns, four independent items per
+// thread so that 32 loads are in flight before the mixing matrix is needed
+constexpr int AGG_ILP = 4;
+template <int TMAX>
+__global__ void __launch_bounds__(G_THREADS, 2)
+graph_agg_scalar_kernel(const AggJobs jobs)
+{
+    __shared__ float M[TMAX * TMAX];
+    const AggJob jb = jobs.j[blockIdx.z];
+    const int T = jobs.T, b = blockIdx.y, S = jb.S;
+    const size_t off = (size_t)b * jb.Cn * T * S;
+    const int n_items = jb.Cn * S;
+    const float* in = jb.in + off;
+    float* out = jb.out + off;
+    const int stride = gridDim.x * G_THREADS;
+    float x[AGG_ILP][TMAX];
+    size_t base[AGG_ILP];
+    bool ok[AGG_ILP];
+    int item0 = blockIdx.x * G_THREADS + threadIdx.x;
+    auto load = [&]() {
+#pragma unroll
+        for (int u = 0; u < AGG_ILP; ++u) {
+            const int item = item0 + u * stride;
+            ok[u] = item < n_items;
+            if (ok[u]) {
+                const int c = item / S, sv = item - c * S;
+                base[u] = (size_t)c * T * S + sv;
+#pragma unroll
+                for (int j = 0; j < TMAX; ++j) if (j < T) x[u][j] = __ldg(in + base[u] + (size_t)j * S);
+            }
+        }
+    };
+    load();
+    for (int p = threadIdx.x; p < TMAX * TMAX; p += G_THREADS) {
+        const int i = p / TMAX, j = p - i * TMAX;
+        float m = 0.f;
+        if (i < T && j < T) m = __ldg(jb.M + (size_t)b * T * T + (jb.transpose ? j * T + i : i * T + j));
+        M[p] = m;
+    }
+    __syncthreads();
+    while (item0 < n_items) {
+#pragma unroll
+        for (int u = 0; u < AGG_ILP; ++u) {
+            if (ok[u]) {
+#pragma unroll
+                for (int i = 0; i < TMAX; ++i) {
+                    if (i < T) {
+                        float y = jb.skip ? x[u][i] : 0.f;
+#pragma unroll
+                        for (int j = 0; j < TMAX; ++j) if (j < T) y = fmaf(M[i * TMAX + j], x[u][j], y);
+                        out[base[u] + (size_t)i * S] = y;
+                    }
+                }
+            }
+        }
+        item0 += AGG_ILP * stride;
+        if (item0 < n_items) load();
+    }
+}
+
+template <int TMAX>
+__global__ void __launch_bounds__(G_THREADS, (TMAX <= 8) ? 2 : 1)
 graph_agg_kernel(const AggJobs jobs)
 {
     __shared__ float M[G_TMAXMAX * G_TMAXMAX];
@@ -82,7 +200,7 @@ static int graph_fwd_adj_launch(const GraphArgs& a, bool fused, cudaStream_t st)
     }
 }
 
-int graph_agg_launch(const AggJobs& jobs, int njobs, int B, cudaStream_t st)
+static int agg_launch_group(const AggJobs& jobs, int njobs, int B, bool vec4, cudaStream_t st)
 {
     long long max_items = 0;
     for (int i = 0; i < njobs; ++i) {
@@ -93,6 +211,30 @@ int graph_agg_launch(const AggJobs& jobs, int njobs, int B, cudaStream_t st)
     if (chunks < 1) chunks = 1;
     if (chunks > 256) chunks = 256;
     dim3 grid(chunks, B, njobs);
+    if (vec4) {
+        if (jobs.T <= 4) graph_agg_vec4_kernel<4><<<grid, G_THREADS, 0, st>>>(jobs);
+        else             graph_agg_vec4_kernel<8><<<grid, G_THREADS, 0, st>>>(jobs);
+        GCA_LAUNCH_CHECK("graph_agg_vec4_kernel");
+        count_launch(1);
+        return GCA_OK;
+    }
+    if (jobs.T <= 8) {
+        long long mi = 0;
+        for (int i = 0; i < njobs; ++i) { const long long it = (long long)jobs.j[i].Cn * jobs.j[i].S; if (it > mi) mi = it; }
+        int ch = (int)((mi + (long long)G_THREADS * AGG_ILP - 1) / ((long long)G_THREADS * AGG_ILP));
+        // about two resident CTAs per SM over the whole grid; each thread then loops with its next 32 loads issued right
+        // behind the current stores (one wave, no per-CTA ramp per item)
+        const int want = (2 * sm_count_cached() + B * njobs - 1) / (B * njobs);
+        if (ch > want) ch = want;
+        if (ch < 1) ch = 1;
+        if (ch > 256) ch = 256;
+        dim3 g2(ch, B, njobs);
+        if (jobs.T <= 4) graph_agg_scalar_kernel<4><<<g2, G_THREADS, 0, st>>>(jobs);
+        else             graph_agg_scalar_kernel<8><<<g2, G_THREADS, 0, st>>>(jobs);
+        GCA_LAUNCH_CHECK("graph_agg_scalar_kernel");
+        count_launch(1);
+        return GCA_OK;
+    }
     switch (pick_tmax(jobs.T)) {
         case 4:  graph_agg_kernel<4><<<grid, G_THREADS, 0, st>>>(jobs); break;
         case 8:  graph_agg_kernel<8><<<grid, G_THREADS, 0, st>>>(jobs); break;
@@ -101,6 +243,23 @@ int graph_agg_launch(const AggJobs& jobs, int njobs, int B, cudaStream_t st)
     }
     GCA_LAUNCH_CHECK("graph_agg_kernel");
     count_launch(1);
+    return GCA_OK;
+}
+
+// jobs whose rows are 128-bit addressable (T <= 8) go to the vec4 kernel, the rest to the generic one: two launches at most
+int graph_agg_launch(const AggJobs& jobs, int njobs, int B, cudaStream_t st)
+{
+    AggJobs fast{}, slow{};
+    fast.T = slow.T = jobs.T;
+    int nf = 0, ns = 0;
+    for (int i = 0; i < njobs; ++i) {
+        const AggJob& jb = jobs.j[i];
+        const bool v = jobs.T <= 8 && jb.S % 4 == 0 &&
+                       ((reinterpret_cast<uintptr_t>(jb.in) | reinterpret_cast<uintptr_t>(jb.out)) & 15) == 0;
+        if (v) fast.j[nf++] = jb; else slow.j[ns++] = jb;
+    }
+    if (nf) { const int rc = agg_launch_group(fast, nf, B, true, st); if (rc != GCA_OK) return rc; }
+    if (ns) { const int rc = agg_launch_group(slow, ns, B, false, st); if (rc != GCA_OK) return rc; }
     return GCA_OK;
 }
 

@@ -13,6 +13,32 @@ namespace gca {
 constexpr int PD_THREADS = 256;
 constexpr int PD_MAX_CHUNKS = 64;
 
+// Warp reduction of 64 per-lane values in 62 shuffles instead of 64 x 5: at every butterfly step a lane keeps half of its
+// values and hands the other half to its partner, so after 5 steps lane L holds the two complete sums with indices
+// 2 * bitrev-free code(L) + {0, 1}:  idx = 32*b4 + 16*b3 + 8*b2 + 4*b1 + 2*b0 + r  (b_k = bit k of L).  Fixed order.
+__device__ __forceinline__ void warp_reduce64(float (&v)[64], int lane)
+{
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { const bool up = lane & 16; const float send = up ? v[k] : v[k + 32], keep = up ? v[k + 32] : v[k];
+                                   v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { const bool up = lane & 8; const float send = up ? v[k] : v[k + 16], keep = up ? v[k + 16] : v[k];
+                                   v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const bool up = lane & 4; const float send = up ? v[k] : v[k + 8], keep = up ? v[k + 8] : v[k];
+                                  v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const bool up = lane & 2; const float send = up ? v[k] : v[k + 4], keep = up ? v[k + 4] : v[k];
+                                  v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2); }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { const bool up = lane & 1; const float send = up ? v[k] : v[k + 2], keep = up ? v[k + 2] : v[k];
+                                  v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1); }
+}
+__device__ __forceinline__ int warp_reduce64_index(int lane)
+{
+    return 32 * ((lane >> 4) & 1) + 16 * ((lane >> 3) & 1) + 8 * ((lane >> 2) & 1) + 4 * ((lane >> 1) & 1) + 2 * (lane & 1);
+}
+
 __global__ void __launch_bounds__(PD_THREADS)
 pairdots_partial_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int Cn, int T, int S, int nchunk,
                         float* __restrict__ partials /* [videos, nchunk, T*T] */)
@@ -70,6 +96,59 @@ pairdots_partial_kernel(const float* __restrict__ A, const float* __restrict__ B
     }
 }
 
+// same partials for T <= 8 and S % 4 == 0 with 128-bit loads: 16 independent float4 loads (256 B) in flight per thread
+__global__ void __launch_bounds__(PD_THREADS, 2)
+pairdots_partial_vec4_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int Cn, int T, int S, int nchunk,
+                             float* __restrict__ partials /* [videos, nchunk, T*T] */)
+{
+    __shared__ float red[PD_THREADS / 32][64];
+    const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int SV = S / 4;
+    const long long E = (long long)Cn * SV;
+    const long long e0 = E * chunk / nchunk, e1 = E * (chunk + 1) / nchunk;
+    const float* Ab = A + (size_t)b * Cn * T * S;
+    const float* Bb = Bm + (size_t)b * Cn * T * S;
+    float* out = partials + ((size_t)b * nchunk + chunk) * T * T;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long e = e0 + tid; e < e1; e += PD_THREADS) {
+        const int c = (int)(e / SV), sv = (int)(e - (long long)c * SV);
+        const size_t base = (size_t)c * T * S + (size_t)sv * 4;
+        float4 a[8], bb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = (i < T) ? __ldg(reinterpret_cast<const float4*>(Ab + base + (size_t)i * S)) : zero;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bb[j] = (j < T) ? __ldg(reinterpret_cast<const float4*>(Bb + base + (size_t)j * S)) : zero;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = acc[i * 8 + j];
+                v = fmaf(a[i].x, bb[j].x, v); v = fmaf(a[i].y, bb[j].y, v);
+                v = fmaf(a[i].z, bb[j].z, v); v = fmaf(a[i].w, bb[j].w, v);
+                acc[i * 8 + j] = v;
+            }
+    }
+    warp_reduce64(acc, lane);
+    {
+        const int idx = warp_reduce64_index(lane);
+        red[warp][idx] = acc[0];
+        red[warp][idx + 1] = acc[1];
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const int i = tid / 8, j = tid % 8;
+        if (i < T && j < T) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < PD_THREADS / 32; ++w) v += red[w][tid];
+            out[i * T + j] = v;
+        }
+    }
+}
+
 template <bool kBwd>
 __global__ void __launch_bounds__(G_THREADS)
 adj_from_partials_kernel(const GraphArgs a, const float* __restrict__ partials, int nchunk)
@@ -77,11 +156,18 @@ adj_from_partials_kernel(const GraphArgs a, const float* __restrict__ partials, 
     __shared__ float m0[G_TMAXMAX * G_TMAXMAX], m1[G_TMAXMAX * G_TMAXMAX], m2[G_TMAXMAX * G_TMAXMAX];
     const int b = blockIdx.x, T = a.T;
     const size_t tt = (size_t)b * T * T;
+    // chunk partials: four interleaved chains per element keep the loads independent; combined in a fixed order
     for (int p = threadIdx.x; p < T * T; p += G_THREADS) {
-        float v = 0.f;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
         const float* src = partials + (size_t)b * nchunk * T * T + p;
-        for (int ch = 0; ch < nchunk; ++ch) v += __ldg(src + (size_t)ch * T * T);
-        m0[p] = v;
+        int ch = 0;
+        for (; ch + 3 < nchunk; ch += 4) {
+            const float a0 = __ldg(src + (size_t)ch * T * T), a1 = __ldg(src + (size_t)(ch + 1) * T * T);
+            const float a2 = __ldg(src + (size_t)(ch + 2) * T * T), a3 = __ldg(src + (size_t)(ch + 3) * T * T);
+            v0 += a0; v1 += a1; v2 += a2; v3 += a3;
+        }
+        for (; ch < nchunk; ++ch) v0 += __ldg(src + (size_t)ch * T * T);
+        m0[p] = (v0 + v1) + (v2 + v3);
     }
     __syncthreads();
     if (kBwd) {
@@ -107,7 +193,22 @@ int graph_split_adj_launch(const GraphArgs& a, bool bwd, float* scratch, cudaStr
     if (nchunk > PD_MAX_CHUNKS) nchunk = PD_MAX_CHUNKS;
     if (nchunk > E) nchunk = (int)E;
     if (nchunk < 1) nchunk = 1;
-    pairdots_partial_kernel<<<dim3(nchunk, a.B), PD_THREADS, 0, st>>>(A, Bm, Cn, a.T, S, nchunk, scratch);
+    {   // two CTAs are resident per SM: among the next few chunk counts take the one whose last wave is fullest
+        const double slots = 2.0 * sm_count_cached();
+        int best = nchunk; double best_fill = 0.0;
+        const long long per_thread_min = (a.T <= 8 && S % 4 == 0) ? 8 : 8;      // elements a thread should still own
+        for (int n = nchunk; n <= nchunk + 8 && n <= PD_MAX_CHUNKS && n <= E; ++n) {
+            if (n > nchunk && E / n < per_thread_min * PD_THREADS) break;
+            const double waves = n * (double)a.B / slots;
+            const double fill = waves / (double)((long long)(waves + 0.999999));
+            if (fill > best_fill + 1e-9) { best_fill = fill; best = n; }
+        }
+        nchunk = best;
+    }
+    if (a.T <= 8 && S % 4 == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bm)) & 15) == 0)
+        pairdots_partial_vec4_kernel<<<dim3(nchunk, a.B), PD_THREADS, 0, st>>>(A, Bm, Cn, a.T, S, nchunk, scratch);
+    else
+        pairdots_partial_kernel<<<dim3(nchunk, a.B), PD_THREADS, 0, st>>>(A, Bm, Cn, a.T, S, nchunk, scratch);
     GCA_LAUNCH_CHECK("pairdots_partial_kernel");
     if (bwd) adj_from_partials_kernel<true><<<a.B, G_THREADS, 0, st>>>(a, scratch, nchunk);
     else     adj_from_partials_kernel<false><<<a.B, G_THREADS, 0, st>>>(a, scratch, nchunk);
