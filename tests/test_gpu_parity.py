@@ -195,6 +195,30 @@ def test_infonce_tcgen05_vs_bf16_input_oracle(GF, B, K):
     del o
 
 
+def test_infonce_tcgen05_unnormalised_inputs_leave_the_packed_loss_word(GF):
+    """Logits far outside [-1/T, 1/T] do not fit the packed fixed-point loss word of the finalize kernel: the stream /
+    prep kernels flag it and the launch takes the wide accumulators -- then the flag is cleared, so a unit-row step on the
+    same workspace goes back to the packed word.  Loss mean and hit counts are checked in all three launches."""
+    gen = torch.Generator().manual_seed(9)
+    T = 0.07
+    mem_big = (torch.randn(4096, 128, generator=gen) * 0.5).to(torch.bfloat16)          # |row| ~ 5.7: logits up to ~ +-400
+    mem_unit = unit_rows(4096, 128, gen).to(torch.bfloat16)
+    q_big, k_big = torch.randn(64, 128, generator=gen) * 0.5, torch.randn(64, 128, generator=gen) * 0.5
+    q_u, k_u = unit_rows(64, 128, gen), unit_rows(64, 128, gen)
+    for q, k, mem in ((q_u, k_u, mem_unit), (q_big, k_big, mem_big), (q_u, -k_u * 1.5, mem_unit), (q_u, k_u, mem_unit)):
+        rq = bf16r(q)
+        pos = (q.double() * k.double()).sum(1) / T
+        neg = (rq.double() @ mem.double().t()) / T
+        lse = torch.logsumexp(torch.cat([pos[:, None], neg], 1), 1)
+        loss_ref = float((lse - pos).mean())
+        r = GF.infonce_forward(cu(q), cu(k), cu(mem), T, algo="tcgen05", want_grad=True)
+        torch.cuda.synchronize()
+        assert abs(float(r["loss"]) - loss_ref) <= 3e-5 * abs(loss_ref), (float(r["loss"]), loss_ref)
+        assert abs(float(r["loss"]) - float(r["loss_rows"].double().mean())) <= 1e-6 * abs(loss_ref)
+        rank = r["rank"].cpu()
+        assert r["hits"].cpu().tolist() == [int((rank < 1).sum()), int((rank < 5).sum())]
+
+
 @pytest.mark.parametrize("B,K", [(32, 4096), (256, 65536)])
 def test_infonce_bf16_mode_within_baseline_tolerance(GF, B, K):
     """bf16 mode against the fp32 reference arithmetic on UNrounded inputs: loss 2e-3, gradient 1e-2 (BASELINE.json)."""

@@ -123,6 +123,9 @@ infonce_finalize_kernel(const FinalizeParams F)
     // Loads first, arithmetic later: warp 0 puts the split statistics of its row in flight (they head the memory queue),
     // then every thread puts its share of the gradient partials in flight (raw values: the split weights are not needed to
     // LOAD them) -- one L2 round trip for the whole block instead of a chain of dependent ones.
+    // control word 6: a stream / prep kernel of the tcgen05 family saw a logit outside the unit-row range (uniform for
+    // the whole launch: written before this kernel started, cleared by the last ticket holder below)
+    const unsigned int range_flag = (kMode == FIN_FULL && F.pk_nb > 0) ? __ldcg(F.counter + 6) : 0u;
     float st_m[FIN_STAT], st_s[FIN_STAT];
     int st_c[FIN_STAT];
     const bool stat_fast = (ns <= 32 * FIN_STAT);
@@ -146,6 +149,7 @@ infonce_finalize_kernel(const FinalizeParams F)
         }
     }
 
+    int row_rank = 0;                                          // thread 0: #negatives above the positive (FIN_FULL)
     if (warp == 0) {
         float lse = 0.f, pos = 0.f;
         if (kMode == FIN_BWD) {
@@ -191,6 +195,7 @@ infonce_finalize_kernel(const FinalizeParams F)
                     F.lse[b] = lse;
                     F.loss_rows[b] = lse - pos;
                     F.rank_gt[b] = cnt;
+                    row_rank = cnt;
                 }
                 const float corr = __expf(m - lse);            // = 1 / S
                 for (int sp = lane; sp < ns; sp += 32) w_s[sp] *= corr;
@@ -201,6 +206,21 @@ infonce_finalize_kernel(const FinalizeParams F)
         if (lane == 0) { row_stat[0] = lse; row_stat[1] = pos; }
     }
     __syncthreads();
+    // Mean loss and top-k hit counts without a second pass over the rows.  Packed form (the usual case): ONE 64-bit
+    // atomicAdd per row carries [ticket | top-1 bit | top-5 bit | loss as a fixed-point integer]; integer addition is
+    // associative, so the total is exact and order-independent (deterministic), and the value the atomic RETURNS to the last
+    // ticket holder plus its own contribution is the complete sum -- no fence, no read-back.  It is issued here, before the
+    // gradient accumulation, and only looked at afterwards, so its L2 round trip is off the critical path.
+    unsigned long long pk_mine = 0ull, pk_old = 0ull;
+    const bool pk_on = (kMode == FIN_FULL) && F.pk_nb > 0 && (F.loss_mean != nullptr || F.top_hits != nullptr) && tid == 0 &&
+                       range_flag == 0u;
+    if (pk_on) {
+        const float lrow = row_stat[0] - row_stat[1];                      // lse - pos of this row (>= 0)
+        const int nb = F.pk_nb;
+        pk_mine = 1ull | ((row_rank < 1 ? 1ull : 0ull) << nb) | ((row_rank < 5 ? 1ull : 0ull) << (2 * nb)) |
+                  ((unsigned long long)__double2ll_rn((double)lrow * (double)(1ull << F.pk_frac)) << (3 * nb));
+        pk_old = atomicAdd(reinterpret_cast<unsigned long long*>(F.counter + 2), pk_mine);
+    }
     if (F.timebuf && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.timebuf[32 * 400 + 4 * blockIdx.x + 1] = t; }
 
     // Gradient accumulator: each of the FIN_GROUPS thread groups sums its interleaved splits in order, then the groups are
@@ -244,11 +264,23 @@ infonce_finalize_kernel(const FinalizeParams F)
     }
 
     if (F.timebuf && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.timebuf[32 * 400 + 4 * blockIdx.x + 2] = t; }
-    // Mean loss and top-k hit counts without a second pass over the rows: every row block adds its loss as a 64-bit
-    // fixed-point integer (2^-36 resolution; integer addition is associative, so the sum is exact and order-independent --
-    // deterministic) and its two hit bits to accumulators in the control block, then takes a ticket; the last ticket holder
-    // converts and re-arms.  counter layout (gca_common.cuh): [0] ticket, [2..3] loss accumulator, [4] top-1, [5] top-5.
-    if (kMode == FIN_FULL && (F.loss_mean != nullptr || F.top_hits != nullptr) && tid == 0) {
+    // counter layout (gca_common.cuh): [0] ticket, [2..3] loss accumulator (or the packed word), [4] top-1, [5] top-5.
+    if (pk_on) {
+        const int nb = F.pk_nb;
+        const unsigned long long mask = (1ull << nb) - 1ull;
+        if ((pk_old & mask) == (unsigned long long)(F.B - 1)) {              // every other row is already in pk_old
+            const unsigned long long tot = pk_old + pk_mine;
+            if (F.loss_mean) *F.loss_mean = (float)((double)(tot >> (3 * nb)) / (double)(1ull << F.pk_frac) / (double)F.B);
+            if (F.top_hits) { F.top_hits[0] = (int)((tot >> nb) & mask); F.top_hits[1] = (int)((tot >> (2 * nb)) & mask); }
+            *reinterpret_cast<unsigned long long*>(F.counter + 2) = 0ull;   // re-arm for the next launch on this workspace
+            if (F.timebuf) {
+                unsigned long long tt;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+                F.timebuf[32 * 1000 + 1] = tt;
+            }
+        }
+    } else if (kMode == FIN_FULL && (F.loss_mean != nullptr || F.top_hits != nullptr) && tid == 0) {
+        // unpacked form (very large B or temperatures so small that the fixed-point fields do not fit 64 bits)
         const float lrow = row_stat[0] - row_stat[1];                      // lse - pos of this row
         unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(F.counter + 2);
         atomicAdd(acc64, (unsigned long long)__double2ll_rn((double)lrow * 68719476736.0));   // exact: ulp(lrow) >= 2^-36
@@ -263,6 +295,7 @@ infonce_finalize_kernel(const FinalizeParams F)
             if (F.loss_mean) *F.loss_mean = (float)((double)tot / 68719476736.0 / (double)F.B);
             if (F.top_hits) { F.top_hits[0] = (int)atomicAdd(F.counter + 4, 0u); F.top_hits[1] = (int)atomicAdd(F.counter + 5, 0u); }
             F.counter[0] = 0u; F.counter[2] = 0u; F.counter[3] = 0u; F.counter[4] = 0u; F.counter[5] = 0u;
+            F.counter[6] = 0u;
             if (F.timebuf) {
                 unsigned long long tt;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
@@ -277,6 +310,20 @@ int infonce_finalize_launch(const FinalizeParams& F_, int mode, cudaStream_t st)
     FinalizeParams F = F_;
     F.timebuf = debug_timebuf();
     if (F.nsplit > FIN_MAX_SPLITS) return set_err(GCA_ERR_UNSUPPORTED, "finalize: %d splits > %d", F.nsplit, FIN_MAX_SPLITS);
+    F.pk_nb = 0; F.pk_frac = 0;
+    if (mode == FIN_FULL && F.range_checked) {
+        // packed loss/hit/ticket word: nb bits each for the ticket and the two hit counts, the rest for the loss sum as a
+        // fixed-point integer.  A row loss is at most 2 L + ln(K+1) when every |logit| <= L; the stream kernels of the
+        // tcgen05 family raise control word 6 when a logit leaves L = 1.0625 / T (unit rows stay within 1 / T), and the
+        // kernel then takes the unpacked path.
+        int nb = 1;
+        while ((1ll << nb) <= (long long)F.B) ++nb;
+        const double lmax = (2.125 * (double)F.inv_T + 45.0) * (double)F.B;
+        int ib = 1;
+        while ((double)(1ull << ib) <= lmax && ib < 40) ++ib;
+        const int frac = 64 - 3 * nb - ib - 1;
+        if (frac >= 20) { F.pk_nb = nb; F.pk_frac = frac > 36 ? 36 : frac; }
+    }
     int enq_blocks = 0;
     if (F.xchg.mailboxes && F.xchg.W * XCHG_SLICES > FIN_THREADS)
         return set_err(GCA_ERR_UNSUPPORTED, "finalize: peer exchange over %d ranks", F.xchg.W);

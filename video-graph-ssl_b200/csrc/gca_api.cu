@@ -189,6 +189,7 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
     F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
     F.part_acc = dq_unit ? ws.part_acc : nullptr;
     F.nsplit = ws.nsplit; F.Bpad = ws.Bpad;
+    F.range_checked = (pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05 && logits_out == nullptr) ? 1 : 0;
     if (keys_ready_event) GCA_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)keys_ready_event, 0));
     return infonce_finalize_launch(F, FIN_FULL, st);
 }

@@ -62,6 +62,8 @@ struct FinalizeParams {
     long long enq_index; long long* enq_state;
     PeerXchg xchg;                 // enq_keys == NULL and xchg on: the rows come from this rank's mailbox (all W*B of them)
     unsigned long long* timebuf;   // bring-up only (tools/tc_timeline.py): entry / exit time stamps
+    int range_checked;             // the stream kernel reports out-of-range logits in control word 6 (tcgen05 family)
+    int pk_nb, pk_frac;            // set by infonce_finalize_launch: packed loss/hits/ticket word (0 = unpacked path)
 };
 int infonce_finalize_launch(const FinalizeParams& F, int mode, cudaStream_t st);
 bool pdl_enabled();                    // programmatic dependent launch between prep -> stream -> finalize (default on)

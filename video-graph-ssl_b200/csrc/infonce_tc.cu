@@ -451,6 +451,9 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         if (g == 0) {
             const size_t po = (size_t)split * P.Bpad + row;
             P.part_max[po] = kFixedMax ? 0.f : m_all * 0.6931471805599453f;  // back to natural-log units
+            // logits beyond the unit-row range (un-normalised inputs): the finalize kernel must not use its packed
+            // fixed-point loss word (control word 6, cleared by the finalize kernel)
+            if (!kFixedMax && valid && m_all * 0.6931471805599453f > 1.0625f * P.inv_T) P.counter[6] = 1u;
             P.part_sum[po] = s_run * w_me + s_o * w_ot;
             P.part_cnt[po] = cnt + c_o;
         }
@@ -603,7 +606,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 __global__ void __launch_bounds__(256)
 infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, int B, int Bpad, float inv_T,
                     __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ pos_ws, float* __restrict__ pos_out,
-                    unsigned long long* timebuf, const PeerXchg X, int nprep)
+                    unsigned long long* timebuf, const PeerXchg X, int nprep, unsigned int* range_flag)
 {
     ptx::pdl_launch_dependents();            // the streaming kernel may start its setup and its first queue-tile loads
     if ((int)blockIdx.x >= nprep) {          // key exchange riding in this launch: push slice c of k to rank p (exchange.cu)
@@ -633,6 +636,7 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
     if (lane == 0) {
         pos_ws[row] = dsum;
         if (pos_out && row < B) pos_out[row] = dsum;
+        if (fabsf(dsum) > 1.0625f * inv_T) range_flag[0] = 1u;        // see the partial write of the stream kernel
     }
 }
 
@@ -720,7 +724,7 @@ int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t
         const int nprep = (P.Bpad + 7) / 8;
         const int npush = P.xchg.mailboxes ? P.xchg.W * XCHG_SLICES : 0;
         infonce_prep_kernel<<<nprep + npush, 256, 0, st>>>(P.q, P.k, P.B, P.Bpad, P.inv_T, (__nv_bfloat16*)P.q_bf16_ws,
-                                                           P.pos_ws, P.pos_out, debug_timebuf(), P.xchg, nprep);
+                                                           P.pos_ws, P.pos_out, debug_timebuf(), P.xchg, nprep, P.counter + 6);
         GCA_LAUNCH_CHECK("infonce_prep_kernel");
         count_launch(1);
     }
