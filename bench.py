@@ -357,7 +357,7 @@ def run_multi(args, rank, world, local_rank):
     if xmode in ("fused", "p2p"):
         try:
             from gca_b200.peer import PeerKeyExchange
-            exchange = PeerKeyExchange(B, D, device=dev)
+            exchange = PeerKeyExchange(B, D, device=dev, timeout_ms=30000)
             probe = batches[0][B:2 * B].contiguous()
             got = torch.empty(world * B, D, device=dev)
             want = torch.empty(world * B, D, device=dev)
@@ -382,6 +382,8 @@ def run_multi(args, rank, world, local_rank):
         s.inputs[:2 * B].copy_(batches[i])
         steps_g.append(s)
     graphed = True
+    torch.cuda.synchronize()
+    dist.barrier()                                           # ranks enter the (peer-synchronised) warm-up launches together
     try:
         for s in steps_g:
             s.capture()
@@ -459,7 +461,19 @@ def run_multi(args, rank, world, local_rank):
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
 
     if exchange is not None:
-        exchange.check()                                    # raises if any in-kernel wait for a peer ever timed out
+        # an in-kernel wait for a peer that timed out (a rank stalled for > 30 s) invalidates the run: every rank agrees on it
+        # and the whole measurement is repeated once with the NCCL all-gather instead
+        bad = torch.tensor([1 if int(exchange.xstate[2]) != 0 else 0], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad) != 0:
+            if rank == 0:
+                print("peer-memory key exchange timed out waiting for a rank; repeating the run with NCCL", file=sys.stderr)
+            dist.barrier()
+            torch.cuda.synchronize()
+            os.environ["GCA_BENCH_EXCHANGE"] = "nccl"
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os.execv(sys.executable, [sys.executable] + sys.argv)
     sharded = time_sharded_k1m(rank, world, dev, flush) if not args.no_sharded else None
     if rank == 0:
         line = {
