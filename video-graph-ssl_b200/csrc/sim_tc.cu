@@ -72,7 +72,7 @@ sim_split_kernel(const float* __restrict__ x, int n, int d, int normalize, __nv_
 
 __global__ void __launch_bounds__(SG_THREADS, 1)
 sim_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
-              int Nq, int Ng, int d, float* __restrict__ S, long long ldS)
+              int Nq, int Ng, int d, float* __restrict__ S, long long ldS, float* __restrict__ tilemax /* [Nq, ntn] */)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -157,6 +157,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
             const int gr = tm * SG_BM + warp * 32 + lane;
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + ab * 128;
             float* out = S + (size_t)gr * ldS + (size_t)tn * SG_BN;
+            float rmax = -INFINITY;                      // max of this row over the tile's valid columns (top-k threshold input)
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t r[32];
@@ -164,6 +165,8 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
                 tc_wait_ld();
                 if (gr < Nq) {
                     const int c0 = tn * SG_BN + ch * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (c0 + j < Ng) rmax = fmaxf(rmax, __uint_as_float(r[j]));
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         if (c0 + j + 3 < Ng) {
@@ -176,6 +179,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
                     }
                 }
             }
+            if (gr < Nq) tilemax[(size_t)gr * ntn + tn] = rmax;
             tc_fence_before();
             mbar_arrive(&bar->acc_empty[ab]);
         }
@@ -192,13 +196,14 @@ __device__ __forceinline__ bool tk_better(float v, int i, float bv, int bi) { re
 constexpr int TK_THREADS = 256, TK_CAP = 1024;
 
 // One CTA per query row, two passes over the row:
-//   1. every thread takes the max of its strided elements; the k-th largest of those 256 maxima is a lower bound `thr` of
-//      the row's k-th largest value (they are k distinct elements >= thr)
+//   1. maxima of up to 256 disjoint parts of the row (per-tile maxima from the panel kernel, or per-thread strided maxima):
+//      the k-th largest of them is a lower bound `thr` of the row's k-th largest value (k distinct elements >= thr)
 //   2. elements >= thr (about 1.5 k of them for unstructured data) go to a shared candidate list, which is rank-sorted by
 //      (value desc, index asc) -- ties towards the lower gallery index like a stable argsort of the distances.
 // More than TK_CAP candidates (massive ties): k rounds of block arg-max over the row instead (rows are scratch).
 __global__ void __launch_bounds__(TK_THREADS)
-row_topk_fast_kernel(float* __restrict__ sim, int Ng, long long ld, int k, int* __restrict__ idx_out, float* __restrict__ val_out)
+row_topk_fast_kernel(float* __restrict__ sim, int Ng, long long ld, int k, int* __restrict__ idx_out, float* __restrict__ val_out,
+                     const float* __restrict__ tilemax, int ntn)
 {
     __shared__ float tmax[TK_THREADS];
     __shared__ float cv[TK_CAP];
@@ -210,23 +215,54 @@ row_topk_fast_kernel(float* __restrict__ sim, int Ng, long long ld, int k, int* 
     __shared__ int win_idx;
     float* row = sim + (size_t)blockIdx.x * ld;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // step 1 input: maxima of disjoint parts of the row -- the panel kernel's per-tile row maxima when it wrote them and
+    // there are at least k of them (saves a whole pass over the row), else each thread's strided maximum
     float mx = -INFINITY;
-    for (int j = tid; j < Ng; j += TK_THREADS) mx = fmaxf(mx, __ldcg(row + j));
+    int nparts = TK_THREADS;
+    if (tilemax != nullptr && ntn >= k && ntn <= TK_THREADS) {
+        nparts = ntn;
+        if (tid < ntn) mx = __ldcg(tilemax + (size_t)blockIdx.x * ntn + tid);
+    } else {
+        for (int j = tid; j < Ng; j += TK_THREADS) mx = fmaxf(mx, __ldcg(row + j));
+    }
     tmax[tid] = mx;
     if (tid == 0) ccount = 0;
     __syncthreads();
-    {
+    if (tid < nparts) {
         int rank = 0;
-        for (int o = 0; o < TK_THREADS; ++o) { const float ov = tmax[o]; rank += (ov > mx || (ov == mx && o < tid)) ? 1 : 0; }
+        for (int o = 0; o < nparts; ++o) { const float ov = tmax[o]; rank += (ov > mx || (ov == mx && o < tid)) ? 1 : 0; }
         if (rank == k - 1) thr_s = mx;
     }
     __syncthreads();
     const float thr = thr_s;
-    for (int j = tid; j < Ng; j += TK_THREADS) {
-        const float v = __ldcg(row + j);
-        if (v >= thr) {
-            const int p = atomicAdd(&ccount, 1);
-            if (p < TK_CAP) { cv[p] = v; ci[p] = j; }
+    if ((ld & 3) == 0 && (reinterpret_cast<uintptr_t>(sim) & 15) == 0) {           // 128-bit loads (rows are 16-byte aligned)
+        const int n4 = Ng >> 2;
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        for (int j4 = tid; j4 < n4; j4 += TK_THREADS) {
+            const float4 v = __ldcg(row4 + j4);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (vv[e] >= thr) {
+                    const int p = atomicAdd(&ccount, 1);
+                    if (p < TK_CAP) { cv[p] = vv[e]; ci[p] = 4 * j4 + e; }
+                }
+            }
+        }
+        for (int j = 4 * n4 + tid; j < Ng; j += TK_THREADS) {
+            const float v = __ldcg(row + j);
+            if (v >= thr) {
+                const int p = atomicAdd(&ccount, 1);
+                if (p < TK_CAP) { cv[p] = v; ci[p] = j; }
+            }
+        }
+    } else {
+        for (int j = tid; j < Ng; j += TK_THREADS) {
+            const float v = __ldcg(row + j);
+            if (v >= thr) {
+                const int p = atomicAdd(&ccount, 1);
+                if (p < TK_CAP) { cv[p] = v; ci[p] = j; }
+            }
         }
     }
     __syncthreads();
@@ -307,7 +343,7 @@ size_t sim_tc_pieces_bytes(int Nq, int Ng, int d) { return align_up((size_t)3 * 
 
 // S[Nq, ldS] = normalised(Q) normalised(G)^T through the split-bf16 tcgen05 kernel; `pieces` is sim_tc_pieces_bytes() of scratch
 int sim_tc_panel(const float* queries, const float* gallery, int Nq, int Ng, int d, int normalize, float* S, long long ldS,
-                 void* pieces, cudaStream_t st)
+                 void* pieces, float* tilemax, cudaStream_t st)
 {
     __nv_bfloat16* pq = (__nv_bfloat16*)pieces;
     __nv_bfloat16* pg = pq + (size_t)3 * Nq * d;
@@ -323,15 +359,18 @@ int sim_tc_panel(const float* queries, const float* gallery, int Nq, int Ng, int
     int grid = sm_count_cached();
     if (grid > ntiles) grid = ntiles;
     GCA_CUDA(cudaFuncSetAttribute(sim_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES));
-    sim_tc_kernel<<<grid, SG_THREADS, SG_SMEM_BYTES, st>>>(amap, bmap, Nq, Ng, d, S, ldS);
+    sim_tc_kernel<<<grid, SG_THREADS, SG_SMEM_BYTES, st>>>(amap, bmap, Nq, Ng, d, S, ldS, tilemax);
     GCA_LAUNCH_CHECK("sim_tc_kernel");
     count_launch(3);
     return GCA_OK;
 }
 
-int sim_topk_rows(float* S, int Nq, int Ng, long long ldS, int k, int* idx_out, float* val_out, cudaStream_t st)
+int sim_tc_col_tiles(int Ng) { return (Ng + SG_BN - 1) / SG_BN; }
+
+int sim_topk_rows(float* S, int Nq, int Ng, long long ldS, int k, int* idx_out, float* val_out, const float* tilemax, int ntn,
+                  cudaStream_t st)
 {
-    row_topk_fast_kernel<<<Nq, TK_THREADS, 0, st>>>(S, Ng, ldS, k, idx_out, val_out);
+    row_topk_fast_kernel<<<Nq, TK_THREADS, 0, st>>>(S, Ng, ldS, k, idx_out, val_out, tilemax, ntn);
     GCA_LAUNCH_CHECK("row_topk_fast_kernel");
     count_launch(1);
     return GCA_OK;

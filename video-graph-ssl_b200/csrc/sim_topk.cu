@@ -150,8 +150,10 @@ namespace gca {
 bool sim_tc_supported(int d);
 size_t sim_tc_pieces_bytes(int Nq, int Ng, int d);
 int sim_tc_panel(const float* queries, const float* gallery, int Nq, int Ng, int d, int normalize, float* S, long long ldS,
-                 void* pieces, cudaStream_t st);
-int sim_topk_rows(float* S, int Nq, int Ng, long long ldS, int k, int* idx_out, float* val_out, cudaStream_t st);
+                 void* pieces, float* tilemax, cudaStream_t st);
+int sim_tc_col_tiles(int Ng);
+int sim_topk_rows(float* S, int Nq, int Ng, long long ldS, int k, int* idx_out, float* val_out, const float* tilemax, int ntn,
+                  cudaStream_t st);
 }
 
 static long long sim_ld(int Ng) { return ((long long)Ng + 3) / 4 * 4; }       // panel rows stay 16-byte aligned
@@ -163,7 +165,8 @@ extern "C" size_t gca_sim_topk_workspace_bytes(int Nq, int Ng, int d, int k)
     const size_t panel = gca::align_up((size_t)Nq * sim_ld(Ng) * sizeof(float), 1024);
     const size_t norms = gca::align_up((size_t)(Nq + Ng) * sizeof(float), 256);
     const size_t pieces = gca::sim_tc_supported(d) ? gca::sim_tc_pieces_bytes(Nq, Ng, d) : 0;
-    return panel + (pieces > norms ? pieces : norms);
+    const size_t tmax = gca::sim_tc_supported(d) ? gca::align_up((size_t)Nq * gca::sim_tc_col_tiles(Ng) * sizeof(float), 256) : 0;
+    return panel + (pieces > norms ? pieces : norms) + tmax;
 }
 
 extern "C" int gca_sim_topk(const float* queries, const float* gallery, int Nq, int Ng, int d, int k, int normalize,
@@ -182,9 +185,10 @@ extern "C" int gca_sim_topk(const float* queries, const float* gallery, int Nq, 
     char* tail = (char*)workspace + align_up((size_t)Nq * ld * sizeof(float), 1024);
     if (sim_tc_supported(d)) {
         // tensor-core path: exact 3-way bf16 split of the normalised rows, 6 MMAs per product term (sim_tc.cu)
-        int rc = sim_tc_panel(queries, gallery, Nq, Ng, d, normalize, sim, ld, tail, st);
+        float* tilemax = (float*)(tail + sim_tc_pieces_bytes(Nq, Ng, d));
+        int rc = sim_tc_panel(queries, gallery, Nq, Ng, d, normalize, sim, ld, tail, tilemax, st);
         if (rc != GCA_OK) return rc;
-        return sim_topk_rows(sim, Nq, Ng, ld, k, idx_out, val_out, st);
+        return sim_topk_rows(sim, Nq, Ng, ld, k, idx_out, val_out, tilemax, sim_tc_col_tiles(Ng), st);
     }
     float* invq = (float*)tail;
     float* invg = invq + Nq;
@@ -199,5 +203,5 @@ extern "C" int gca_sim_topk(const float* queries, const float* gallery, int Nq, 
     }
     GCA_LAUNCH_CHECK("sim_topk kernels");
     count_launch(3);
-    return sim_topk_rows(sim, Nq, Ng, ld, k, idx_out, val_out, st);
+    return sim_topk_rows(sim, Nq, Ng, ld, k, idx_out, val_out, nullptr, 0, st);
 }
