@@ -600,6 +600,35 @@ def test_graphed_step_matches_oracle_over_a_lap(lib, queue_dtype, B, N, K):
     assert torch.equal(moco.memory.cpu(), ref_mem)                          # slot contents: exact
 
 
+def test_graphed_step_host_io_equals_device_step(lib):
+    """step_host_io(): the H2D copy of the pinned inputs, the step and the D2H copy of loss | hits | dq as ONE graph; same
+    bits as step() on device-resident inputs, queue and pointer advance identically."""
+    import gca_b200
+    from gca_b200.graphed import GraphedMoCoStep
+    gen = torch.Generator().manual_seed(77)
+    B, K = 64, 2048
+    mocos = []
+    for _ in range(2):
+        torch.manual_seed(4)
+        mocos.append(gca_b200.RGBMoCo(128, K=K, T=0.07, queue_dtype="bf16").cuda())
+    a = GraphedMoCoStep(mocos[0], B, B).capture()
+    b = GraphedMoCoStep(mocos[1], B, B)
+    host_in = torch.empty(3 * B, 128).pin_memory()
+    host_out = torch.empty(b.outputs.shape).pin_memory()
+    b.capture_host_io(host_in, host_out)
+    with pytest.raises(ValueError):
+        b.capture_host_io(torch.empty(3 * B, 128), host_out)               # pageable memory is refused
+    for it in range(3):
+        pk = torch.cat([unit_rows(B, 128, gen), unit_rows(B, 128, gen), unit_rows(B, 128, gen)])
+        host_in.copy_(pk)
+        a.step(cu(pk[:B]), cu(pk[B:2 * B]), cu(pk[2 * B:]))
+        b.step_host_io()
+        torch.cuda.synchronize()
+        assert torch.equal(host_out, a.outputs.cpu())
+        assert float(host_out[0]) == float(a.loss)
+        assert torch.equal(mocos[0].memory, mocos[1].memory) and mocos[0].index == mocos[1].index == (it + 1) * B
+
+
 # ============================================================================================ EMA (momentum encoder update)
 @pytest.mark.parametrize("layout", ["contiguous", "channels_last_3d"])
 def test_momentum_update_matches_reference_loop(lib, layout):

@@ -9,7 +9,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgca_b200.so")
+LIB_PATH = os.environ.get("GCA_B200_LIB") or os.path.join(_HERE, "libgca_b200.so")   # (override: kernel bring-up builds)
 
 GCA_OK = 0
 GCA_F32, GCA_BF16 = 0, 1
