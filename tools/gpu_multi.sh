@@ -1,3 +1,4 @@
+# Multi-GPU evidence run (gpurun --gpus N -- bash tools/gpu_multi.sh N): parity workers, bench (replicas + K-sharded), pre-train step
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 N=${1:-2}

@@ -1,3 +1,4 @@
+# A/B of the key exchange at N GPUs: fused peer-memory exchange vs NCCL all-gather (bench.py, replicas only)
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 N=${1:-2}
