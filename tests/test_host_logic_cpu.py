@@ -114,3 +114,50 @@ def test_build_aug_block_wraps_named_modules():
     assert isinstance(net.base[0], nn.Conv3d)
     agg = gca_b200.get_agg("avg", "3D")
     assert agg(torch.ones(2, 3, 4)).shape == (2, 4)            # upstream always pools dim 1 (build.py:6)
+
+
+# --------------------------------------------------------------------------------------------- ShuffleBN routing tables
+@pytest.mark.parametrize("world,bsz", [(1, 5), (2, 6), (4, 3), (8, 16)])
+def test_shuffle_plan_reproduces_reference_indexing(world, bsz):
+    """gca_b200.dist.shuffle_plan against the reference's gather-everything indexing (train...:203-215), all ranks
+    simulated in one process: what every rank sends, concatenated by destination, is exactly node_x[this_ids]."""
+    from gca_b200.dist import shuffle_plan
+    from oracle.shuffle import shuffle_bn_all_ranks
+    gen = torch.Generator().manual_seed(world * 100 + bsz)
+    xs = [torch.randn(bsz, 7, generator=gen) for _ in range(world)]
+    ids = torch.randperm(world * bsz, generator=gen)
+    _, _, ref_this = shuffle_bn_all_ranks(xs, lambda t: t, ids)
+    plans = [shuffle_plan(ids, bsz, world, r) for r in range(world)]
+    for r in range(world):
+        rows, sc, rc, place = plans[r]
+        assert sum(sc) == bsz and sum(rc) == bsz
+        assert rc == [plans[s][1][r] for s in range(world)]               # what r receives from s == what s sends to r
+        # emulate the all-to-all: the chunk rank s sends to r, in source-rank order
+        recv = []
+        for s in range(world):
+            srows, ssc = plans[s][0], plans[s][1]
+            off = sum(ssc[:r])
+            recv.append(xs[s][srows[off:off + ssc[r]]])
+        recv = torch.cat(recv)
+        out = torch.empty_like(recv)
+        out[place] = recv
+        assert torch.equal(out, ref_this[r])
+
+
+def test_ema_layout_rules_on_cpu():
+    """MomentumUpdater refuses CPU parameters (no CPU path) and its density check accepts permuted-dense layouts only."""
+    from gca_b200.ema import MomentumUpdater, _dense
+    a = torch.randn(4, 3, 5, 6, 7)
+    assert _dense(a) and _dense(a.to(memory_format=torch.channels_last_3d)) and _dense(a.permute(4, 3, 2, 1, 0))
+    assert not _dense(a[:, :2]) and not _dense(torch.randn(6)[::2])
+    assert _dense(torch.randn(1, 5)) and _dense(torch.randn(()))
+    with pytest.raises(RuntimeError):
+        MomentumUpdater(nn.Linear(3, 3), nn.Linear(3, 3))
+
+
+def test_peer_exchange_and_graphed_steps_need_cuda():
+    """The multi-GPU helpers have no CPU path either: they raise before touching the library."""
+    from gca_b200.graphed import GraphedMoCoStep
+    m = gca_b200.RGBMoCo(32, K=64)
+    with pytest.raises(RuntimeError):
+        GraphedMoCoStep(m, 8)
