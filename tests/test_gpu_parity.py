@@ -195,6 +195,32 @@ def test_infonce_tcgen05_vs_bf16_input_oracle(GF, B, K):
     del o
 
 
+def test_infonce_tcgen05_rank_count_skipped_when_positive_dominates(GF):
+    """Rows whose positive beats every negative let a warp skip the rank count of a step (warp-uniform branch): ranks stay
+    exact for all-dominant rows, for mixed warps (first 40 rows dominant, the rest random) and hit counts follow."""
+    gen = torch.Generator().manual_seed(21)
+    T, B, K = 0.07, 192, 4096
+    mem = unit_rows(K, 128, gen).to(torch.bfloat16)
+    q = unit_rows(B, 128, gen)
+    k = unit_rows(B, 128, gen)
+    k[:40] = q[:40]                                                        # cos = 1: nothing in the queue can beat it
+    k[128:160] = q[128:160]                                                # one whole warp (32 rows) dominant
+    rq = bf16r(q)
+    pos = (q.double() * k.double()).sum(1) / T
+    neg = (rq.double() @ mem.double().t()) / T
+    rank_ref = (neg > pos[:, None]).sum(1)
+    lse = torch.logsumexp(torch.cat([pos[:, None], neg], 1), 1)
+    r = GF.infonce_forward(cu(q), cu(k), cu(mem), T, algo="tcgen05", want_grad=True)
+    torch.cuda.synchronize()
+    rank = r["rank"].cpu().long()
+    assert int(rank[:40].sum()) == 0 and int(rank[128:160].sum()) == 0
+    margin = (neg - pos[:, None]).abs().min(dim=1).values
+    ok = margin > 1e-3
+    assert torch.equal(rank[ok], rank_ref[ok])
+    assert r["hits"].cpu().tolist() == [int((rank < 1).sum()), int((rank < 5).sum())]
+    assert abs(float(r["loss"]) - float((lse - pos).mean())) <= 3e-5 * float((lse - pos).mean())
+
+
 def test_infonce_tcgen05_unnormalised_inputs_leave_the_packed_loss_word(GF):
     """Logits far outside [-1/T, 1/T] do not fit the packed fixed-point loss word of the finalize kernel: the stream /
     prep kernels flag it and the launch takes the wide accumulators -- then the flag is cleared, so a unit-row step on the

@@ -142,6 +142,9 @@ for Bq in (64, 256):
     qb, kb = q[:Bq].contiguous(), k[:Bq].contiguous()
     report("infonce bf16 (tcgen05) fused fwd+grad+finalize B=%d K=65536" % Bq,
            timeit(lambda: GF.infonce_forward(qb, kb, moco.memory, 0.07, algo="tcgen05")), K * 128 * 2, flops=4.0 * Bq * K * 128)
+# a "learnt" encoder: every positive beats the whole queue, so the rank count of each step is skipped (warp-uniform branch)
+report("infonce bf16 (tcgen05) fused fwd+grad+finalize B=256 K=65536, positives dominate (k = q)",
+       timeit(lambda: GF.infonce_forward(q, q, moco.memory, 0.07, algo="tcgen05")), K * 128 * 2, flops=4.0 * B * K * 128)
 K1 = 1 << 20
 big = F.normalize(torch.randn(K1, 128, device="cuda")).to(torch.bfloat16)
 for Bq in (64, 256):

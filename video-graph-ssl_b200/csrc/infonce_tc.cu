@@ -361,6 +361,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < TC_SUB; ++j) if (j >= nvalid) sv[j] = -INFINITY;   // TMA zero-filled rows past K
             }
+            bool count_step = true;
             if (!kFixedMax) {
                 // row max with four independent chains
                 float tm0 = -INFINITY, tm1 = -INFINITY, tm2 = -INFINITY, tm3 = -INFINITY;
@@ -371,7 +372,11 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     tm2 = max3(tm2, sv[j + 4], sv[j + 5]);
                     tm3 = max3(tm3, sv[j + 6], sv[j + 7]);
                 }
-                const float xm = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3)) * c2;   // -inf when the step is fully masked
+                const float raw_max = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3));
+                // no logit of this step beats the positive in any row of the warp: the rank count below is skipped (the
+                // usual case once the encoder has learnt something; with random rows it almost never triggers)
+                count_step = __any_sync(0xffffffffu, raw_max > pos_dot);
+                const float xm = raw_max * c2;                              // -inf when the step is fully masked
                 const bool need = xm > m_run + TC_RESCALE_LOG2;             // (m_run = -inf before the first valid step)
                 if (__any_sync(0xffffffffu, need)) {                        // warp-uniform: TMEM ld/st are collective
                     const float m_new = need ? xm : m_run;
@@ -404,17 +409,28 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
             float cf0 = 0.f, cf1 = 0.f, cf2 = 0.f, cf3 = 0.f;
             uint32_t pk[32];
+            if (count_step) {
 #pragma unroll
-            for (int j = 0; j < TC_SUB; j += 4) {
-                cf0 += (sv[j] > pos_dot) ? 1.f : 0.f;
-                cf1 += (sv[j + 1] > pos_dot) ? 1.f : 0.f;
-                cf2 += (sv[j + 2] > pos_dot) ? 1.f : 0.f;
-                cf3 += (sv[j + 3] > pos_dot) ? 1.f : 0.f;
-                const float p0 = ex2(fmaf(sv[j], c2, neg_m)), p1 = ex2(fmaf(sv[j + 1], c2, neg_m));
-                const float p2 = ex2(fmaf(sv[j + 2], c2, neg_m)), p3 = ex2(fmaf(sv[j + 3], c2, neg_m));
-                rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-                pk[j >> 1] = pack_bf16(p0, p1);
-                pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+                for (int j = 0; j < TC_SUB; j += 4) {
+                    cf0 += (sv[j] > pos_dot) ? 1.f : 0.f;
+                    cf1 += (sv[j + 1] > pos_dot) ? 1.f : 0.f;
+                    cf2 += (sv[j + 2] > pos_dot) ? 1.f : 0.f;
+                    cf3 += (sv[j + 3] > pos_dot) ? 1.f : 0.f;
+                    const float p0 = ex2(fmaf(sv[j], c2, neg_m)), p1 = ex2(fmaf(sv[j + 1], c2, neg_m));
+                    const float p2 = ex2(fmaf(sv[j + 2], c2, neg_m)), p3 = ex2(fmaf(sv[j + 3], c2, neg_m));
+                    rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                    pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < TC_SUB; j += 4) {
+                    const float p0 = ex2(fmaf(sv[j], c2, neg_m)), p1 = ex2(fmaf(sv[j + 1], c2, neg_m));
+                    const float p2 = ex2(fmaf(sv[j + 2], c2, neg_m)), p3 = ex2(fmaf(sv[j + 3], c2, neg_m));
+                    rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                    pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+                }
             }
             cnt += (int)((cf0 + cf1) + (cf2 + cf3));
             s_run += (rs0 + rs1) + (rs2 + rs3);
