@@ -96,6 +96,24 @@ def _worker(rank, world, port, out_dir):
     k = torch.from_numpy(g["k0"])[rank * B_loc:(rank + 1) * B_loc]
     with pytest.raises(ValueError):
         moco(q, k, all_k=keys[:3])                                  # gathered keys must cover every rank's rows
+    # checkpoints: the collective full_state_dict() is the upstream format; loading a full queue keeps the owned slots
+    moco.index = 77
+    sd = moco.full_state_dict(include_pointer=True)
+    assert list(sd.keys()) == ["memory", "index"] and sd["memory"].dtype == torch.float32 and sd["memory"].shape == (K, d)
+    assert torch.equal(sd["memory"], moco.gather_full_queue())
+    fresh = ShardedRGBMoCo(d, K=K, T=T, compute=OracleCompute())
+    fresh.load_state_dict(sd)
+    assert torch.equal(fresh.memory, moco.memory) and fresh.index == 77
+    upstream = {"memory": sd["memory"].clone()}                       # what an unmodified RGBMoCo checkpoint holds
+    fresh2 = ShardedRGBMoCo(d, K=K, T=T, compute=OracleCompute())
+    fresh2.load_state_dict(upstream)
+    assert torch.equal(fresh2.memory, sd["memory"][rank * Ks:(rank + 1) * Ks]) and fresh2.index == 0
+    local = moco.state_dict()                                          # non-collective: this rank's shard
+    assert list(local.keys()) == ["memory"] and torch.equal(local["memory"], moco.memory.float())
+    fresh2.load_state_dict(local)
+    assert torch.equal(fresh2.memory, moco.memory)
+    with pytest.raises((ValueError, RuntimeError)):
+        fresh2.load_state_dict({"memory": torch.zeros(K + 8, d)})
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     dist.destroy_process_group()
 

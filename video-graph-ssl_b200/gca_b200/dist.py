@@ -161,6 +161,38 @@ class ShardedRGBMoCo(nn.Module):
         """The whole [K, d] queue in fp32 (checkpoint format of the reference, train...:278)."""
         return _all_gather_rows(self.memory.float(), self.group)
 
+    # ---- checkpoints -------------------------------------------------------------------------------------------
+    # `state_dict()` stays local and non-collective (the trainer saves on rank 0 only, train...:270-285): it holds this
+    # rank's shard.  `full_state_dict()` is the upstream format -- one fp32 [K, d] `memory` -- and is COLLECTIVE: every rank
+    # calls it, any rank may write the result.  `load_state_dict` takes either; a full queue is cut down to the owned slots.
+    def full_state_dict(self, include_pointer=False):
+        """{'memory': fp32 [K, d]} exactly as `RGBMoCo.state_dict()` / the reference would save it.  With
+        include_pointer=True the ring pointer travels as 'index' (the reference drops it on resume)."""
+        sd = {"memory": self.gather_full_queue().cpu()}
+        if include_pointer:
+            sd["index"] = torch.tensor(int(self.index), dtype=torch.int64)
+        return sd
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super(ShardedRGBMoCo, self)._save_to_state_dict(destination, prefix, keep_vars)
+        if self.memory.dtype == torch.bfloat16:
+            destination[prefix + "memory"] = self.memory.float()
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        key = prefix + "memory"
+        if key in state_dict:
+            mem = state_dict[key]
+            Ks = self.memory.shape[0]
+            if mem.shape[0] == self.K and self.world > 1:            # a full (upstream-format) queue: keep the owned slots
+                mem = mem[self.k_begin:self.k_begin + Ks]
+            elif mem.shape[0] != Ks:
+                raise ValueError("checkpoint queue has %d rows; expected the full %d or this rank's %d"
+                                 % (mem.shape[0], self.K, Ks))
+            state_dict[key] = mem.to(self.memory.dtype)
+        if prefix + "index" in state_dict:
+            self.index = int(state_dict.pop(prefix + "index")) % self.K
+        super(ShardedRGBMoCo, self)._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # ShuffleBN clip exchange (train_video_contrast_dis.py:189-231)
