@@ -107,6 +107,18 @@ int gca_moco_step(const float* q, const float* k, void* queue, int dtype_queue, 
                   float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt, int* top_hits,
                   float* dq_unit, void* workspace, size_t workspace_bytes, void* stream);
 
+/* gca_moco_step with the tail of the projection head fused in (Normalize(2) after the last Linear of ProjectHead,
+ * lib/modeling/project_head.py:4-10, 22-28, applied by both encoders before RGBMoCo.forward): zq and zk are the
+ * UN-normalised [B, d] outputs of that Linear.  The first launch L2-normalises both rows (x / max(||x||, 1e-12)) while it
+ * prepares the bf16 query block and the positives; the last launch pushes the gradient back through the normalisation,
+ *     dz_unit = (g - (g . q) q) / ||zq||,   g = d loss / d q,   q = zq / ||zq||,
+ * and enqueues the normalised keys (enqueue_keys == NULL, N == B) or caller-gathered ones.  k_hat_out [B, d] receives the
+ * normalised keys (may be NULL).  Same launches as gca_moco_step; bf16 queue with d == 128 only (tcgen05 family). */
+int gca_moco_step_proj(const float* zq, const float* zk, void* queue, int dtype_queue, int B, long long K, int d, float inv_T,
+                       int algo, const float* enqueue_keys, int N, long long index, long long* state,
+                       float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt, int* top_hits,
+                       float* dz_unit, float* k_hat_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Stage 1 of gca_infonce_fwd on its own: only the queue-streaming kernel, leaving the per-split partials in the
  * workspace (layout: csrc/gca_common.cuh).  For profiling / roofline timing of the dominant kernel.
  * want_acc: bit 0 = also accumulate the gradient partials; bit 1 = skip the per-step q -> bf16 / positive-logit

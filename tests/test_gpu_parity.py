@@ -626,6 +626,46 @@ def test_graphed_step_matches_oracle_over_a_lap(lib, queue_dtype, B, N, K):
     assert torch.equal(moco.memory.cpu(), ref_mem)                          # slot contents: exact
 
 
+@pytest.mark.parametrize("B,K,with_all_k", [(64, 2048, False), (200, 4096, True), (256, 65536, False)])
+def test_projection_tail_fusion_matches_normalize_then_head(lib, B, K, with_all_k):
+    """gca_moco_step_proj / RGBMoCo.forward_from_projections: Normalize(2) of both projections inside the kernels ==
+    F.normalize followed by the ordinary head, in loss, in the gradient w.r.t. the UN-normalised zq (through the
+    normalisation) and in the enqueued keys."""
+    import gca_b200
+    gen = torch.Generator().manual_seed(B + K)
+    T = 0.07
+    moco = gca_b200.RGBMoCo(128, K=K, T=T, queue_dtype="bf16").cuda()
+    moco.index = K - B // 2                                             # the enqueue wraps
+    mem0 = moco.memory.float().cpu().clone()
+    zq = (torch.randn(B, 128, generator=gen) * 3.0)
+    zk = (torch.randn(B, 128, generator=gen) * 0.2)
+    all_k = unit_rows(B + 24, 128, gen) if with_all_k else None
+    zq_g = cu(zq).requires_grad_(True)
+    out, labels, k_hat = moco.forward_from_projections(zq_g, cu(zk), all_k=None if all_k is None else cu(all_k))
+    loss = gca_b200.NCESoftmaxLoss()(out)
+    loss.backward()
+    torch.cuda.synchronize()
+    # reference arithmetic in fp64 on the CPU: normalise, then the head on the bf16-rounded query (the kernel's arithmetic)
+    zq64 = zq.double().requires_grad_(True)
+    qh = zq64 / zq64.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    kh = zk.double() / zk.double().norm(dim=1, keepdim=True).clamp_min(1e-12)
+    assert rel_max(k_hat, kh) <= 2e-6
+    pos = (qh * kh).sum(1) / T
+    neg = (qh @ mem0.double().t()) / T
+    loss_ref = (torch.logsumexp(torch.cat([pos[:, None], neg], 1), 1) - pos).mean()
+    loss_ref.backward()
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= LOSS_RTOL_BF16 * abs(float(loss_ref.detach()))
+    assert rel_max(zq_g.grad, zq64.grad) <= GRAD_RTOL, rel_max(zq_g.grad, zq64.grad)
+    # the gradient is orthogonal to zq (scale invariance of the normalised head)
+    assert float((zq_g.grad.double().cpu() * zq.double()).sum(1).abs().max()) <= 1e-3 * float(zq_g.grad.abs().max()) * float(zq.norm(dim=1).max())
+    # queue: exactly the RNE-bf16 of the keys the call reports (or of all_k), at the wrapped slots
+    keys = k_hat.cpu() if all_k is None else all_k
+    ref_mem = mem0.clone()
+    idx = oracle.enqueue(ref_mem, keys.to(torch.bfloat16).float(), K - B // 2)
+    assert moco.index == idx and torch.equal(moco.memory.float().cpu(), ref_mem)
+    assert labels.shape == (B,) and int(labels.sum()) == 0
+
+
 def test_graphed_step_host_io_equals_device_step(lib):
     """step_host_io(): the H2D copy of the pinned inputs, the step and the D2H copy of loss | hits | dq as ONE graph; same
     bits as step() on device-resident inputs, queue and pointer advance identically."""

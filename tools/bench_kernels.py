@@ -145,6 +145,18 @@ for Bq in (64, 256):
 # a "learnt" encoder: every positive beats the whole queue, so the rank count of each step is skipped (warp-uniform branch)
 report("infonce bf16 (tcgen05) fused fwd+grad+finalize B=256 K=65536, positives dominate (k = q)",
        timeit(lambda: GF.infonce_forward(q, q, moco.memory, 0.07, algo="tcgen05")), K * 128 * 2, flops=4.0 * B * K * 128)
+# projection-head tail fused (gca_moco_step_proj) vs F.normalize x2 + step + enqueue + the normalisation's autograd backward
+zq_, zk_ = torch.randn(B, 128, device="cuda") * 3, torch.randn(B, 128, device="cuda")
+def proj_fused():
+    GF.moco_step_proj(zq_, zk_, moco.memory, 0.07, 0)
+def proj_unfused():
+    z = zq_.detach().requires_grad_(True)
+    qn, kn = F.normalize(z), F.normalize(zk_)
+    o = GF.infonce_forward(qn, kn, moco.memory, 0.07, algo="tcgen05")
+    GF.enqueue_(moco.memory, kn, 0)
+    qn.backward(o["dq_unit"])
+report("head step from un-normalised projections, normalisation fused (gca_moco_step_proj) B=256 K=65536", timeit(proj_fused),
+       K * 128 * 2, flops=4.0 * B * K * 128, ref_us=timeit(proj_unfused))
 K1 = 1 << 20
 big = F.normalize(torch.randn(K1, 128, device="cuda")).to(torch.bfloat16)
 for Bq in (64, 256):

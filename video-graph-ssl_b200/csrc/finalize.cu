@@ -252,13 +252,22 @@ infonce_finalize_kernel(const FinalizeParams F)
             }
             colsum[grp][col] = a;
             __syncthreads();
+            float t = 0.f;
             if (grp == 0 && c < F.d) {
-                float t = colsum[0][col];
+                t = colsum[0][col];
 #pragma unroll
                 for (int g = 1; g < FIN_GROUPS; ++g) t += colsum[g][col];
                 if (kMode != FIN_SHARD) t = scale * fmaf(p0m1, F.k[(size_t)b * F.d + c], t);
-                out[(size_t)b * F.d + c] = t;
             }
+            if (kMode == FIN_FULL && F.zq != nullptr) {
+                // q = zq / ||zq||  =>  d loss / d zq = (g - (g . q) q) / ||zq||   (g = d loss / d q, this row; d == FIN_COLS)
+                const float inv = F.inv_nq[b];
+                const float qh = (grp == 0 && c < F.d) ? F.zq[(size_t)b * F.d + c] * inv : 0.f;
+                __syncthreads();                                       // colsum is re-used by nobody below; red is free
+                const float dot = block_sum<FIN_THREADS>(t * qh, red);
+                t = (t - dot * qh) * inv;
+            }
+            if (grp == 0 && c < F.d) out[(size_t)b * F.d + c] = t;
             __syncthreads();
         }
     }

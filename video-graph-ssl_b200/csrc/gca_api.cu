@@ -63,6 +63,8 @@ InfoNceWs infonce_ws_carve(void* base, int B, int d, int nsplit)
     w.pos_ws   = (float*)(p + off);                    off += align_up((size_t)w.Bpad * sizeof(float), 256);
     w.q_bf16   = (void*)(p + off);                     off += align_up((size_t)w.Bpad * d * 2, 1024);
     w.part_acc = (float*)(p + off);                    off += align_up(rows * d * sizeof(float), 256);
+    w.k_hat    = (float*)(p + off);                    off += align_up((size_t)w.Bpad * d * sizeof(float), 256);
+    w.inv_nq   = (float*)(p + off);                    off += align_up((size_t)w.Bpad * sizeof(float), 256);
     w.bytes = off;
     return w;
 }
@@ -101,7 +103,8 @@ static int nsplit_for(int algo, int B, long long K, int d)
 static int run_stream(const float* q, const float* k, const void* queue, int dtype_queue, int B, long long K, int d,
                       float inv_T, int algo, const float* lse_fixed, bool want_acc, float* pos_out, float* logits_out,
                       void* workspace, size_t workspace_bytes, InfoNceWs* ws_out, cudaStream_t st, bool skip_prep = false,
-                      FinalizeParams* fuse = nullptr, const PeerXchg* px = nullptr)
+                      FinalizeParams* fuse = nullptr, const PeerXchg* px = nullptr, float* proj_k_hat = nullptr,
+                      bool proj = false)
 {
     const int a = pick_algo(algo, dtype_queue, d);
     if (sm_count_cached() < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
@@ -115,6 +118,12 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
     P.part_acc = want_acc ? ws.part_acc : nullptr;
     P.nsplit = nsplit; P.Bpad = ws.Bpad; P.pos_out = pos_out ? pos_out : ws.pos_tmp; P.logits_out = logits_out; P.ld_logits = K + 1;
     P.q_bf16_ws = ws.q_bf16; P.pos_ws = ws.pos_ws; P.T_ = 1.f / inv_T; P.skip_prep = skip_prep ? 1 : 0;
+    if (proj) {
+        if (a != GCA_ALGO_TCGEN05)
+            return set_err(GCA_ERR_UNSUPPORTED, "projection-tail fusion exists for the tcgen05 family only (bf16 queue, d == 128)");
+        P.k_hat = proj_k_hat ? proj_k_hat : ws.k_hat;
+        P.inv_nq = ws.inv_nq;
+    }
     if (px) {
         if (a != GCA_ALGO_TCGEN05)
             return set_err(GCA_ERR_UNSUPPORTED, "the peer-fused step exists for the tcgen05 family only (bf16 queue, d == 128)");
@@ -155,13 +164,14 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
                             long long K, int d, float inv_T, int algo, float* loss_mean, float* loss_rows, float* lse,
                             float* pos_logit, int* rank_gt, int* top_hits, float* dq_unit, float* logits_out,
                             const float* enq_keys, int enq_N, long long enq_index, long long* enq_state, void* keys_ready_event,
-                            void* workspace, size_t workspace_bytes, void* stream, const gca::PeerXchg* px = nullptr)
+                            void* workspace, size_t workspace_bytes, void* stream, const gca::PeerXchg* px = nullptr,
+                            bool proj = false, float* k_hat_out = nullptr)
 {
     using namespace gca;
     int rc = check_infonce_args(fn, q, k, queue, dtype_queue, B, K, d, inv_T, algo);
     if (rc != GCA_OK) return rc;
     GCA_CHECK_ARG(loss_rows && lse && pos_logit && rank_gt, "%s: loss_rows, lse, pos_logit, rank_gt are required", fn);
-    if (enq_keys) {
+    if (enq_keys || (proj && enq_N > 0)) {
         GCA_CHECK_ARG(enq_N >= 0 && enq_N <= K, "%s: N=%d rows do not fit a ring of %lld slots", fn, enq_N, K);
         GCA_CHECK_ARG(enq_state || (enq_index >= 0 && enq_index < K), "%s: pointer %lld outside [0, %lld)", fn, enq_index, K);
     }
@@ -170,7 +180,7 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
     FinalizeParams F{};
     F.B = B; F.d = d; F.inv_T = inv_T; F.k = k; F.pos = pos_logit;
     F.lse = lse; F.loss_rows = loss_rows; F.rank_gt = rank_gt; F.dq = dq_unit; F.loss_mean = loss_mean; F.top_hits = top_hits;
-    if (enq_keys || px) {
+    if (enq_keys || px || (proj && enq_N > 0)) {
         F.enq_queue = const_cast<void*>(queue); F.enq_dtype = dtype_queue; F.enq_K = K; F.enq_keys = enq_keys; F.enq_N = enq_N;
         F.enq_index = enq_index; F.enq_state = enq_state;
         if (px) F.xchg = *px;
@@ -178,14 +188,19 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
     // tcgen05 with gradient and no materialised logits: one launch does stream + finalize (+ enqueue) behind a grid barrier.
     // (an enqueue that has to wait for an event on another stream keeps the two-kernel path: the wait sits between them)
     const bool fused = pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05 && dq_unit != nullptr && logits_out == nullptr &&
-                       keys_ready_event == nullptr && px == nullptr && infonce_tc_can_fuse(B, K);
+                       keys_ready_event == nullptr && px == nullptr && !proj && infonce_tc_can_fuse(B, K);
     if (fused) {
         return run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, true, pos_logit, nullptr, workspace,
                           workspace_bytes, &ws, st, false, &F);
     }
     rc = run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, dq_unit != nullptr, pos_logit, logits_out,
-                    workspace, workspace_bytes, &ws, st, false, nullptr, px);
+                    workspace, workspace_bytes, &ws, st, false, nullptr, px, k_hat_out, proj);
     if (rc != GCA_OK) return rc;
+    if (proj) {                                          // the finalize kernel works on the normalised keys and maps dq to dzq
+        const float* kh = k_hat_out ? k_hat_out : ws.k_hat;
+        F.k = kh; F.zq = q; F.inv_nq = ws.inv_nq;
+        if (F.enq_queue && F.enq_keys == nullptr) F.enq_keys = kh;
+    }
     F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
     F.part_acc = dq_unit ? ws.part_acc : nullptr;
     F.nsplit = ws.nsplit; F.Bpad = ws.Bpad;
@@ -232,6 +247,21 @@ extern "C" int gca_moco_step_peer(const float* q, const float* k, void* queue, i
     return infonce_fwd_impl("gca_moco_step_peer", q, k, queue, dtype_queue, B, K, d, inv_T, algo, loss_mean, loss_rows, lse,
                             pos_logit, rank_gt, top_hits, dq_unit, nullptr, nullptr, W * B, 0, state, nullptr,
                             workspace, workspace_bytes, stream, &X);
+}
+
+extern "C" int gca_moco_step_proj(const float* zq, const float* zk, void* queue, int dtype_queue, int B, long long K, int d,
+                                  float inv_T, int algo, const float* enqueue_keys, int N, long long index, long long* state,
+                                  float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt,
+                                  int* top_hits, float* dz_unit, float* k_hat_out, void* workspace, size_t workspace_bytes,
+                                  void* stream)
+{
+    using namespace gca;
+    GCA_CHECK_ARG(N >= 0, "gca_moco_step_proj: N < 0");
+    GCA_CHECK_ARG(enqueue_keys != nullptr || N == 0 || N == B,
+                  "gca_moco_step_proj: without enqueue_keys the step enqueues its own B normalised keys (N must be 0 or B)");
+    return infonce_fwd_impl("gca_moco_step_proj", zq, zk, queue, dtype_queue, B, K, d, inv_T, algo, loss_mean, loss_rows, lse,
+                            pos_logit, rank_gt, top_hits, dz_unit, nullptr, enqueue_keys, N, index, state, nullptr,
+                            workspace, workspace_bytes, stream, nullptr, true, k_hat_out);
 }
 
 extern "C" int gca_infonce_partials(const float* q, const float* k, const void* queue, int dtype_queue, int B,

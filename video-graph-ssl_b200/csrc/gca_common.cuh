@@ -43,6 +43,8 @@ struct InfoNceWs {
     float* pos_tmp;     // [Bpad] positive logits when the caller gave no output buffer
     float* pos_ws;      // [Bpad] positive logits for the tcgen05 kernel (written by its prep kernel)
     void*  q_bf16;      // [Bpad, d] bf16 copy of q for the tcgen05 kernel
+    float* k_hat;       // [Bpad, d] L2-normalised keys (projection-tail fusion: written by the prep kernel)
+    float* inv_nq;      // [Bpad] 1 / ||zq|| of the same mode
     int    nsplit;
     int    Bpad;
     size_t bytes;

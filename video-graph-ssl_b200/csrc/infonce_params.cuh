@@ -30,6 +30,9 @@ struct InfoNceStreamParams {
     float  T_;               // 1 / inv_T
     int    skip_prep;        // reuse q_bf16_ws / pos_ws from the previous launch on this workspace (profiling)
     PeerXchg xchg;           // tcgen05 family: extra CTAs of the prep kernel push k[B, d] to every peer's mailbox (off if null)
+    // projection-tail fusion (tcgen05 family): q and k are UN-normalised; the prep kernel L2-normalises both rows
+    float* k_hat;            // [Bpad, d] out: normalised keys (NULL = inputs are already unit rows)
+    float* inv_nq;           // [Bpad] out: 1 / max(||q||, 1e-12)
 };
 
 // ffma family (infonce_ffma.cu)
@@ -62,6 +65,7 @@ struct FinalizeParams {
     long long enq_index; long long* enq_state;
     PeerXchg xchg;                 // enq_keys == NULL and xchg on: the rows come from this rank's mailbox (all W*B of them)
     unsigned long long* timebuf;   // bring-up only (tools/tc_timeline.py): entry / exit time stamps
+    const float* zq; const float* inv_nq;   // projection-tail fusion: dq is pushed back through q = zq / ||zq|| (NULL = off)
     int range_checked;             // the stream kernel reports out-of-range logits in control word 6 (tcgen05 family)
     int pk_nb, pk_frac;            // set by infonce_finalize_launch: packed loss/hits/ticket word (0 = unpacked path)
 };

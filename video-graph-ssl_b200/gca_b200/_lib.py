@@ -72,6 +72,10 @@ SIGNATURES = {
                                    c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_size_t, c_void_p]),
+    "gca_moco_step_proj": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
+                                   c_void_p, c_int, c_longlong, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_size_t, c_void_p]),
     "gca_sim_topk_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gca_sim_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_size_t, c_void_p]),

@@ -96,6 +96,55 @@ def infonce_forward(q, k, queue, T, algo="auto", want_grad=True, materialize=Fal
     return out
 
 
+def moco_step_proj(zq, zk, queue, T, index, enqueue_keys=None, enqueue=True, algo="auto"):
+    """gca_moco_step_proj: the head on UN-normalised projections zq, zk (the L2 normalisation of the projection head
+    fused in), followed by the in-place enqueue of the normalised keys (or of `enqueue_keys`).  Returns a dict with
+    loss, loss_rows, lse, pos, rank, hits, dz_unit (= d loss / d zq), k_hat (normalised keys) and the new pointer."""
+    _need_cuda(zq, zk, queue)
+    zq, zk = _f32c(zq.detach()), _f32c(zk.detach())
+    B, d = zq.shape
+    K = queue.shape[0]
+    dev = zq.device
+    qd = queue_dtype_code(queue)
+    out = {
+        "loss": torch.empty((), dtype=torch.float32, device=dev),
+        "loss_rows": torch.empty(B, dtype=torch.float32, device=dev),
+        "lse": torch.empty(B, dtype=torch.float32, device=dev),
+        "pos": torch.empty(B, dtype=torch.float32, device=dev),
+        "rank": torch.empty(B, dtype=torch.int32, device=dev),
+        "hits": torch.empty(2, dtype=torch.int32, device=dev),
+        "dz_unit": torch.empty(B, d, dtype=torch.float32, device=dev),
+        "k_hat": torch.empty(B, d, dtype=torch.float32, device=dev),
+    }
+    keys = _f32c(enqueue_keys.detach()) if enqueue_keys is not None else None
+    N = 0 if not enqueue else (keys.shape[0] if keys is not None else B)
+    ws = workspace(dev, infonce_workspace_bytes(B, K, d, qd, algo), "infonce")
+    _lib.call("gca_moco_step_proj", ptr(zq), ptr(zk), ptr(queue), qd, B, K, d, 1.0 / T, _lib.ALGO[algo],
+              ptr(keys) if enqueue else None, N, int(index), None,
+              ptr(out["loss"]), ptr(out["loss_rows"]), ptr(out["lse"]), ptr(out["pos"]), ptr(out["rank"]), ptr(out["hits"]),
+              ptr(out["dz_unit"]), ptr(out["k_hat"]), ptr(ws), ws.numel(), _stream(zq))
+    out["index"] = (int(index) + N) % K
+    return out
+
+
+class _InfoNCEFromProjections(torch.autograd.Function):
+    """loss, ... = f(zq; zk, queue) with the projection head's Normalize(2) inside the kernels; the queue is updated in place
+    by the same call (the enqueue rides in the last launch), so nothing is left for the caller to order."""
+
+    @staticmethod
+    def forward(ctx, zq, zk, queue, T, algo, index, all_k):
+        o = moco_step_proj(zq, zk, queue, T, index, enqueue_keys=all_k, algo=algo)
+        ctx.in_dtype = zq.dtype
+        ctx.save_for_backward(o["dz_unit"])
+        ctx.mark_non_differentiable(o["loss_rows"], o["lse"], o["pos"], o["rank"], o["k_hat"])
+        return o["loss"], o["loss_rows"], o["lse"], o["pos"], o["rank"], o["k_hat"]      # (queue: a buffer, updated in place)
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        (dz_unit,) = ctx.saved_tensors
+        return (dz_unit * g_loss).to(ctx.in_dtype), None, None, None, None, None, None
+
+
 def infonce_backward_recompute(q, k, queue, T, lse, grad_scale, algo="auto"):
     """Two-pass backward (gca_infonce_bwd): dq = grad_scale * d(sum_b loss_b)/dq against the given queue."""
     _need_cuda(q, k, queue, lse)

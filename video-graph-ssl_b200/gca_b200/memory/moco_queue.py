@@ -143,6 +143,19 @@ class RGBMoCo(BaseMoCo):
         return tuple(heads) + (self._labels(q),)
 
 
+    def forward_from_projections(self, zq, zk, all_k=None):
+        """`forward(normalize(zq), normalize(zk), all_k=all_k)` with the projection head's trailing `Normalize(2)`
+        (lib/modeling/project_head.py:4-10, 22-28) done inside the kernels: zq / zk are the outputs of the head's last
+        Linear, the gradient flows back to zq through the normalisation, and the normalised keys (or `all_k`, already
+        normalised rows gathered from every rank) are enqueued by the same call.  bf16 queue with n_dim == 128 only.
+        Returns (FusedLogits, labels, k_hat) -- k_hat are the normalised keys, e.g. for the key all-gather."""
+        loss, loss_rows, lse, pos, rank, k_hat = GF._InfoNCEFromProjections.apply(
+            zq, zk.detach(), self.memory, self.T, self.algo, self.index, None if all_k is None else all_k.detach())
+        n = zq.shape[0] if all_k is None else all_k.shape[0]
+        self._update_pointer(n)
+        return FusedLogits(loss, loss_rows, lse, pos, rank, zq.shape[0], self.K), self._labels(zq), k_hat
+
+
 class CMCMoCo(BaseMoCo):
     """Two-modality variant (mem_moco.py:91-142): two queues, cross-modal positives, same kernels."""
 
