@@ -112,6 +112,26 @@ for shape, sub, tag in (((128, 192, 8, 14, 14), True, "c3-fmap"), ((128, 1024, 8
     t_b = timeit(bwd)
     report("graph_bwd %s %s" % (tag, list(shape)), t_b, bwd_bytes)
 
+    def eager_fwd_bwd():    # the same op sequence through autograd (what the reference trainer runs per step)
+        a, b, c = gq.detach().requires_grad_(True), gk.detach().requires_grad_(True), sup.detach().requires_grad_(True)
+        Gq = a.transpose(2, 1).contiguous().view(Bv, T, -1)
+        Gk = b.transpose(2, 1).contiguous().view(Bv, T, -1)
+        sim_ = F.softmax(torch.matmul(Gq, Gk.permute(0, 2, 1)), dim=-1)
+        hop = (torch.arange(T, device="cuda")[:, None] - torch.arange(T, device="cuda")[None, :]).abs()
+        wfull = torch.zeros(T, T, device="cuda")
+        for h in range(min(4, T)):
+            wfull[hop == h] = float(wmat[0, h])
+        adj_ = sim_ * wfull
+        eps = torch.finfo(torch.float32).eps
+        pr, uu = adj_.clamp(min=eps, max=1 - eps), u.clamp(min=eps, max=1 - eps)
+        sg = torch.sigmoid((uu.log() - (-uu).log1p() + pr.log() - (-pr).log1p()) / 1.0)
+        ye = torch.einsum('bij,bcjhw->bcihw', sg, c) + c
+        ye.backward(dy)
+
+    t_eb = timeit(eager_fwd_bwd, n=10, warm=3)
+    report("graph core fwd+bwd %s: %d videos per step" % (tag, Bv), t_f + t_b, fwd_bytes + bwd_bytes, ref_us=t_eb,
+           videos_per_s=round(Bv / ((t_f + t_b) * 1e-6), 0))
+
 # ---- enqueue, negcos
 moco = gca_b200.RGBMoCo(128, K=65536, queue_dtype="bf16").cuda()
 keys = F.normalize(torch.randn(256, 128, device="cuda"))
