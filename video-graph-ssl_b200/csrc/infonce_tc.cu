@@ -274,8 +274,11 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const int nrows = (P.B - row0 < TC_BM) ? (P.B - row0) : TC_BM;        // valid query rows of this block
 
     const long long ntiles = (P.K + TC_BN - 1) / TC_BN;
-    const long long t_begin = ntiles * split / P.nsplit, t_end = ntiles * (split + 1) / P.nsplit;
-    const int n = (int)(t_end - t_begin);
+    // tiles are dealt round-robin: split s takes tiles s, s + nsplit, s + 2 nsplit, ...  At any moment the CTAs of a launch
+    // read one contiguous window of the queue (148 x 32 KB) that moves through it, instead of 148 far-apart streams
+    // that can pile onto the same HBM channels; the online softmax does not care about the order.
+    const int n = (split < ntiles) ? (int)((ntiles - split + P.nsplit - 1) / P.nsplit) : 0;
+#define TC_TILE_OF(i) ((long long)split + (long long)(i) * P.nsplit)
 
     if (threadIdx.x == 0) tc_stamp(dbg, 0);
     pdl_launch_dependents();                 // the finalize kernel may begin its (independent) prologue
@@ -344,7 +347,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             tc_fence_after();
             if (threadIdx.x == 0 && v == 0) tc_stamp(dbg, 4);
             if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 17);
-            const long long key0 = (t_begin + v) * TC_BN + g * TC_SUB;
+            const long long key0 = TC_TILE_OF(v) * TC_BN + g * TC_SUB;
             const int nvalid = (P.K - key0 < TC_SUB) ? (int)((P.K - key0 > 0) ? (P.K - key0) : 0) : TC_SUB;
             uint32_t sr[64];
             tmem_ld32(s_addr, sr);
@@ -517,7 +520,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             auto load_tile = [&](int i) {
                 const int stage = i % TC_STAGES;
                 uint8_t* dst = stages + (size_t)stage * TC_STAGE_BYTES;
-                const int key0 = (int)((t_begin + i) * TC_BN);
+                const int key0 = (int)(TC_TILE_OF(i) * TC_BN);
                 mbar_arrive_expect_tx(&bar->full[stage], TC_STAGE_BYTES);
                 tma_load_2d(dst, &tmap, &bar->full[stage], 0, key0);                     // features  0..63
                 tma_load_2d(dst + TC_HALF_BYTES, &tmap, &bar->full[stage], 64, key0);    // features 64..127
