@@ -226,8 +226,9 @@ def run_single(args):
     host_in = synthetic_batches(3, POOL, B, B, pin=True)
     g0 = steps_g[0]
     host_outs = [torch.empty_like(g0.outputs, device="cpu").pin_memory() for _ in range(POOL)]
+    zc_in = os.environ.get("GCA_BENCH_ZC_IN", "1") == "1"  # first kernel reads q|k (and the enqueue CTAs all_k) from pinned host memory
     for i in range(POOL):
-        steps_g[i].capture_host_io(host_in[i], host_outs[i])
+        steps_g[i].capture_host_io(host_in[i], host_outs[i], zero_copy_out=True, zero_copy_in=zc_in)
     e2e_t = []
     e2e_steps = min(args.steps, 2000)
     e2e_loss = 0.0
@@ -347,8 +348,12 @@ def run_single(args):
         "ms_per_step_median": dev_ms[len(dev_ms) // 2], "wall_s_total": wall, "loss_last": loss_last,
         "clocks": clocks,
         "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                "path": "GraphedMoCoStep.step_host_io(): pinned host q|k|all_k -> H2D -> step (C ABI) -> D2H loss|top-k hits|dq as "
-                        "one graph launch, stream synchronised and the loss read on the host every step",
+                "path": ("GraphedMoCoStep.step_host_io(): the step's first kernel reads q|k from the pinned host buffer over PCIe "
+                         "(zero-copy, each once), its enqueue CTAs read all_k from it, " if zc_in else
+                         "GraphedMoCoStep.step_host_io(): pinned host q|k|all_k -> H2D copy -> step (C ABI), ") +
+                        "its last kernel stores loss|top-k hits|dq straight into the pinned host result buffer -- one graph "
+                        "launch, stream synchronised and the loss read on the host every step",
+                "zero_copy_in": zc_in,
                 "loss_last": e2e_loss},
         "gpu_launches": launches,
         "roofline": roof,

@@ -118,11 +118,12 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
     P.part_acc = want_acc ? ws.part_acc : nullptr;
     P.nsplit = nsplit; P.Bpad = ws.Bpad; P.pos_out = pos_out ? pos_out : ws.pos_tmp; P.logits_out = logits_out; P.ld_logits = K + 1;
     P.q_bf16_ws = ws.q_bf16; P.pos_ws = ws.pos_ws; P.T_ = 1.f / inv_T; P.skip_prep = skip_prep ? 1 : 0;
+    P.k_hat = ws.k_hat; P.inv_nq = ws.inv_nq;           // tcgen05 family: the prep kernel stages k (ffma family: unused)
     if (proj) {
         if (a != GCA_ALGO_TCGEN05)
             return set_err(GCA_ERR_UNSUPPORTED, "projection-tail fusion exists for the tcgen05 family only (bf16 queue, d == 128)");
-        P.k_hat = proj_k_hat ? proj_k_hat : ws.k_hat;
-        P.inv_nq = ws.inv_nq;
+        if (proj_k_hat) P.k_hat = proj_k_hat;
+        P.normalize = 1;
     }
     if (px) {
         if (a != GCA_ALGO_TCGEN05)
@@ -200,6 +201,8 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
         const float* kh = k_hat_out ? k_hat_out : ws.k_hat;
         F.k = kh; F.zq = q; F.inv_nq = ws.inv_nq;
         if (F.enq_queue && F.enq_keys == nullptr) F.enq_keys = kh;
+    } else if (pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05) {
+        F.k = ws.k_hat;                                  // staged by the prep kernel: k is read once per step
     }
     F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
     F.part_acc = dq_unit ? ws.part_acc : nullptr;

@@ -31,8 +31,9 @@ struct InfoNceStreamParams {
     int    skip_prep;        // reuse q_bf16_ws / pos_ws from the previous launch on this workspace (profiling)
     PeerXchg xchg;           // tcgen05 family: extra CTAs of the prep kernel push k[B, d] to every peer's mailbox (off if null)
     // projection-tail fusion (tcgen05 family): q and k are UN-normalised; the prep kernel L2-normalises both rows
-    float* k_hat;            // [Bpad, d] out: normalised keys (NULL = inputs are already unit rows)
-    float* inv_nq;           // [Bpad] out: 1 / max(||q||, 1e-12)
+    float* k_hat;            // [B.., d] out: the positive keys staged for the finalize kernel (normalised if `normalize`)
+    float* inv_nq;           // [Bpad] out: 1 / max(||q||, 1e-12) (normalize only)
+    int    normalize;
 };
 
 // ffma family (infonce_ffma.cu)

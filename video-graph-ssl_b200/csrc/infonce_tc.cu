@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(256)
 infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, int B, int Bpad, float inv_T,
                     __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ pos_ws, float* __restrict__ pos_out,
                     unsigned long long* timebuf, const PeerXchg X, int nprep, unsigned int* range_flag,
-                    float* __restrict__ k_hat, float* __restrict__ inv_nq)
+                    float* __restrict__ k_hat, float* __restrict__ inv_nq, int normalize)
 {
     ptx::pdl_launch_dependents();            // the streaming kernel may start its setup and its first queue-tile loads
     if ((int)blockIdx.x >= nprep) {          // key exchange riding in this launch: push slice c of k to rank p (exchange.cu)
@@ -647,7 +647,7 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
         a = __ldg(reinterpret_cast<const float4*>(q + (size_t)row * TC_D) + lane);
         b = __ldg(reinterpret_cast<const float4*>(k + (size_t)row * TC_D) + lane);
     }
-    if (k_hat != nullptr) {
+    if (normalize) {
         // projection-head tail (Normalize(2), project_head.py:4-10) fused in: both rows become unit rows here
         float na = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w)));
         float nb = fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, b.w * b.w)));
@@ -655,9 +655,11 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
         const float ia = 1.f / fmaxf(sqrtf(na), 1e-12f), ib = 1.f / fmaxf(sqrtf(nb), 1e-12f);
         a.x *= ia; a.y *= ia; a.z *= ia; a.w *= ia;
         b.x *= ib; b.y *= ib; b.z *= ib; b.w *= ib;
-        if (row < B) reinterpret_cast<float4*>(k_hat + (size_t)row * TC_D)[lane] = b;     // (may be a caller buffer of B rows)
         if (lane == 0) inv_nq[row] = ia;
     }
+    // the positive keys are staged in device memory for the finalize kernel (normalised or as given): k itself is read
+    // exactly once per step, so it may live in pinned host memory (zero-copy callers)
+    if (row < B) reinterpret_cast<float4*>(k_hat + (size_t)row * TC_D)[lane] = b;         // (may be a caller buffer of B rows)
     float dsum = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
     dsum = warp_sum(dsum) * inv_T;
     uint2 pk;
@@ -751,14 +753,14 @@ int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t
     rc = get_queue_tmap(P.q_bf16_ws, P.Bpad, &qmap);
     if (rc != GCA_OK) return rc;
     if (P.skip_prep && P.xchg.mailboxes) return set_err(GCA_ERR_BAD_ARG, "the peer key exchange rides in the prep kernel");
-    if (P.k_hat && (P.xchg.mailboxes || P.skip_prep))
+    if (P.normalize && (P.xchg.mailboxes || P.skip_prep))
         return set_err(GCA_ERR_UNSUPPORTED, "projection-tail fusion cannot be combined with the peer exchange or skip_prep");
     if (!P.skip_prep) {
         const int nprep = (P.Bpad + 7) / 8;
         const int npush = P.xchg.mailboxes ? P.xchg.W * XCHG_SLICES : 0;
         infonce_prep_kernel<<<nprep + npush, 256, 0, st>>>(P.q, P.k, P.B, P.Bpad, P.inv_T, (__nv_bfloat16*)P.q_bf16_ws,
                                                            P.pos_ws, P.pos_out, debug_timebuf(), P.xchg, nprep, P.counter + 6,
-                                                           P.k_hat, P.inv_nq);
+                                                           P.k_hat, P.inv_nq, P.normalize);
         GCA_LAUNCH_CHECK("infonce_prep_kernel");
         count_launch(1);
     }

@@ -82,11 +82,15 @@ class GraphedMoCoStep(object):
         self.graph = g
         return self
 
-    def capture_host_io(self, host_in, host_out):
+    def capture_host_io(self, host_in, host_out, zero_copy_out=True, zero_copy_in=False):
         """A second graph for callers whose step inputs live in (pinned) host memory: H2D copy of `host_in` into the packed
-        input buffer -> the step -> D2H copy of the packed outputs (loss, top-1/top-5 hits, dq) into `host_out`, all in ONE
-        graph launch.  `host_in` / `host_out` are fixed pinned tensors shaped like .inputs / .outputs; `step_host_io()`
-        replays it (the caller synchronises the stream before reading host_out)."""
+        input buffer -> the step -> the packed outputs (loss, top-1/top-5 hits, dq) in `host_out`, all in ONE graph launch.
+        With zero_copy_out the finalize kernel stores loss | hits | dq straight into the pinned host buffer over PCIe (posted
+        writes, complete when the stream is synchronised) instead of a D2H copy node behind it; .loss/.hits/.dq then hold
+        the results of step() replays only.  With zero_copy_in there is no H2D copy node either: the first kernel reads q and
+        k from the pinned host buffer over PCIe (each exactly once; k is staged on the device for the last kernel) and the
+        enqueue CTAs read the new keys from it.  `host_in` / `host_out` are fixed pinned tensors shaped like .inputs / .outputs;
+        `step_host_io()` replays the graph (the caller synchronises the stream before reading host_out)."""
         if self.graph is None:
             self.capture()
         if not (host_in.is_pinned() and host_out.is_pinned()):
@@ -95,11 +99,27 @@ class GraphedMoCoStep(object):
             raise ValueError("host buffers must match .inputs %r and .outputs %r" % (tuple(self.inputs.shape), tuple(self.outputs.shape)))
         dev = self.moco.memory.device
         self._host_io = (host_in, host_out)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.inputs.copy_(host_in, non_blocking=True)
-            self._enqueue_work(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-            host_out.copy_(self.outputs, non_blocking=True)
+        saved = (self.loss, self.hits, self.dq)
+        saved_in = (self.q, self.k, self.all_k)
+        if zero_copy_in:
+            if self.qd != _lib.GCA_BF16 or self.d != 128:
+                raise ValueError("zero_copy_in needs the tcgen05 family (bf16 queue, d == 128): its first kernel stages k")
+            self.q, self.k, self.all_k = host_in[:self.B], host_in[self.B:2 * self.B], host_in[2 * self.B:]
+        if zero_copy_out:                                            # pinned memory is device-addressable (unified addressing)
+            self.loss = host_out[0:1]
+            self.hits = host_out[1:3].view(torch.int32)
+            self.dq = host_out[4:].view(self.B, self.d)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                if not zero_copy_in:
+                    self.inputs.copy_(host_in, non_blocking=True)
+                self._enqueue_work(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                if not zero_copy_out:
+                    host_out.copy_(self.outputs, non_blocking=True)
+        finally:
+            self.loss, self.hits, self.dq = saved
+            self.q, self.k, self.all_k = saved_in
         self.graph_io = g
         return self
 
