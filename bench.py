@@ -475,7 +475,19 @@ def run_multi(args, rank, world, local_rank):
     # end to end: pinned host q|k per rank -> H2D -> step -> D2H loss|hits|dq, synchronised per step
     host_in = synthetic_batches(200 + rank, pool, B, 0, pin=True)
     g0 = steps_g[0]
-    host_out = torch.empty_like(g0.outputs, device="cpu").pin_memory()
+    host_outs = [torch.empty_like(g0.outputs, device="cpu").pin_memory() for _ in range(pool)]
+    host_io = graphed
+    if graphed:
+        try:                                                 # same path as at one GPU: no copy nodes, one graph launch per step
+            torch.cuda.synchronize()
+            dist.barrier()
+            for i in range(pool):
+                steps_g[i].capture_host_io(host_in[i], host_outs[i], zero_copy_out=True,
+                                           zero_copy_in=(exchange is not None and xmode == "fused"))   # (NCCL gathers device rows)
+        except Exception as e:
+            host_io = False
+            if rank == 0:
+                print("host-io graph unavailable (%s); copying around the step" % e, file=sys.stderr)
     e2e_t = []
     e2e_steps = min(args.steps, 1000)
     for i in range(args.warmup + e2e_steps):
@@ -483,12 +495,15 @@ def run_multi(args, rank, world, local_rank):
         torch.cuda.synchronize()
         dist.barrier()
         t1 = time.perf_counter()
-        g0.inputs[:2 * B].copy_(host_in[i % pool], non_blocking=True)
-        if graphed:
-            g0.step()
+        if host_io:
+            steps_g[i % pool].step_host_io()
         else:
-            g0._enqueue_work(st)
-        host_out.copy_(g0.outputs, non_blocking=True)
+            g0.inputs[:2 * B].copy_(host_in[i % pool], non_blocking=True)
+            if graphed:
+                g0.step()
+            else:
+                g0._enqueue_work(st)
+            host_outs[0].copy_(g0.outputs, non_blocking=True)
         torch.cuda.synchronize()
         if i >= args.warmup:
             e2e_t.append(time.perf_counter() - t1)
@@ -528,7 +543,10 @@ def run_multi(args, rank, world, local_rank):
                                  "(each global step processes n_gpus x 256 rows)"},
             "wall_s_total": wall, "loss_last": loss_last, "replicas_consistent": consistent, "clocks": clocks,
             "e2e": {"value": world * 1e3 / float(e2e), "unit": UNIT, "h2d_bytes_per_step": 2 * B * D * 4,
-                    "d2h_bytes_per_step": g0.outputs.numel() * 4, "ms_per_step": float(e2e)},
+                    "d2h_bytes_per_step": g0.outputs.numel() * 4, "ms_per_step": float(e2e),
+                    "path": "GraphedReplicaStep.step_host_io(): one graph launch per step, q|k read from / results stored to pinned "
+                            "host buffers by the step's own kernels, host barrier + stream sync every step" if host_io else
+                            "H2D copy -> step -> D2H copy, host barrier + stream sync every step"},
             "gpu_launches": launches,
             "sharded_k1m": sharded,
         }

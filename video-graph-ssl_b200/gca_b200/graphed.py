@@ -95,8 +95,11 @@ class GraphedMoCoStep(object):
             self.capture()
         if not (host_in.is_pinned() and host_out.is_pinned()):
             raise ValueError("host buffers must be pinned")
-        if host_in.shape != self.inputs.shape or host_out.shape != self.outputs.shape:
-            raise ValueError("host buffers must match .inputs %r and .outputs %r" % (tuple(self.inputs.shape), tuple(self.outputs.shape)))
+        # host_in holds q | k | all_k like .inputs, or only q | k when the enqueue keys come from elsewhere (replica steps)
+        full = host_in.shape == self.inputs.shape
+        if not (full or host_in.shape == (2 * self.B, self.d)) or host_out.shape != self.outputs.shape:
+            raise ValueError("host buffers must match .inputs %r (or its q|k part) and .outputs %r"
+                             % (tuple(self.inputs.shape), tuple(self.outputs.shape)))
         dev = self.moco.memory.device
         self._host_io = (host_in, host_out)
         saved = (self.loss, self.hits, self.dq)
@@ -104,7 +107,9 @@ class GraphedMoCoStep(object):
         if zero_copy_in:
             if self.qd != _lib.GCA_BF16 or self.d != 128:
                 raise ValueError("zero_copy_in needs the tcgen05 family (bf16 queue, d == 128): its first kernel stages k")
-            self.q, self.k, self.all_k = host_in[:self.B], host_in[self.B:2 * self.B], host_in[2 * self.B:]
+            self.q, self.k = host_in[:self.B], host_in[self.B:2 * self.B]
+            if full:
+                self.all_k = host_in[2 * self.B:]
         if zero_copy_out:                                            # pinned memory is device-addressable (unified addressing)
             self.loss = host_out[0:1]
             self.hits = host_out[1:3].view(torch.int32)
@@ -113,7 +118,7 @@ class GraphedMoCoStep(object):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 if not zero_copy_in:
-                    self.inputs.copy_(host_in, non_blocking=True)
+                    self.inputs[:host_in.shape[0]].copy_(host_in, non_blocking=True)
                 self._enqueue_work(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
                 if not zero_copy_out:
                     host_out.copy_(self.outputs, non_blocking=True)
