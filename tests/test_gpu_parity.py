@@ -221,6 +221,19 @@ def test_infonce_tcgen05_rank_count_skipped_when_positive_dominates(GF):
     assert abs(float(r["loss"]) - float((lse - pos).mean())) <= 3e-5 * float((lse - pos).mean())
 
 
+def test_infonce_tcgen05_saturated_positive_keeps_the_packed_loss_word_sane(GF):
+    """A perfectly learnt batch (k = q, tiny temperature): every row loss is ~0 and may round to -1 ulp; the packed
+    fixed-point loss word must not wrap -- loss stays ~0 and non-negative, hits = B."""
+    gen = torch.Generator().manual_seed(33)
+    B, K, T = 128, 2048, 0.02
+    mem = unit_rows(K, 128, gen).to(torch.bfloat16)
+    q = unit_rows(B, 128, gen)
+    r = GF.infonce_forward(cu(q), cu(q.clone()), cu(mem), T, algo="tcgen05", want_grad=True)
+    torch.cuda.synchronize()
+    assert 0.0 <= float(r["loss"]) <= 1e-6
+    assert r["hits"].cpu().tolist() == [B, B] and int(r["rank"].sum()) == 0
+
+
 def test_infonce_tcgen05_unnormalised_inputs_leave_the_packed_loss_word(GF):
     """Logits far outside [-1/T, 1/T] do not fit the packed fixed-point loss word of the finalize kernel: the stream /
     prep kernels flag it and the launch takes the wide accumulators -- then the flag is cleared, so a unit-row step on the

@@ -215,7 +215,7 @@ infonce_finalize_kernel(const FinalizeParams F)
     const bool pk_on = (kMode == FIN_FULL) && F.pk_nb > 0 && (F.loss_mean != nullptr || F.top_hits != nullptr) && tid == 0 &&
                        range_flag == 0u;
     if (pk_on) {
-        const float lrow = row_stat[0] - row_stat[1];                      // lse - pos of this row (>= 0)
+        const float lrow = fmaxf(row_stat[0] - row_stat[1], 0.f);          // lse - pos of this row: >= 0 up to rounding
         const int nb = F.pk_nb;
         pk_mine = 1ull | ((row_rank < 1 ? 1ull : 0ull) << nb) | ((row_rank < 5 ? 1ull : 0ull) << (2 * nb)) |
                   ((unsigned long long)__double2ll_rn((double)lrow * (double)(1ull << F.pk_frac)) << (3 * nb));
