@@ -738,6 +738,19 @@ def test_momentum_update_matches_reference_loop(lib, layout):
     assert all(torch.equal(a, b) for a, b in zip(before, ema.parameters()))
     up.step(0.0)
     assert all(torch.equal(a, b) for a, b in zip(model.parameters(), ema.parameters()))
+    # the drop-in function keeps its descriptor table on model_ema and reuses it
+    from gca_b200.ema import momentum_update
+    ref2 = [p.detach().clone() for p in ema.parameters()]
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.25)
+    for _ in range(2):
+        momentum_update(model, ema, 0.9)
+        for r, p in zip(ref2, model.parameters()):
+            r.mul_(0.9).add_(p.detach(), alpha=0.1)
+    torch.cuda.synchronize()
+    assert all(rel_max(e, r) <= 1e-6 for r, e in zip(ref2, ema.parameters()))
+    assert ema._gca_ema_updater[1].numel == up.numel
     with pytest.raises(ValueError):                                     # mismatched layouts are refused, not mis-indexed
         MomentumUpdater(make(), make().to(memory_format=torch.channels_last_3d))
 

@@ -57,10 +57,18 @@ class MomentumUpdater(object):
                   ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
 
 
-def momentum_update(model, model_ema, m, _cache={}):
-    """Drop-in for `Trainer._momentum_update(model, model_ema, m)`; the descriptor table is cached per model pair."""
-    key = (id(model), id(model_ema))
-    up = _cache.get(key)
+def momentum_update(model, model_ema, m):
+    """Drop-in for `Trainer._momentum_update(model, model_ema, m)`.  The descriptor table is built on first use and kept on
+    `model_ema` (rebuilt if it is later paired with another model or a parameter was re-allocated)."""
+    import weakref
+    slot = getattr(model_ema, "_gca_ema_updater", None)
+    up = None
+    if slot is not None:
+        ref, cand = slot
+        if ref() is model and all(p.data_ptr() == q.data_ptr() and e.data_ptr() == f.data_ptr()
+                                  for (p, e), (q, f) in zip(zip(model.parameters(), model_ema.parameters()), cand._keep)):
+            up = cand
     if up is None:
-        up = _cache[key] = MomentumUpdater(model, model_ema)
+        up = MomentumUpdater(model, model_ema)
+        object.__setattr__(model_ema, "_gca_ema_updater", (weakref.ref(model), up))
     up.step(m)
