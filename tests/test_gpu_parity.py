@@ -750,7 +750,8 @@ def test_momentum_update_matches_reference_loop(lib, layout):
             r.mul_(0.9).add_(p.detach(), alpha=0.1)
     torch.cuda.synchronize()
     assert all(rel_max(e, r) <= 1e-6 for r, e in zip(ref2, ema.parameters()))
-    assert ema._gca_ema_updater[1].numel == up.numel
+    from gca_b200.ema import _UPDATERS
+    assert _UPDATERS[ema][1].numel == up.numel
     with pytest.raises(ValueError):                                     # mismatched layouts are refused, not mis-indexed
         MomentumUpdater(make(), make().to(memory_format=torch.channels_last_3d))
 

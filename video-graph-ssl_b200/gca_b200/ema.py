@@ -4,6 +4,7 @@ Mirror of `Trainer._momentum_update(model, model_ema, m)` (tools/train_video_con
     for p1, p2 in zip(model.parameters(), model_ema.parameters()):  p2.data.mul_(m).add_(p1.detach().data, alpha=1 - m)
 """
 import ctypes
+import weakref
 
 import numpy as np
 import torch
@@ -57,11 +58,13 @@ class MomentumUpdater(object):
                   ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
 
 
+_UPDATERS = weakref.WeakKeyDictionary()          # model_ema -> (weakref to model, MomentumUpdater); dies with model_ema
+
+
 def momentum_update(model, model_ema, m):
-    """Drop-in for `Trainer._momentum_update(model, model_ema, m)`.  The descriptor table is built on first use and kept on
-    `model_ema` (rebuilt if it is later paired with another model or a parameter was re-allocated)."""
-    import weakref
-    slot = getattr(model_ema, "_gca_ema_updater", None)
+    """Drop-in for `Trainer._momentum_update(model, model_ema, m)`.  The descriptor table is built on first use and kept
+    per `model_ema` (rebuilt if it is later paired with another model or a parameter was re-allocated)."""
+    slot = _UPDATERS.get(model_ema)
     up = None
     if slot is not None:
         ref, cand = slot
@@ -70,5 +73,5 @@ def momentum_update(model, model_ema, m):
             up = cand
     if up is None:
         up = MomentumUpdater(model, model_ema)
-        object.__setattr__(model_ema, "_gca_ema_updater", (weakref.ref(model), up))
+        _UPDATERS[model_ema] = (weakref.ref(model), up)
     up.step(m)
