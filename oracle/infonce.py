@@ -152,3 +152,18 @@ def sharded_infonce(q, k, queue, T, world):
             p = torch.exp((q @ shard.t()) / T - lse[:, None])
             acc = acc + p @ shard
         return {"loss": (lse - pos).mean(), "lse": lse, "rank": rank, "dq": acc / (T * B)}
+
+
+def head_from_projections(zq, zk, memory, index, T, all_k=None):
+    """The head on the UN-normalised outputs of the projection head's last Linear: `Normalize(2)` of both
+    (lib/modeling/project_head.py:4-10, applied at :22-28 as the last module of `ProjectHead.head`), then
+    `infonce_step`.  Returns its dict plus `dz` = d loss / d zq through the normalisation
+    (dz = (g - (g . q) q) / ||zq||, g = d loss / d q) and `k_hat`, the normalised keys that get enqueued."""
+    q = F.normalize(zq, p=2, dim=1)
+    k = F.normalize(zk, p=2, dim=1)
+    out = infonce_step(q, k, memory, index, T, all_k=all_k)
+    g = out["dq"].to(q.dtype)
+    inv = 1.0 / zq.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    out["dz"] = (g - (g * q).sum(1, keepdim=True) * q) * inv
+    out["k_hat"] = k
+    return out

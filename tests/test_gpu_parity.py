@@ -679,6 +679,31 @@ def test_projection_tail_fusion_matches_normalize_then_head(lib, B, K, with_all_
     assert labels.shape == (B,) and int(labels.sum()) == 0
 
 
+def test_projection_tail_fusion_against_reference_fixture(lib, golden):
+    """The fixture was produced by the reference's own Normalize + RGBMoCo + NCESoftmaxLoss + autograd
+    (oracle/gen_golden_proj.py): fp32 loss / gradient / enqueued rows; the kernels run the bf16-queue mode, so the
+    BASELINE bf16 tolerances apply (loss 2e-3, gradient 1e-2) and the enqueued rows are compared after bf16 rounding."""
+    import gca_b200
+    g = golden("proj_tail")
+    T = float(g["T"])
+    B, K = g["zq"].shape[0], g["memory_before"].shape[0]
+    moco = gca_b200.RGBMoCo(128, K=K, T=T, queue_dtype="bf16").cuda()
+    moco.load_state_dict({"memory": T_(g["memory_before"])})
+    zq = cu(T_(g["zq"])).requires_grad_(True)
+    out, labels, k_hat = moco.forward_from_projections(zq, cu(T_(g["zk"])))
+    loss = gca_b200.NCESoftmaxLoss()(out)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss.detach()) - float(g["loss"])) <= LOSS_RTOL_BF16 * float(g["loss"])
+    assert rel_max(zq.grad, T_(g["dz"])) <= GRAD_RTOL
+    assert moco.index == int(g["index_after"])
+    assert rel_max(k_hat, T_(g["enqueued_rows"])) <= 2e-6
+    got = moco.memory[:B].float().cpu()
+    ref = T_(g["enqueued_rows"]).to(torch.bfloat16).float()
+    assert float((got != ref).float().mean()) <= 2e-3          # only values that sit on a bf16 rounding boundary may differ
+    assert float((got - ref).abs().max()) <= 2.0 ** -8          # ... and then by one bf16 ulp of a unit-row entry at most
+
+
 @pytest.mark.parametrize("zero_copy_out,zero_copy_in", [(True, False), (False, False), (True, True)])
 def test_graphed_step_host_io_equals_device_step(lib, zero_copy_out, zero_copy_in):
     """step_host_io(): the H2D copy of the pinned inputs, the step and the D2H copy of loss | hits | dq as ONE graph; same

@@ -153,3 +153,17 @@ def test_retrieval_small_matches_reference(golden):
     hits = oracle.recall_hits(idx, g["small_query_labels"], g["small_gallery_labels"])
     assert [hits[k] for k in oracle.retrieval.KS] == list(g["small_hits"])
     assert list(g["c5_hits"]) == [28, 151, 349, 666, 1478]
+
+
+def test_projection_tail_oracle_matches_reference_fixture(golden):
+    """oracle.infonce.head_from_projections against what the reference's own Normalize + RGBMoCo + NCESoftmaxLoss + autograd
+    produced (tests/golden/proj_tail.npz, written by oracle/gen_golden_proj.py)."""
+    import torch
+    from oracle.infonce import head_from_projections
+    g = golden("proj_tail")
+    zq, zk, mem = torch.from_numpy(g["zq"]), torch.from_numpy(g["zk"]), torch.from_numpy(g["memory_before"]).clone()
+    o = head_from_projections(zq, zk, mem, 0, float(g["T"]))
+    assert abs(float(o["loss"]) - float(g["loss"])) <= 2e-6 * float(g["loss"])
+    assert float((o["dz"] - torch.from_numpy(g["dz"])).abs().max()) <= 1e-4 * float(np.abs(g["dz"]).max())
+    assert o["index"] == int(g["index_after"])
+    assert torch.equal(mem[:zq.shape[0]], torch.from_numpy(g["enqueued_rows"]))        # slot contents: exact
