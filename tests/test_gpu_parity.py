@@ -679,6 +679,26 @@ def test_projection_tail_fusion_matches_normalize_then_head(lib, B, K, with_all_
     assert labels.shape == (B,) and int(labels.sum()) == 0
 
 
+def test_momentum_update_against_reference_fixture(lib, golden):
+    """tests/golden/ema.npz: parameters before / after two calls of the reference's own Trainer._momentum_update
+    (m = 0.999, then 0.5; oracle/gen_golden_dist.py)."""
+    from gca_b200.ema import MomentumUpdater
+    g = golden("ema")
+    n = int(g["n"])
+
+    class Bag(torch.nn.Module):
+        def __init__(self, key):
+            super().__init__()
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(cu(T_(g["%s%d" % (key, i)]).clone())) for i in range(n)])
+    model, ema = Bag("src"), Bag("before")
+    up = MomentumUpdater(model, ema)
+    for m in g["ms"]:
+        up.step(float(m))
+    torch.cuda.synchronize()
+    for i, p in enumerate(ema.parameters()):
+        assert rel_max(p, T_(g["after%d" % i])) <= 1e-6, i
+
+
 def test_projection_tail_fusion_against_reference_fixture(lib, golden):
     """The fixture was produced by the reference's own Normalize + RGBMoCo + NCESoftmaxLoss + autograd
     (oracle/gen_golden_proj.py): fp32 loss / gradient / enqueued rows; the kernels run the bf16-queue mode, so the

@@ -165,3 +165,48 @@ def test_shuffle_bn_matches_reference_indexing(tmp_path, world):
     port = 31500 + (os.getpid() % 2000) + world
     mp.spawn(_shuffle_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+def _make_encoder(seed):
+    """Same construction as oracle/gen_golden_dist.py::make_encoder (batch-dependent: BatchNorm in train mode)."""
+    g = torch.Generator().manual_seed(seed)
+    net = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(24, 16), torch.nn.BatchNorm1d(16), torch.nn.ReLU(),
+                              torch.nn.Linear(16, 8))
+    with torch.no_grad():
+        for p in net.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+    net.train()
+    return net
+
+
+def _shuffle_fixture_worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from gca_b200.dist import ShuffleBN
+    g = dict(np.load(os.path.join(GOLDEN, "shuffle_bn_w2.npz")))
+    assert int(g["world"]) == world
+    enc = _make_encoder(int(g["encoder_seed"]))
+    sbn = ShuffleBN()
+    for it in range(int(g["iters"])):
+        x = torch.from_numpy(g["r%d_x%d" % (rank, it)])
+        torch.manual_seed(7 + it + 50 * rank)                         # the seeds the fixture generator used
+        k, all_k = sbn(x, enc)
+        assert torch.equal(all_k, torch.from_numpy(g["r%d_all_k%d" % (rank, it)])), ("all_k", it)
+        assert torch.equal(k, torch.from_numpy(g["r%d_k%d" % (rank, it)])), ("k", it)
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_shuffle_bn_against_reference_fixture(tmp_path):
+    """tests/golden/shuffle_bn_w2.npz holds what the reference's own Trainer._shuffle_bn returned under gloo at world size 2
+    (oracle/gen_golden_dist.py executes the method bodies from the reference file): the all-to-all version must return
+    the same k and all_k bit for bit -- same permutation draw, same rows through the batch-dependent encoder."""
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_shuffle_fixture_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
