@@ -38,8 +38,10 @@ _WS = {}
 
 
 def workspace(device, nbytes, tag="default"):
-    """Per-(device, tag) scratch buffer, grown on demand; never shrinks."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    """Per-(device, stream, tag) scratch buffer, grown on demand; never shrinks.  Keyed by the current stream because the
+    kernels of one call keep state in it between launches: two streams must not share one."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, int(torch.cuda.current_stream(idx).cuda_stream), tag)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
