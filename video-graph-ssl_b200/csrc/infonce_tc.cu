@@ -13,6 +13,9 @@
 #include "infonce_params.cuh"
 #include "tc_ptx.cuh"
 #include <stdlib.h>
+#ifndef GCA_TC_FUSED_SWEEP
+#define GCA_TC_FUSED_SWEEP 0      // experimental one-pass softmax sweep (see the stream kernel); 0 = product path
+#endif
 
 namespace gca {
 
@@ -364,6 +367,114 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < TC_SUB; ++j) if (j >= nvalid) sv[j] = -INFINITY;   // TMA zero-filled rows past K
             }
+#if GCA_TC_FUSED_SWEEP
+            // EXPERIMENTAL (off by default, not yet measured): one sweep computes p with the row max of the PREVIOUS steps and
+            // tracks this step's row max alongside, so the max / count / exp work shares one instruction stream (more ALU work
+            // between consecutive MUFU.EX2) instead of a separate, serialised max pass.  If the new max exceeds the old one by
+            // more than the lazy-rescale threshold in some row, the step is redone with the new max (rare after the first
+            // few steps).  The first step of a CTA (no previous max) and fixed-max mode take the two-pass path below.
+            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+            float cf0 = 0.f, cf1 = 0.f, cf2 = 0.f, cf3 = 0.f;
+            uint32_t pk[32];
+            const bool one_pass = !kFixedMax && v > 0 && !__any_sync(0xffffffffu, m_run == -INFINITY);
+            if (one_pass) {
+                float tm0 = -INFINITY, tm1 = -INFINITY, tm2 = -INFINITY, tm3 = -INFINITY;
+                float neg_m = -m_run;
+#pragma unroll
+                for (int j = 0; j < TC_SUB; j += 4) {
+                    cf0 += (sv[j] > pos_dot) ? 1.f : 0.f;
+                    cf1 += (sv[j + 1] > pos_dot) ? 1.f : 0.f;
+                    cf2 += (sv[j + 2] > pos_dot) ? 1.f : 0.f;
+                    cf3 += (sv[j + 3] > pos_dot) ? 1.f : 0.f;
+                    const float p0 = ex2(fmaf(sv[j], c2, neg_m)), p1 = ex2(fmaf(sv[j + 1], c2, neg_m));
+                    const float p2 = ex2(fmaf(sv[j + 2], c2, neg_m)), p3 = ex2(fmaf(sv[j + 3], c2, neg_m));
+                    if ((j & 4) == 0) { tm0 = max3(tm0, sv[j], sv[j + 1]); tm1 = max3(tm1, sv[j + 2], sv[j + 3]); }
+                    else              { tm2 = max3(tm2, sv[j], sv[j + 1]); tm3 = max3(tm3, sv[j + 2], sv[j + 3]); }
+                    rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                    pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+                }
+                const float xm = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3)) * c2;
+                const bool need = xm > m_run + TC_RESCALE_LOG2;
+                if (__any_sync(0xffffffffu, need)) {                        // rare: rescale, then redo the step with the new max
+                    const float m_new = need ? xm : m_run;
+                    const float sc = ex2(m_run - m_new);
+                    s_run *= sc;
+                    m_run = m_new;
+                    if (kWantAcc) {
+                        mbar_wait(&bar->o_done[g], (v - 1) & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch) {
+                            uint32_t t[32];
+                            tmem_ld32(o_addr + 32 * ch, t);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) t[j] = __float_as_uint(__uint_as_float(t[j]) * sc);
+                            tmem_st32(o_addr + 32 * ch, t);
+                        }
+                        tc_wait_st();
+                    }
+                    neg_m = -m_run;
+                    rs0 = rs1 = rs2 = rs3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < TC_SUB; j += 4) {
+                        const float p0 = ex2(fmaf(sv[j], c2, neg_m)), p1 = ex2(fmaf(sv[j + 1], c2, neg_m));
+                        const float p2 = ex2(fmaf(sv[j + 2], c2, neg_m)), p3 = ex2(fmaf(sv[j + 3], c2, neg_m));
+                        rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+                        pk[j >> 1] = pack_bf16(p0, p1);
+                        pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+                    }
+                }
+            } else {
+                if (!kFixedMax) {
+                    float tm0 = -INFINITY, tm1 = -INFINITY, tm2 = -INFINITY, tm3 = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < TC_SUB; j += 8) {
+                        tm0 = max3(tm0, sv[j], sv[j + 1]);
+                        tm1 = max3(tm1, sv[j + 2], sv[j + 3]);
+                        tm2 = max3(tm2, sv[j + 4], sv[j + 5]);
+                        tm3 = max3(tm3, sv[j + 6], sv[j + 7]);
+                    }
+                    const float xm = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3)) * c2;
+                    const bool need = xm > m_run + TC_RESCALE_LOG2;
+                    if (__any_sync(0xffffffffu, need)) {
+                        const float m_new = need ? xm : m_run;
+                        const float sc = (m_run == -INFINITY) ? 0.f : ex2(m_run - m_new);
+                        s_run *= sc;
+                        m_run = m_new;
+                        if (kWantAcc && v > 0) {
+                            mbar_wait(&bar->o_done[g], (v - 1) & 1);
+                            tc_fence_after();
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch) {
+                                uint32_t t[32];
+                                tmem_ld32(o_addr + 32 * ch, t);
+                                tc_wait_ld();
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) t[j] = __float_as_uint(__uint_as_float(t[j]) * sc);
+                                tmem_st32(o_addr + 32 * ch, t);
+                            }
+                            tc_wait_st();
+                        }
+                    }
+                }
+                if (v == 0) { if (g == 0) named_barrier_arrive(2, 256); }
+                const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+#pragma unroll
+                for (int j = 0; j < TC_SUB; j += 4) {
+                    cf0 += (sv[j] > pos_dot) ? 1.f : 0.f;
+                    cf1 += (sv[j + 1] > pos_dot) ? 1.f : 0.f;
+                    cf2 += (sv[j + 2] > pos_dot) ? 1.f : 0.f;
+                    cf3 += (sv[j + 3] > pos_dot) ? 1.f : 0.f;
+                    const float p0 = ex2(fmaf(sv[j], c2, neg_m)), p1 = ex2(fmaf(sv[j + 1], c2, neg_m));
+                    const float p2 = ex2(fmaf(sv[j + 2], c2, neg_m)), p3 = ex2(fmaf(sv[j + 3], c2, neg_m));
+                    rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                    pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+                }
+            }
+#else
             bool count_step = true;
             if (!kFixedMax) {
                 // row max with four independent chains
@@ -435,6 +546,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     pk[(j >> 1) + 1] = pack_bf16(p2, p3);
                 }
             }
+#endif
             cnt += (int)((cf0 + cf1) + (cf2 + cf3));
             s_run += (rs0 + rs1) + (rs2 + rs3);
             if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 20);
