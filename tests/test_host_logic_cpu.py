@@ -161,3 +161,25 @@ def test_peer_exchange_and_graphed_steps_need_cuda():
     m = gca_b200.RGBMoCo(32, K=64)
     with pytest.raises(RuntimeError):
         GraphedMoCoStep(m, 8)
+
+
+def test_shuffle_plan_properties_randomised():
+    """Random worlds / batch sizes / permutations: counts are consistent across ranks, every row is sent exactly once,
+    and `place` is a permutation (hypothesis-style sweep with a fixed seed so the suite stays deterministic)."""
+    from gca_b200.dist import shuffle_plan
+    rng = np.random.default_rng(123)
+    for _ in range(60):
+        world, bsz = int(rng.integers(1, 9)), int(rng.integers(1, 33))
+        ids = torch.from_numpy(rng.permutation(world * bsz))
+        plans = [shuffle_plan(ids, bsz, world, r) for r in range(world)]
+        sent = []
+        for r, (rows, sc, rc, place) in enumerate(plans):
+            assert len(sc) == world and len(rc) == world and sum(sc) == sum(rc) == bsz
+            assert sorted(rows.tolist()) == list(range(bsz))                    # every local row leaves exactly once
+            assert sorted(place.tolist()) == list(range(bsz))
+            for dst in range(world):
+                assert sc[dst] == plans[dst][2][r]
+            sent.append(rows)
+        # reverse ids undo the shuffle: argsort(ids)[ids[g]] == g
+        rev = torch.argsort(ids)
+        assert torch.equal(ids[rev], torch.arange(world * bsz))
