@@ -42,6 +42,9 @@ extern "C" {
 #define GCA_ALGO_FFMA    1   /* CUDA-core fp32 FMA, exact fp32 arithmetic (parity mode), any d % 32 == 0, d <= 1024 */
 #define GCA_ALGO_TCGEN05 2   /* TMA -> smem -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM); bf16 queue, d == 128 */
 
+/* ranks are exact below this value when the caller asks for top-k hit counts only (rank_gt == NULL) */
+#define GCA_TOPK_RANK_CAP 8
+
 /* graph head flags (0 = the reference's arithmetic) */
 #define GCA_GRAPH_REFERENCE 0u
 
@@ -79,7 +82,10 @@ int gca_enqueue_devptr(void* queue, int dtype_queue, long long K_global, long lo
  *   queue       : [K, d] (dtype_queue) -- read in place; the caller orders it before this step's enqueue
  *   outputs     : loss_mean[1]   = mean_b (lse_b - pos_b)                   (criterion.py:44)
  *                 loss_rows[B], lse[B] (log-sum-exp over the K+1 logits), pos_logit[B] = q_b.k_b / T
- *                 rank_gt[B]     = number of negatives STRICTLY greater than the positive (top-k hit <=> < k)
+ *                 rank_gt[B]     = number of negatives STRICTLY greater than the positive (top-k hit <=> < k).  May be
+ *                                  NULL when only top_hits is wanted: the tcgen05 kernel then stops counting in a warp
+ *                                  once all of its rows are past GCA_TOPK_RANK_CAP (exact below it, which is all that
+ *                                  top-1 / top-5 need)
  *                 top_hits[2]    = #rows with rank_gt < 1, #rows with rank_gt < 5 (the counts behind
  *                                  accuracy(topk=(1,5)), train_video_contrast_dis.py:428); may be NULL
  *                 dq_unit[B, d]  = d loss_mean / d q (may be NULL: forward only)

@@ -31,6 +31,13 @@ def bf16r(t):
     return t.to(torch.bfloat16).float()
 
 
+def tcq(q, T):
+    """The queries as the tcgen05 kernels see them: log2(e)/T is folded into the bf16 query block, so it is q * log2(e)/T
+    (an fp32 product) that is rounded to bf16 -- expressed back in q units (float64)."""
+    c2 = torch.tensor(1.0 / T, dtype=torch.float32) * torch.tensor(1.4426950408889634, dtype=torch.float32)
+    return (q.float() * c2).to(torch.bfloat16).double() / c2.double()
+
+
 def rel_max(a, b):
     """max |a - b| / max |b|  (norm-wise relative error)."""
     a, b = a.double().cpu(), b.double().cpu()
@@ -173,7 +180,7 @@ def test_infonce_tcgen05_vs_bf16_input_oracle(GF, B, K):
     mem = unit_rows(K, 128, gen).to(torch.bfloat16)
     q, k = unit_rows(B, 128, gen), unit_rows(B, 128, gen)
     T = 0.07
-    rq = bf16r(q)
+    rq = tcq(q, T)
     o = oracle.infonce_step(rq.double(), k.double(), mem.double().clone(), 0, T)
     # the positive logit is taken from the unrounded q (fp32), the negatives from the rounded one
     pos = (q.double() * k.double()).sum(1) / T
@@ -205,7 +212,7 @@ def test_infonce_tcgen05_rank_count_skipped_when_positive_dominates(GF):
     k = unit_rows(B, 128, gen)
     k[:40] = q[:40]                                                        # cos = 1: nothing in the queue can beat it
     k[128:160] = q[128:160]                                                # one whole warp (32 rows) dominant
-    rq = bf16r(q)
+    rq = tcq(q, T)
     pos = (q.double() * k.double()).sum(1) / T
     neg = (rq.double() @ mem.double().t()) / T
     rank_ref = (neg > pos[:, None]).sum(1)
@@ -245,7 +252,7 @@ def test_infonce_tcgen05_unnormalised_inputs_leave_the_packed_loss_word(GF):
     q_big, k_big = torch.randn(64, 128, generator=gen) * 0.5, torch.randn(64, 128, generator=gen) * 0.5
     q_u, k_u = unit_rows(64, 128, gen), unit_rows(64, 128, gen)
     for q, k, mem in ((q_u, k_u, mem_unit), (q_big, k_big, mem_big), (q_u, -k_u * 1.5, mem_unit), (q_u, k_u, mem_unit)):
-        rq = bf16r(q)
+        rq = tcq(q, T)
         pos = (q.double() * k.double()).sum(1) / T
         neg = (rq.double() @ mem.double().t()) / T
         lse = torch.logsumexp(torch.cat([pos[:, None], neg], 1), 1)
@@ -273,7 +280,7 @@ def test_infonce_tcgen05_materialised_logits(GF):
     mem = unit_rows(K, 128, gen).to(torch.bfloat16)
     q, k = unit_rows(B, 128, gen), unit_rows(B, 128, gen)
     r = GF.infonce_forward(cu(q), cu(k), cu(mem), 0.07, algo="tcgen05", want_grad=False, materialize=True)
-    neg = (bf16r(q).double() @ mem.double().t()) / 0.07
+    neg = (tcq(q, 0.07) @ mem.double().t()) / 0.07
     assert rel_max(r["logits"][:, 1:], neg) <= 1e-5
     assert rel_max(r["logits"][:, 0], (q.double() * k.double()).sum(1) / 0.07) <= 1e-5
 
@@ -287,7 +294,7 @@ def test_infonce_tcgen05_unnormalised_inputs_trigger_rescale(GF):
     mem = mem.to(torch.bfloat16)
     q, k = torch.randn(B, 128, generator=gen), torch.randn(B, 128, generator=gen)
     T = 1.0
-    rq = bf16r(q)
+    rq = tcq(q, T)
     pos = (q.double() * k.double()).sum(1) / T
     neg = (rq.double() @ mem.double().t()) / T
     lse = torch.logsumexp(torch.cat([pos[:, None], neg], 1), 1)
@@ -625,7 +632,7 @@ def test_graphed_step_matches_oracle_over_a_lap(lib, queue_dtype, B, N, K):
     for it in range(K // N + 3):
         q, k, all_k = unit_rows(B, 128, gen), unit_rows(B, 128, gen), unit_rows(N, 128, gen)
         loss = step.step(cu(q), cu(k), cu(all_k))
-        rq = bf16r(q) if queue_dtype == "bf16" else q
+        rq = tcq(q, moco.T) if queue_dtype == "bf16" else q
         o = oracle.infonce_step(rq.double(), k.double(), ref_mem.double(), 0, 0.07)
         idx = oracle.enqueue(ref_mem, all_k, idx)
         tol = LOSS_RTOL_BF16 if queue_dtype == "bf16" else LOSS_RTOL_FP32

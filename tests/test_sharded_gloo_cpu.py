@@ -96,6 +96,24 @@ def _worker(rank, world, port, out_dir):
     k = torch.from_numpy(g["k0"])[rank * B_loc:(rank + 1) * B_loc]
     with pytest.raises(ValueError):
         moco(q, k, all_k=keys[:3])                                  # gathered keys must cover every rank's rows
+    # the trainer's all_k is in ShuffleBN (permuted) row order (train...:222, 231): it feeds the enqueue only -- the positives
+    # are the local, un-shuffled k of every rank
+    moco.index = ref_idx = 16
+    ref_mem = moco.gather_full_queue().clone()
+    q_all, k_all = torch.from_numpy(g["q1"]), torch.from_numpy(g["k1"])
+    all_k = k_all[torch.randperm(8, generator=torch.Generator().manual_seed(3))]
+    assert not torch.equal(all_k, k_all)
+    q = q_all[rank * B_loc:(rank + 1) * B_loc].clone().requires_grad_(True)
+    k = k_all[rank * B_loc:(rank + 1) * B_loc]
+    out, labels = moco(q, k, all_k=all_k)
+    loss = crit(out)
+    loss.backward()
+    o = oracle.infonce_step(q.detach(), k, ref_mem.clone(), 0, T)
+    assert abs(float(loss) - float(o["loss"])) <= 1e-5 * abs(float(o["loss"])), (float(loss), float(o["loss"]))
+    assert torch.allclose(q.grad, o["dq"], rtol=1e-4, atol=1e-6), (rank, float((q.grad - o["dq"]).abs().max()), float(o["dq"].abs().max()))
+    assert torch.equal(out.rank.long(), o["rank"])
+    ref_idx = oracle.enqueue(ref_mem, all_k, ref_idx)               # the rows every replica of the reference enqueues
+    assert moco.index == ref_idx and torch.equal(moco.gather_full_queue(), ref_mem)
     # checkpoints: the collective full_state_dict() is the upstream format; loading a full queue keeps the owned slots
     moco.index = 77
     sd = moco.full_state_dict(include_pointer=True)
@@ -108,10 +126,19 @@ def _worker(rank, world, port, out_dir):
     fresh2 = ShardedRGBMoCo(d, K=K, T=T, compute=OracleCompute())
     fresh2.load_state_dict(upstream)
     assert torch.equal(fresh2.memory, sd["memory"][rank * Ks:(rank + 1) * Ks]) and fresh2.index == 0
-    local = moco.state_dict()                                          # non-collective: this rank's shard
-    assert list(local.keys()) == ["memory"] and torch.equal(local["memory"], moco.memory.float())
-    fresh2.load_state_dict(local)
+    local = moco.state_dict()                                          # non-collective: this rank's shard + its slot range
+    assert list(local.keys()) == ["memory", "shard_begin", "shard_world"] and torch.equal(local["memory"], moco.memory.float())
+    assert int(local["shard_begin"]) == rank * Ks and int(local["shard_world"]) == world
+    fresh2.load_state_dict(dict(local))
     assert torch.equal(fresh2.memory, moco.memory)
+    # what an unmodified trainer would do: rank 0 saves its state_dict(), every rank resumes from it -> loud failure on rank != 0
+    everyone = [None] * world
+    dist.all_gather_object(everyone, {k_: v.clone() for k_, v in local.items()})
+    if rank != 0:
+        with pytest.raises((ValueError, RuntimeError)):
+            fresh2.load_state_dict(dict(everyone[0]))
+        with pytest.raises((ValueError, RuntimeError)):
+            fresh2.load_state_dict({"memory": everyone[0]["memory"]})   # a bare shard names no slots
     with pytest.raises((ValueError, RuntimeError)):
         fresh2.load_state_dict({"memory": torch.zeros(K + 8, d)})
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")

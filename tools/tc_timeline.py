@@ -55,7 +55,7 @@ for cold in (True, False):
         rel = (t[:, sl] - t[:, 0]) / 1e3
         print("   %-32s mean %6.2f us   min %6.2f   max %6.2f   (since own entry)" % (names[sl], rel.mean(), rel.min(), rel.max()))
     print("   entry skew across CTAs: %.2f us" % ((t[:, 0].max() - t0) / 1e3))
-    cn = {17: "softmax tile2: wait S", 18: "  tcgen05.ld 128 cols", 19: "  max + count pass", 20: "  exp + sum pass", 21: "  pack + tcgen05.st + arrive",
+    cn = {17: "softmax tile2: wait S", 18: "  tcgen05.ld", 19: "  exp + sum sweep", 20: "  rank count", 21: "  tcgen05.st + arrive",
           22: "softmax tile3 end (full period)"}
     prev = 16
     for sl in sorted(cn):

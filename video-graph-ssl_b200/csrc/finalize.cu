@@ -3,6 +3,8 @@
 // every sum has a fixed association order.  Math: SURVEY.md Appendix A.1-A.4.
 #include "gca_common.cuh"
 #include "infonce_params.cuh"
+#include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace gca {
 
@@ -12,6 +14,7 @@ constexpr int FIN_GROUPS = FIN_THREADS / FIN_COLS;
 constexpr int FIN_MAX_SPLITS = 1024;
 constexpr int FIN_STAT = 5;                   // split statistics a lane of warp 0 keeps in registers (<= 160 splits)
 constexpr int FIN_CHUNK = 40;                 // gradient partials a thread keeps in flight at once
+constexpr int FIN_VCH = 10;                   // vector path: 128-bit partial loads a thread keeps in flight (8 warps x 10 = 80 splits)
 
 // last-block ticket: returns true in exactly one block, after every other block's global writes are visible
 __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigned int nblocks, int* flag_smem)
@@ -89,11 +92,15 @@ __device__ __forceinline__ void enqueue_rows(const FinalizeParams& F, int blk, i
     }
 }
 
-template <int kMode>
+// kVec (d == 128, <= 8 * FIN_VCH splits: the tcgen05 family at its usual sizes): every warp reads whole 512-byte partial rows
+// with one 128-bit load per lane (warp w takes splits w, w + 8, ...), a quarter of the load instructions and L1 requests of
+// the column-per-thread path; the eight per-warp sums of a column are then added in warp order (fixed: deterministic).
+template <int kMode, bool kVec>
 __global__ void __launch_bounds__(FIN_THREADS)
 infonce_finalize_kernel(const FinalizeParams F)
 {
-    __shared__ float w_s[FIN_MAX_SPLITS];
+    __shared__ float4 colsum4[kVec ? (FIN_THREADS / 32) * 32 : 1];
+    __shared__ float w_s[kVec ? 8 * FIN_VCH : FIN_MAX_SPLITS];
     __shared__ float red[FIN_THREADS / 32];
     __shared__ float colsum[FIN_GROUPS][FIN_COLS];
     __shared__ float row_stat[2];                              // lse, pos of this row
@@ -139,8 +146,18 @@ infonce_finalize_kernel(const FinalizeParams F)
             st_c[i] = (sp < ns) ? __ldcg(F.part_cnt + o) : 0;
         }
     }
-    float v[FIN_CHUNK];
-    if (want_acc && col < F.d) {
+    float v[kVec ? 1 : FIN_CHUNK];
+    float4 v4[kVec ? FIN_VCH : 1];
+    if constexpr (kVec) {
+        if (want_acc) {
+            const float4* src4 = reinterpret_cast<const float4*>(F.part_acc + (size_t)b * FIN_COLS) + lane;
+#pragma unroll
+            for (int i = 0; i < FIN_VCH; ++i) {
+                const int sp = warp + i * (FIN_THREADS / 32);
+                v4[i] = (sp < ns) ? __ldcg(src4 + (size_t)sp * (stride / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    } else if (want_acc && col < F.d) {
         const float* src = F.part_acc + (size_t)b * F.d + col;
 #pragma unroll
         for (int i = 0; i < FIN_CHUNK; ++i) {
@@ -194,7 +211,7 @@ infonce_finalize_kernel(const FinalizeParams F)
                 if (lane == 0) {
                     F.lse[b] = lse;
                     F.loss_rows[b] = lse - pos;
-                    F.rank_gt[b] = cnt;
+                    if (F.rank_gt) F.rank_gt[b] = cnt;
                     row_rank = cnt;
                 }
                 const float corr = __expf(m - lse);            // = 1 / S
@@ -232,6 +249,27 @@ infonce_finalize_kernel(const FinalizeParams F)
                           : (kMode == FIN_BWD)  ? F.inv_T * F.grad_scale : 1.f;
         for (int c0 = 0; c0 < F.d; c0 += FIN_COLS) {
             const int c = c0 + col;
+            float t = 0.f;
+            if constexpr (kVec) {
+                float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < FIN_VCH; ++i) {
+                    const int sp = warp + i * (FIN_THREADS / 32);
+                    if (sp < ns) {
+                        const float w = (kMode == FIN_BWD) ? 1.f : w_s[sp];
+                        a4.x = fmaf(w, v4[i].x, a4.x); a4.y = fmaf(w, v4[i].y, a4.y);
+                        a4.z = fmaf(w, v4[i].z, a4.z); a4.w = fmaf(w, v4[i].w, a4.w);
+                    }
+                }
+                colsum4[warp * 32 + lane] = a4;
+                __syncthreads();
+                if (grp == 0) {
+                    const float* cs = reinterpret_cast<const float*>(colsum4);
+                    t = cs[col];
+#pragma unroll
+                    for (int w = 1; w < FIN_THREADS / 32; ++w) t += cs[w * FIN_COLS + col];
+                }
+            } else {
             float a = 0.f;
             if (c < F.d) {
                 const float* src = F.part_acc + (size_t)b * F.d + c;
@@ -252,11 +290,13 @@ infonce_finalize_kernel(const FinalizeParams F)
             }
             colsum[grp][col] = a;
             __syncthreads();
-            float t = 0.f;
             if (grp == 0 && c < F.d) {
                 t = colsum[0][col];
 #pragma unroll
                 for (int g = 1; g < FIN_GROUPS; ++g) t += colsum[g][col];
+            }
+            }
+            if (grp == 0 && c < F.d) {
                 if (kMode != FIN_SHARD) t = scale * fmaf(p0m1, F.k[(size_t)b * F.d + c], t);
             }
             if (kMode == FIN_FULL && F.zq != nullptr) {
@@ -293,7 +333,7 @@ infonce_finalize_kernel(const FinalizeParams F)
         const float lrow = row_stat[0] - row_stat[1];                      // lse - pos of this row
         unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(F.counter + 2);
         atomicAdd(acc64, (unsigned long long)__double2ll_rn((double)lrow * 68719476736.0));   // exact: ulp(lrow) >= 2^-36
-        const int r = F.rank_gt[b];
+        const int r = row_rank;
         if (r < 1) atomicAdd(F.counter + 4, 1u);
         if (r < 5) atomicAdd(F.counter + 5, 1u);
         __threadfence();
@@ -341,14 +381,22 @@ int infonce_finalize_launch(const FinalizeParams& F_, int mode, cudaStream_t st)
         if (enq_blocks > 64) enq_blocks = 64;
     }
     cudaLaunchConfig_t cfg{};
+    static int vec_on = -1;                                   // GCA_FIN_NOVEC=1: column-per-thread loads everywhere (A/B timing)
+    if (vec_on < 0) { const char* e = getenv("GCA_FIN_NOVEC"); vec_on = (e && e[0] == '1') ? 0 : 1; }
+    const bool vec = vec_on && F.d == FIN_COLS && F.nsplit <= 8 * FIN_VCH && F.part_acc != nullptr &&
+                     ((mode == FIN_SHARD) ? F.out_acc != nullptr : F.dq != nullptr);
     cfg.gridDim = dim3(F.B + enq_blocks); cfg.blockDim = dim3(FIN_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;    // PDL: be resident when the stream kernel drains
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    if (mode == FIN_FULL)       GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_finalize_kernel<FIN_FULL>, F));
-    else if (mode == FIN_SHARD) GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_finalize_kernel<FIN_SHARD>, F));
-    else                        GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_finalize_kernel<FIN_BWD>, F));
+#define GCA_FIN_LAUNCH(MODE) do { \
+        if (vec) GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_finalize_kernel<MODE, true>, F)); \
+        else     GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_finalize_kernel<MODE, false>, F)); } while (0)
+    if (mode == FIN_FULL)       GCA_FIN_LAUNCH(FIN_FULL);
+    else if (mode == FIN_SHARD) GCA_FIN_LAUNCH(FIN_SHARD);
+    else                        GCA_FIN_LAUNCH(FIN_BWD);
+#undef GCA_FIN_LAUNCH
     GCA_LAUNCH_CHECK("infonce_finalize_kernel");
     count_launch(1);
     return GCA_OK;

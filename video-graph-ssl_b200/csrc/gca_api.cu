@@ -104,7 +104,7 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
                       float inv_T, int algo, const float* lse_fixed, bool want_acc, float* pos_out, float* logits_out,
                       void* workspace, size_t workspace_bytes, InfoNceWs* ws_out, cudaStream_t st, bool skip_prep = false,
                       FinalizeParams* fuse = nullptr, const PeerXchg* px = nullptr, float* proj_k_hat = nullptr,
-                      bool proj = false)
+                      bool proj = false, int rank_cap = 0)
 {
     const int a = pick_algo(algo, dtype_queue, d);
     if (sm_count_cached() < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
@@ -119,6 +119,7 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
     P.nsplit = nsplit; P.Bpad = ws.Bpad; P.pos_out = pos_out ? pos_out : ws.pos_tmp; P.logits_out = logits_out; P.ld_logits = K + 1;
     P.q_bf16_ws = ws.q_bf16; P.pos_ws = ws.pos_ws; P.T_ = 1.f / inv_T; P.skip_prep = skip_prep ? 1 : 0;
     P.k_hat = ws.k_hat; P.inv_nq = ws.inv_nq;           // tcgen05 family: the prep kernel stages k (ffma family: unused)
+    P.rank_cap = rank_cap; P.q_scale = 1.f;
     if (proj) {
         if (a != GCA_ALGO_TCGEN05)
             return set_err(GCA_ERR_UNSUPPORTED, "projection-tail fusion exists for the tcgen05 family only (bf16 queue, d == 128)");
@@ -171,7 +172,8 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
     using namespace gca;
     int rc = check_infonce_args(fn, q, k, queue, dtype_queue, B, K, d, inv_T, algo);
     if (rc != GCA_OK) return rc;
-    GCA_CHECK_ARG(loss_rows && lse && pos_logit && rank_gt, "%s: loss_rows, lse, pos_logit, rank_gt are required", fn);
+    GCA_CHECK_ARG(loss_rows && lse && pos_logit, "%s: loss_rows, lse, pos_logit are required", fn);
+    GCA_CHECK_ARG(rank_gt || top_hits, "%s: rank_gt == NULL (top-k hits only) needs top_hits", fn);
     if (enq_keys || (proj && enq_N > 0)) {
         GCA_CHECK_ARG(enq_N >= 0 && enq_N <= K, "%s: N=%d rows do not fit a ring of %lld slots", fn, enq_N, K);
         GCA_CHECK_ARG(enq_state || (enq_index >= 0 && enq_index < K), "%s: pointer %lld outside [0, %lld)", fn, enq_index, K);
@@ -195,7 +197,7 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
                           workspace_bytes, &ws, st, false, &F);
     }
     rc = run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, dq_unit != nullptr, pos_logit, logits_out,
-                    workspace, workspace_bytes, &ws, st, false, nullptr, px, k_hat_out, proj);
+                    workspace, workspace_bytes, &ws, st, false, nullptr, px, k_hat_out, proj, rank_gt ? 0 : GCA_TOPK_RANK_CAP);
     if (rc != GCA_OK) return rc;
     if (proj) {                                          // the finalize kernel works on the normalised keys and maps dq to dzq
         const float* kh = k_hat_out ? k_hat_out : ws.k_hat;

@@ -34,6 +34,8 @@ struct InfoNceStreamParams {
     float* k_hat;            // [B.., d] out: the positive keys staged for the finalize kernel (normalised if `normalize`)
     float* inv_nq;           // [Bpad] out: 1 / max(||q||, 1e-12) (normalize only)
     int    normalize;
+    int    rank_cap;         // tcgen05 single-pass kernel: > 0 = the caller only needs ranks below this value (top-k hits)
+    float  q_scale;          // factor folded into the bf16 queries by the prep kernel (1, or log2(e)/T for infonce_tcx)
 };
 
 // ffma family (infonce_ffma.cu)

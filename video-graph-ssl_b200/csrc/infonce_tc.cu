@@ -37,6 +37,9 @@ constexpr size_t TC_QTILE_BYTES = (size_t)TC_BM * TC_D * 2;   // bf16 q block, s
 constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + TC_QTILE_BYTES + 512;
 static_assert((size_t)TC_BM * TC_OST_STRIDE * 4 <= (size_t)TC_STAGES * TC_STAGE_BYTES, "O staging must fit in the tile ring");
 
+bool infonce_tcx_enabled();                                         // infonce_tcx.cu
+int infonce_tcx_launch(const InfoNceStreamParams& P, cudaStream_t st);
+
 struct TcDebug { unsigned long long* timebuf; };   // bring-up only: phase time stamps (tools/tc_timeline.py)
 
 __device__ __forceinline__ void tc_stamp(const TcDebug& dbg, int slot)
@@ -170,7 +173,7 @@ __device__ void fused_finalize(const FinalizeParams& F, float* scratch, const Tc
             if (lane == 0) {
                 F.lse[my_row] = lse;
                 F.loss_rows[my_row] = lse - pos;
-                F.rank_gt[my_row] = cnt;
+                if (F.rank_gt) F.rank_gt[my_row] = cnt;
                 rstat[2 * w] = lse; rstat[2 * w + 1] = pos;
                 // exact, order-independent accumulators (see infonce_finalize_kernel)
                 unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(F.counter + 2);
@@ -314,13 +317,16 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const bool valid = row < P.B;
         const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
         const uint32_t o_addr = lane_addr + tm_o(g);
-        const float c2 = P.inv_T * 1.4426950408889634f;               // logits -> log2 domain
+        // logits -> log2 domain.  The prep kernel folded P.q_scale (= log2(e)/T for this family) into the bf16 queries, so the
+        // S tile is already in log2 units and the remaining factor is exactly 1
+        const float c2 = 1.f;
+        const float s_to_nat = 0.6931471805599453f;                    // S tile -> natural-log logits (materialised logits)
 
         // The bf16 q block and the positive logits were prepared once per step by infonce_prep_kernel (below): 148 CTAs
         // re-reading and re-converting the same fp32 rows would cost more L2 traffic than the queue itself.
         pdl_wait();                                                   // prep kernel results (pos_ws) are visible from here
         const float pos_nat0 = P.pos_ws[row];                         // natural-log units (q.k / T); 0 for padding rows
-        const float pos_dot = pos_nat0 * P.T_;                        // the raw dot product the S tile is compared with
+        const float pos_dot = pos_nat0 * 1.4426950408889634f;         // the positive in the units of the S tile
         if (split == 0 && blockIdx.y == 0 && threadIdx.x == 0) { for (int w = 0; w < 6; ++w) P.counter[w] = 0u; }      // re-arm the finalize control block
         if (split == 0 && g == 0 && valid && P.logits_out) P.logits_out[(size_t)row * P.ld_logits] = pos_nat0;
         if (threadIdx.x == 0) tc_stamp(dbg, 3);
@@ -361,7 +367,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             if (P.logits_out && valid) {                                   // parity / debug path only
                 float* dst = P.logits_out + (size_t)row * P.ld_logits + 1 + key0;
 #pragma unroll
-                for (int j = 0; j < TC_SUB; ++j) if (j < nvalid) dst[j] = sv[j] * P.inv_T;
+                for (int j = 0; j < TC_SUB; ++j) if (j < nvalid) dst[j] = sv[j] * s_to_nat;
             }
             if (nvalid < TC_SUB) {
 #pragma unroll
@@ -738,9 +744,21 @@ __global__ void __launch_bounds__(256)
 infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, int B, int Bpad, float inv_T,
                     __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ pos_ws, float* __restrict__ pos_out,
                     unsigned long long* timebuf, const PeerXchg X, int nprep, unsigned int* range_flag,
-                    float* __restrict__ k_hat, float* __restrict__ inv_nq, int normalize)
+                    float* __restrict__ k_hat, float* __restrict__ inv_nq, int normalize,
+                    const char* __restrict__ pf_base, unsigned long long pf_bytes, float q_scale)
 {
     ptx::pdl_launch_dependents();            // the streaming kernel may start its setup and its first queue-tile loads
+    // warm the L2 with the head of the queue (the first tile waves of the stream kernel): this launch starts ~1 us before
+    // the stream kernel's TMA producer can, and a cold queue tile costs a full HBM round trip at the head of every CTA's
+    // pipeline.  32 KB bulk prefetches, dealt round-robin over the CTAs of this launch (a few per SM).
+    if (pf_base != nullptr && (int)blockIdx.x < nprep) {
+        const unsigned long long off = ((unsigned long long)blockIdx.x + (unsigned long long)nprep * threadIdx.x) * 32768ull;
+        if (off < pf_bytes) {
+            const unsigned long long rest = pf_bytes - off;
+            const unsigned int nb = rest < 32768ull ? (unsigned int)rest : 32768u;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(pf_base + off), "r"(nb) : "memory");
+        }
+    }
     if ((int)blockIdx.x >= nprep) {          // key exchange riding in this launch: push slice c of k to rank p (exchange.cu)
         const int e = blockIdx.x - nprep;
         const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(X.xstate);
@@ -774,9 +792,9 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
     if (row < B) reinterpret_cast<float4*>(k_hat + (size_t)row * TC_D)[lane] = b;         // (may be a caller buffer of B rows)
     float dsum = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
     dsum = warp_sum(dsum) * inv_T;
-    uint2 pk;
-    pk.x = ptx::pack_bf16(a.x, a.y);
-    pk.y = ptx::pack_bf16(a.z, a.w);
+    uint2 pk;                                                        // (q_scale: see infonce_tcx.cu -- log2(e)/T or 1)
+    pk.x = ptx::pack_bf16(a.x * q_scale, a.y * q_scale);
+    pk.y = ptx::pack_bf16(a.z * q_scale, a.w * q_scale);
     reinterpret_cast<uint2*>(q_bf16 + (size_t)row * TC_D)[lane] = pk;
     if (lane == 0) {
         pos_ws[row] = dsum;
@@ -806,7 +824,7 @@ static EncodeTiledFn encode_fn()
 struct TmapCache { const void* ptr; long long K; CUtensorMap map; bool ok; };
 
 // row-major bf16 [rows, 128] tensor, box = 128 rows x 64 features, 128-byte swizzle (queue tiles and the q block alike)
-static int get_queue_tmap(const void* queue, long long K, CUtensorMap* out)
+int get_queue_tmap(const void* queue, long long K, CUtensorMap* out)
 {
     static thread_local TmapCache cache[8] = {};
     static thread_local int next = 0;
@@ -854,8 +872,10 @@ unsigned long long* debug_timebuf()
 
 static TcDebug tc_debug_knobs() { return TcDebug{debug_timebuf()}; }
 
-int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t st, const FinalizeParams* fuse)
+int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_t st, const FinalizeParams* fuse)
 {
+    InfoNceStreamParams P = P_;
+    P.q_scale = P.inv_T * 1.4426950408889634f;        // every kernel of this family works on log2-domain S tiles
     if (P.d != TC_D) return set_err(GCA_ERR_UNSUPPORTED, "tcgen05 InfoNCE kernel needs d == %d (got %d)", TC_D, P.d);
     if (P.K >= (1ll << 31) - TC_BN) return set_err(GCA_ERR_UNSUPPORTED, "tcgen05 InfoNCE kernel: K too large");
     if ((reinterpret_cast<uintptr_t>(P.queue) & 15) != 0) return set_err(GCA_ERR_BAD_ARG, "queue must be 16-byte aligned");
@@ -867,17 +887,29 @@ int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t
     if (P.skip_prep && P.xchg.mailboxes) return set_err(GCA_ERR_BAD_ARG, "the peer key exchange rides in the prep kernel");
     if (P.normalize && (P.xchg.mailboxes || P.skip_prep))
         return set_err(GCA_ERR_UNSUPPORTED, "projection-tail fusion cannot be combined with the peer exchange or skip_prep");
+    // loss + gradient in one sweep (the product path): second-generation stream kernel (infonce_tcx.cu)
+    const bool use_tcx = P.part_acc != nullptr && !fixed_max && !fuse && P.logits_out == nullptr && infonce_tcx_enabled();
     if (!P.skip_prep) {
         const int nprep = (P.Bpad + 7) / 8;
         const int npush = P.xchg.mailboxes ? P.xchg.W * XCHG_SLICES : 0;
+        // queue head to prefetch into L2 (at most 32 MB; GCA_NO_L2PF=1 turns it off for A/B timing)
+        static int pf_on = -1;
+        if (pf_on < 0) { const char* e = getenv("GCA_NO_L2PF"); pf_on = (e && e[0] == '1') ? 0 : 1; }
+        unsigned long long pf_bytes = (unsigned long long)P.K * TC_D * 2;
+        const unsigned long long pf_waves = 2ull * (unsigned long long)P.nsplit * TC_STAGE_BYTES;   // tiles 0 and 1 of every split
+        if (pf_bytes > pf_waves) pf_bytes = pf_waves;
+        if ((unsigned long long)nprep * 256ull * 32768ull < pf_bytes) pf_bytes = (unsigned long long)nprep * 256ull * 32768ull;
         infonce_prep_kernel<<<nprep + npush, 256, 0, st>>>(P.q, P.k, P.B, P.Bpad, P.inv_T, (__nv_bfloat16*)P.q_bf16_ws,
                                                            P.pos_ws, P.pos_out, debug_timebuf(), P.xchg, nprep, P.counter + 6,
-                                                           P.k_hat, P.inv_nq, P.normalize);
+                                                           P.k_hat, P.inv_nq, P.normalize,
+                                                           pf_on ? (const char*)P.queue : nullptr, pf_bytes,
+                                                           P.q_scale);
         GCA_LAUNCH_CHECK("infonce_prep_kernel");
         count_launch(1);
     }
     const TcDebug dbg = tc_debug_knobs();
     const bool want_acc = P.part_acc != nullptr;
+    if (use_tcx) return infonce_tcx_launch(P, st);
     dim3 grid(P.nsplit, P.Bpad / TC_BM);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = st;

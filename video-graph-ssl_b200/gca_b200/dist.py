@@ -92,15 +92,17 @@ def _reduce_scatter_rows(x, group):
 
 class _ShardedInfoNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k_all_or_k, shard, owner):
+    def forward(ctx, q, k, shard, owner):
+        """q, k: the LOCAL rows, k in the same (un-shuffled) order as q: row b of k is the positive of row b of q
+        (mem_moco.py:36-38).  Both are gathered here; a caller-supplied `all_k` is never used for the positives -- the one
+        `_shuffle_bn` returns is in SHUFFLED row order (train_video_contrast_dis.py:222, 231) and only feeds the enqueue."""
         group, T, comp = owner.group, owner.T, owner.compute
         W, r = dist.get_world_size(group), dist.get_rank(group)
         want = ctx.needs_input_grad[0]
         B_loc = q.shape[0]
         q32 = q.detach().float().contiguous()
         q_all = _all_gather_rows(q32, group)
-        k_all = k_all_or_k if k_all_or_k.shape[0] == q_all.shape[0] else _all_gather_rows(k_all_or_k.float(), group)
-        k_all = k_all.float().contiguous()
+        k_all = _all_gather_rows(k.detach().float().contiguous(), group)
         pos, stats, acc = comp.shard_fwd(q_all, k_all, shard, T, owner.algo, want)
         all_stats = _all_gather_rows(stats.unsqueeze(0), group)              # [W, 3, B_glob]
         lse, loss_rows, rank_gt = comp.shard_combine(all_stats, r, pos, acc)
@@ -150,10 +152,13 @@ class ShardedRGBMoCo(nn.Module):
         k = k.detach()
         if all_k is not None and all_k.shape[0] != self.world * q.shape[0]:
             raise ValueError("all_k must hold the keys of every rank (%d rows), got %d" % (self.world * q.shape[0], all_k.shape[0]))
-        src = all_k.detach() if all_k is not None else k
-        loss, loss_rows, lse, pos, rank_gt, k_all = _ShardedInfoNCE.apply(q, src, self.memory, self)
+        # positives: the local k, gathered in rank order (row b of k belongs to row b of q).  Enqueue: the caller's all_k in
+        # ITS row order when given (the trainer's is in ShuffleBN order, train...:222 -- every replica of the reference
+        # enqueues exactly those rows, mem_moco.py:81-82), else the rank-ordered gather.
+        loss, loss_rows, lse, pos, rank_gt, k_all = _ShardedInfoNCE.apply(q, k, self.memory, self)
+        rows = all_k.detach().float() if all_k is not None else k_all
         with torch.no_grad():
-            self.index = self.compute.enqueue(self.memory, k_all, self.index, self.K, self.k_begin)
+            self.index = self.compute.enqueue(self.memory, rows, self.index, self.K, self.k_begin)
         labels = torch.zeros(q.shape[0], dtype=torch.long, device=q.device)
         return FusedLogits(loss, loss_rows, lse, pos, rank_gt, q.shape[0], self.K), labels
 
@@ -163,8 +168,11 @@ class ShardedRGBMoCo(nn.Module):
 
     # ---- checkpoints -------------------------------------------------------------------------------------------
     # `state_dict()` stays local and non-collective (the trainer saves on rank 0 only, train...:270-285): it holds this
-    # rank's shard.  `full_state_dict()` is the upstream format -- one fp32 [K, d] `memory` -- and is COLLECTIVE: every rank
-    # calls it, any rank may write the result.  `load_state_dict` takes either; a full queue is cut down to the owned slots.
+    # rank's shard, labelled with the slots it covers ('shard_begin', 'shard_world') so that it can only be loaded back into
+    # the rank that owns them -- an unmodified trainer that saves rank 0's state_dict() and resumes on every rank gets an
+    # error instead of W copies of rank 0's shard.  `full_state_dict()` is the upstream format -- one fp32 [K, d] `memory` --
+    # and is COLLECTIVE: every rank calls it, any rank may write the result (INTEGRATION.md shows the trainer change).
+    # `load_state_dict` takes either; a full queue is cut down to the owned slots.
     def full_state_dict(self, include_pointer=False):
         """{'memory': fp32 [K, d]} exactly as `RGBMoCo.state_dict()` / the reference would save it.  With
         include_pointer=True the ring pointer travels as 'index' (the reference drops it on resume)."""
@@ -177,9 +185,14 @@ class ShardedRGBMoCo(nn.Module):
         super(ShardedRGBMoCo, self)._save_to_state_dict(destination, prefix, keep_vars)
         if self.memory.dtype == torch.bfloat16:
             destination[prefix + "memory"] = self.memory.float()
+        if self.world > 1:
+            destination[prefix + "shard_begin"] = torch.tensor(int(self.k_begin), dtype=torch.int64)
+            destination[prefix + "shard_world"] = torch.tensor(int(self.world), dtype=torch.int64)
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         key = prefix + "memory"
+        begin = state_dict.pop(prefix + "shard_begin", None)
+        sworld = state_dict.pop(prefix + "shard_world", None)
         if key in state_dict:
             mem = state_dict[key]
             Ks = self.memory.shape[0]
@@ -188,6 +201,15 @@ class ShardedRGBMoCo(nn.Module):
             elif mem.shape[0] != Ks:
                 raise ValueError("checkpoint queue has %d rows; expected the full %d or this rank's %d"
                                  % (mem.shape[0], self.K, Ks))
+            elif self.world > 1:
+                # a per-rank shard: only the rank that owns those slots may take it
+                if begin is None or sworld is None:
+                    raise ValueError("checkpoint holds a %d-row queue shard without its slot range; save the sharded queue "
+                                     "with full_state_dict() (collective) or state_dict() of this module" % Ks)
+                if int(begin) != self.k_begin or int(sworld) != self.world:
+                    raise ValueError("checkpoint shard covers slots from %d (world %d); this rank owns slots from %d (world "
+                                     "%d) -- a sharded queue must be saved with full_state_dict() (collective) or per rank"
+                                     % (int(begin), int(sworld), self.k_begin, self.world))
             state_dict[key] = mem.to(self.memory.dtype)
         if prefix + "index" in state_dict:
             self.index = int(state_dict.pop(prefix + "index")) % self.K

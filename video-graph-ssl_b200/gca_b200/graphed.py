@@ -21,7 +21,10 @@ from ._lib import ptr
 
 
 class GraphedMoCoStep(object):
-    def __init__(self, moco, batch, n_enqueue=None, algo=None, state=None):
+    def __init__(self, moco, batch, n_enqueue=None, algo=None, state=None, want_rank=True):
+        """want_rank=False: only the top-1 / top-5 hit counts are produced (what `accuracy(output, labels, topk=(1, 5))`
+        reports, train_video_contrast_dis.py:428), not the per-row rank of the positive: the kernel may then stop counting
+        once every row of a warp is past rank 8 (include/gca_b200.h, GCA_TOPK_RANK_CAP); .rank is None."""
         mem = moco.memory
         if not mem.is_cuda:
             raise RuntimeError("GraphedMoCoStep needs the queue on a CUDA device; there is no CPU path")
@@ -42,7 +45,7 @@ class GraphedMoCoStep(object):
         self.loss_rows = torch.empty(self.B, dtype=torch.float32, device=dev)
         self.lse = torch.empty_like(self.loss_rows)
         self.pos = torch.empty_like(self.loss_rows)
-        self.rank = torch.empty(self.B, dtype=torch.int32, device=dev)
+        self.rank = torch.empty(self.B, dtype=torch.int32, device=dev) if want_rank else None
         # ring pointer + ticket in device memory; several captured steps over the same queue share one state tensor
         self.state = state if state is not None else torch.tensor([moco.index, 0], dtype=torch.int64, device=dev)
         self.qd = GF.queue_dtype_code(mem)
@@ -158,7 +161,7 @@ class GraphedReplicaStep(GraphedMoCoStep):
     only needs the LOCAL keys for its positives; the gathered keys are first needed by the enqueue at the end of the step.
     Every rank must hold an identical queue and ring pointer (same seed or a broadcast, as upstream)."""
 
-    def __init__(self, moco, batch, group=None, algo=None, state=None, exchange=None, fuse_exchange=True):
+    def __init__(self, moco, batch, group=None, algo=None, state=None, exchange=None, fuse_exchange=True, want_rank=True):
         """`exchange`: None -> NCCL all-gather on a side stream.  A gca_b200.peer.PeerKeyExchange (shared by every
         captured step of this process; the steps then must replay in the same order on all ranks) -> the keys travel
         through peer memory: fused into the step's own launches (gca_moco_step_peer: pushed by the first launch,
@@ -167,7 +170,8 @@ class GraphedReplicaStep(GraphedMoCoStep):
         import torch.distributed as dist
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
-        super(GraphedReplicaStep, self).__init__(moco, batch, n_enqueue=batch * self.world, algo=algo, state=state)
+        super(GraphedReplicaStep, self).__init__(moco, batch, n_enqueue=batch * self.world, algo=algo, state=state,
+                                                 want_rank=want_rank)
         self.side = torch.cuda.Stream(moco.memory.device)
         self.keys_ready = torch.cuda.Event()
         self.exchange = exchange
