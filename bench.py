@@ -7,9 +7,12 @@ pointer update.  Arms:
   (default)          the B200 path: libgca_b200.so through gca_b200.GraphedMoCoStep (N=1) / ShardedRGBMoCo (N>1)
   --impl reference   the reference's CPU implementation of the same step (oracle port; the reference is pure Python
                      and does not exist on the GPU box), all host threads, rank 0 only
-Prints ONE JSON line (contract in the task statement): value = device-timed steps/s with inputs resident in HBM,
-e2e = same step from pinned HOST buffers with the H2D / D2H copies inside the timed region, roofline for the dominant
-kernel (infonce_tc_kernel) timed alone, cpu_baseline = the oracle port timed on this box's host cores.
+Prints ONE JSON line (contract in the task statement): value = device-timed steps/s with inputs resident in HBM -- EXACTLY
+`--steps` steps back to back between one pair of CUDA events, every step on its own replica of the queue so that the
+working set (318 MB) exceeds the L2 -- e2e = same step from pinned HOST buffers with the H2D / D2H traffic inside the
+timed region, roofline for the dominant kernel (infonce_tcx_kernel) timed alone, cpu_baseline = the oracle port timed on
+this box's host cores.  `ms_per_step_isolated` keeps round 1's figure next to it: one step between its own event pair
+after an explicit L2 flush (it additionally contains ~2.5 us of graph-launch latency that back-to-back steps overlap).
 """
 import argparse
 import ctypes
@@ -29,7 +32,9 @@ METRIC = "contrastive_head_fwd_bwd_steps_per_s"
 UNIT = "steps/s (1 step = fwd+bwd+top-k+enqueue of 256 query rows against the 65536 x 128 queue)"
 B, K, D, T = 256, 65536, 128, 0.07
 POOL = 8                                  # distinct input batches cycled through the timed steps
-L2_FLUSH_BYTES = 256 << 20                # > 126 MB L2
+QPOOL = 12                                # distinct queue replicas cycled through the timed steps: 12 x (16.8 MB queue + 9.7 MB
+                                          # split partials) = 318 MB > the 126 MB L2, so every step streams its queue from HBM
+L2_FLUSH_BYTES = 256 << 20                # > 126 MB L2 (isolated-step and e2e legs)
 
 
 def peaks():
@@ -170,6 +175,93 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------- secondary figures
+def _time_graph(fn, flush, iters=20, warm=3):
+    """fn() captured once in a CUDA graph, replayed with an L2 flush before every replay; mean device ms per replay."""
+    import torch
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    ts = []
+    for i in range(warm + iters):
+        flush.fill_(i & 1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            ts.append(a.elapsed_time(b))
+    return sum(ts) / len(ts)
+
+
+def secondary_measurements(dev, flush, pk):
+    """Driver-visible figures for the other SURVEY 8 configs, each a few replays (cold L2) of the C-ABI call: the fp32 parity
+    mode of the head, the head at K = 2^20 on one GPU (the N = 1 point of the K-sharded series), the temporal-graph core
+    forward + backward at BASELINE config 3 with its fraction of the measured HBM peak, SimSiam's D, retrieval (config 5)."""
+    import torch
+    import torch.nn.functional as F
+    from gca_b200 import functional as GF
+    out = {}
+    g = torch.Generator().manual_seed(5)
+    unit = lambda n: F.normalize(torch.randn(n, D, generator=g)).to(dev)
+    q, k = unit(B), unit(B)
+    try:
+        mem32 = unit(K)
+        ms = _time_graph(lambda: GF.infonce_forward(q, k, mem32, T, algo="ffma", want_grad=True), flush, iters=8, warm=2)
+        out["fp32_mode"] = {"what": "fused head, fp32 queue + fp32 FMA arithmetic (1e-5 parity mode), B=256 K=65536", "ms": ms,
+                            "steps_per_s": 1e3 / ms, "tflops_fp32": 4.0 * B * K * D / (ms * 1e-3) / 1e12}
+        del mem32
+    except Exception as e:                                   # a secondary figure must never take the headline down
+        out["fp32_mode"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    try:
+        K1 = 1 << 20
+        mem1 = F.normalize(torch.randn(K1, D, generator=g)).to(torch.bfloat16).to(dev)
+        ms = _time_graph(lambda: GF.infonce_forward(q, k, mem1, T, algo="tcgen05", want_grad=True), flush, iters=10, warm=2)
+        fl = 4.0 * B * K1 * D
+        out["head_k1m_1gpu"] = {"what": "fused head, bf16 queue 2^20 x 128 on ONE GPU, B=256 (N=1 point of the K-sharded series)",
+                                "ms": ms, "global_rows_per_s": B / ms * 1e3, "tflops": fl / (ms * 1e-3) / 1e12,
+                                "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / pk["bf16_tflops"]}
+        del mem1
+    except Exception as e:
+        out["head_k1m_1gpu"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    try:
+        Bv, C, Tt, HW, Cq, S = 128, 192, 8, 196, 96, 49      # S3D base.5 map [128,192,8,14,14], sub-sampled projections (7x7)
+        gq = torch.randn(Bv, Cq, Tt, S, device=dev) * 0.02
+        gk = torch.randn(Bv, Cq, Tt, S, device=dev) * 0.02
+        sup = torch.randn(Bv, C, Tt, HW, device=dev)
+        u = torch.rand(Bv, Tt, Tt, device=dev)
+        dy = torch.randn(Bv, C, Tt, HW, device=dev)
+        gq.requires_grad_(True); gk.requires_grad_(True); sup.requires_grad_(True)
+
+        def fb():
+            y = GF.graph_core(gq, gk, sup, u)[0]
+            torch.autograd.grad(y, (gq, gk, sup), dy)
+        ms = _time_graph(fb, flush, iters=10, warm=2)
+        per_dir = 4.0 * (2 * Tt * Cq * S + 2 * C * Tt * HW + 2 * Tt * Tt) * Bv          # SURVEY 8d, per direction
+        bwd = 4.0 * (2 * Tt * Cq * S * 2 + 3 * C * Tt * HW + 4 * Tt * Tt) * Bv          # reads gq,gk,sup,dy,T^2 terms; writes d_gq,d_gk,d_sup
+        out["graph_head_c3"] = {"what": "temporal-graph core fwd+bwd (gca_graph_fwd + gca_graph_bwd), 128 x [192,8,14,14]", "ms": ms,
+                                "videos_per_s": Bv / ms * 1e3, "alg_bytes": per_dir + bwd,
+                                "hbm_frac": (per_dir + bwd) / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
+    except Exception as e:
+        out["graph_head_c3"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    try:
+        rng = torch.Generator().manual_seed(0)
+        gal, qry = torch.randn(13320, 512, generator=rng).to(dev), torch.randn(3783, 512, generator=rng).to(dev)
+        ms = _time_graph(lambda: GF.cosine_topk(qry, gal, 50, normalize=True), flush, iters=8, warm=2)
+        out["retrieval_c5"] = {"what": "cosine top-50, 3783 x 13320 x 512 (gca_sim_topk)", "ms": ms,
+                               "tflops_bf16_equiv": 6 * 2.0 * 3783 * 13320 * 512 / (ms * 1e-3) / 1e12}
+    except Exception as e:
+        out["retrieval_c5"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- B200 arm, N = 1
 def run_single(args):
     import torch
@@ -182,43 +274,55 @@ def run_single(args):
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     torch.manual_seed(1)
-    moco = gca_b200.RGBMoCo(D, K=K, T=T, queue_dtype="bf16").to(dev)
     batches = synthetic_batches(2, POOL, B, B, device=dev)
-    state = torch.tensor([0, 0], dtype=torch.int64, device=dev)
+    # QPOOL replicas of the queue, one captured step each (the step's inputs cycle through POOL batches): consecutive timed
+    # steps touch disjoint 26.5 MB working sets, 318 MB in all, so no step finds its queue in the 126 MB L2
+    mocos = [gca_b200.RGBMoCo(D, K=K, T=T, queue_dtype="bf16").to(dev) for _ in range(QPOOL)]
+    moco = mocos[0]
     steps_g = []
-    for i in range(POOL):                                  # one captured step per pool entry, shared queue + ring pointer
-        s = GraphedMoCoStep(moco, B, B, state=state)
-        s.inputs.copy_(batches[i])
-        steps_g.append(s)
-    for s in steps_g:
-        s.capture()
+    for i in range(QPOOL):
+        # want_rank=False: the step reports what the trainer logs -- the top-1 / top-5 hit counts (train...:428) -- not 256 ranks
+        sg = GraphedMoCoStep(mocos[i], B, B, want_rank=False)
+        sg.inputs.copy_(batches[i % POOL])
+        steps_g.append(sg)
+    for sg in steps_g:
+        sg.capture()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
     def one(i):
-        steps_g[i % POOL].step()
+        steps_g[i % QPOOL].step()
 
     sampler = ClockSampler(0)
     for i in range(args.warmup):
-        flush.fill_(i & 1)
         one(i)
     sampler.wait_first_sample()
     torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_start()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 1)                                 # L2 flush between timed iterations (not inside the events)
-        ev[i][0].record()
+    ev0.record()
+    for i in range(args.steps):                            # EXACTLY K steps, back to back, between one event pair
         one(args.warmup + i)
-        ev[i][1].record()
+    ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     sampler.mark_end()
     clocks = sampler.stop()
-    dev_ms = sorted(a.elapsed_time(b) for a, b in ev)
-    ms_per_step = sum(dev_ms) / len(dev_ms)
+    ms_per_step = ev0.elapsed_time(ev1) / args.steps
     launches = steps_g[0].launches_per_step * args.steps
-    loss_last = float(steps_g[(args.warmup + args.steps - 1) % POOL].loss)
+    loss_last = float(steps_g[(args.warmup + args.steps - 1) % QPOOL].loss)
+    # round 1's figure for continuity: one step between its own event pair, L2 flushed before it
+    iso = []
+    for i in range(60):
+        flush.fill_(i & 1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        one(i)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 10:
+            iso.append(a.elapsed_time(b))
+    ms_isolated = sum(iso) / len(iso)
 
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H of loss/top-k/dq, synchronised every step
     # (each pool entry owns a pinned input batch and a pinned result buffer; the two copies are nodes of the step's graph, so
@@ -226,6 +330,7 @@ def run_single(args):
     host_in = synthetic_batches(3, POOL, B, B, pin=True)
     g0 = steps_g[0]
     host_outs = [torch.empty_like(g0.outputs, device="cpu").pin_memory() for _ in range(POOL)]
+    assert POOL <= QPOOL
     zc_in = os.environ.get("GCA_BENCH_ZC_IN", "1") == "1"  # first kernel reads q|k (and the enqueue CTAs all_k) from pinned host memory
     for i in range(POOL):
         steps_g[i].capture_host_io(host_in[i], host_outs[i], zero_copy_out=True, zero_copy_in=zc_in)
@@ -316,25 +421,30 @@ def run_single(args):
         del queues
     pk = peaks()
     flops = 4.0 * B * K * D                                 # single pass: S = q Q^T and O += P Q
-    alg_bytes = K * D * 2 + 2 * B * D * 4 + 74 * B * (D + 3) * 4   # queue once + q,k + split partials written
+    # ALGORITHMIC bytes of the single-pass formulation: queue once + q, k, dq + enqueued rows + per-row scalars
+    alg_bytes = K * D * 2 + 12 * B * D + B * D * (4 + 2) + 16 * B
     t_tensor = flops / (pk["bf16_tflops"] * 1e12)
     t_hbm = alg_bytes / (pk["hbm_gbs"] * 1e9)
     ach_tf = flops / (k_ms * 1e-3) / 1e12
     roof = {"bound": "tensor" if t_tensor >= t_hbm else "hbm", "achieved": ach_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": ach_tf / pk["bf16_tflops"], "traffic": None, "kernel": "infonce_tc_kernel<acc,online-max>", "kernel_ms": k_ms,
+            "frac": ach_tf / pk["bf16_tflops"], "traffic": None, "kernel": "infonce_tcx_kernel", "kernel_ms": k_ms,
             "alg_flops": flops, "alg_bytes": alg_bytes, "hbm_achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
-            "hbm_frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peaks": pk["source"] + ", burst bf16 (kernel timed alone)",
+            "hbm_frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "step_frac": flops / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops"],
+            "step_hbm_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "peaks": pk["source"] + ", burst bf16 (kernel timed alone)",
             "timing": ("in-graph CUDA events around a train of %d launches over %d distinct queue copies (%.0f MB > L2), time / launches"
                        % (train["launches_per_train"], train["launches_per_train"], train["distinct_queue_bytes"] / 1e6))
                       if train else "CUDA events around a graph replay",
             "kernel_ms_single_launch": k_ms_single, "frac_single_launch": flops / (k_ms_single * 1e-3) / 1e12 / pk["bf16_tflops"],
             "l2": "flushed before every train; every launch of a train reads a queue copy that is not L2-resident"}
-    prof = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    prof = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
     if os.path.exists(prof):
         try:
-            roof["traffic"] = json.load(open(prof)).get("infonce_tc_kernel_dram_bytes")
+            roof["traffic"] = json.load(open(prof)).get("infonce_tcx_kernel_dram_bytes")
         except (ValueError, OSError):
             pass
+    secondary = None if args.no_secondary else secondary_measurements(dev, flush, pk)
 
     cpu_rate, cpu_ms, cpu_n, cores = cpu_head_rate(60, 2, budget_s=15.0) if not args.no_cpu else (None, None, 0, 0)
     line = {
@@ -343,9 +453,14 @@ def run_single(args):
         "data": "synthetic",
         "config": {"workload": "moco_head_B256_K65536_d128", "B": B, "K": K, "d": D, "T": T, "queue_dtype": "bf16",
                    "algo": "tcgen05 single-pass (loss + dq in one queue sweep)", "cuda_graph": True, "input_pool": POOL,
-                   "l2": "flushed between timed iterations (256 MiB write, outside the per-step events)",
-                   "timing": "per-step CUDA events on the launch stream; value = 1000 / mean(ms)"},
-        "ms_per_step_median": dev_ms[len(dev_ms) // 2], "wall_s_total": wall, "loss_last": loss_last,
+                   "queue_pool": QPOOL, "outputs": "loss, dq[256,128], top-1/top-5 hit counts (rank_gt = NULL), enqueue + pointer",
+                   "l2": "no flush needed: consecutive steps use %d distinct queue replicas + workspaces (%.0f MB > 126 MB L2)"
+                         % (QPOOL, QPOOL * (K * D * 2 + 74 * B * D * 4) / 1e6),
+                   "timing": "EXACTLY `steps` graph-replayed steps back to back between ONE CUDA event pair on the launch "
+                             "stream, synchronised on both sides; value = steps / elapsed"},
+        "ms_per_step_isolated": ms_isolated, "isolated_note": "one step between its own event pair after a 256 MiB L2 flush "
+                                "(round 1's method; includes the launch latency of a lone graph)",
+        "wall_s_total": wall, "loss_last": loss_last,
         "clocks": clocks,
         "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                 "path": ("GraphedMoCoStep.step_host_io(): the step's first kernel reads q|k from the pinned host buffer over PCIe "
@@ -357,6 +472,7 @@ def run_single(args):
                 "loss_last": e2e_loss},
         "gpu_launches": launches,
         "roofline": roof,
+        "secondary": secondary,
         "cpu_baseline": None if args.no_cpu else {
             "value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": cpu_ms,
             "sample": "%d full-size steps (B=%d, K=%d, d=%d, fp32) of the oracle port of the reference step, %s" % (cpu_n, B, K, D, cpu_model())},
@@ -379,12 +495,16 @@ def run_multi(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(1)                                     # identical queue on every replica (upstream: broadcast from rank 0)
-    moco = gca_b200.RGBMoCo(D, K=K, T=T, queue_dtype="bf16").to(dev)
-    dist.broadcast(moco.memory, 0)
-    pool = 4
-    batches = synthetic_batches(100 + rank, pool, B, 0, device=dev)
-    state = torch.tensor([0, 0], dtype=torch.int64, device=dev)
+    # QPOOL queue replicas per rank (consecutive timed steps stream disjoint working sets from HBM, see run_single); every
+    # rank draws its own and rank 0's wins, as upstream (train_video_contrast_dis.py:233-242)
+    torch.manual_seed(1 + 1000 * rank)
+    mocos = [gca_b200.RGBMoCo(D, K=K, T=T, queue_dtype="bf16").to(dev) for _ in range(QPOOL)]
+    for m in mocos:
+        dist.broadcast(m.memory, 0)
+    moco = mocos[0]
+    pool = QPOOL
+    batches = synthetic_batches(100 + rank, 4, B, 0, device=dev)
+    states = [torch.tensor([0, 0], dtype=torch.int64, device=dev) for _ in range(QPOOL)]
     # key exchange: one peer-memory kernel per step (gca_keys_exchange over NVLink); NCCL all-gather if symmetric memory
     # cannot be set up on this box (GCA_BENCH_EXCHANGE=nccl forces it).  All ranks agree on the mode.
     exchange, why = None, "forced by GCA_BENCH_EXCHANGE"
@@ -413,8 +533,8 @@ def run_multi(args, rank, world, local_rank):
             exchange = None
     steps_g = []
     for i in range(pool):
-        s = GraphedReplicaStep(moco, B, state=state, exchange=exchange, fuse_exchange=(xmode == "fused"))
-        s.inputs[:2 * B].copy_(batches[i])
+        s = GraphedReplicaStep(mocos[i], B, state=states[i], exchange=exchange, fuse_exchange=(xmode == "fused"), want_rank=False)
+        s.inputs[:2 * B].copy_(batches[i % len(batches)])
         steps_g.append(s)
     graphed = True
     torch.cuda.synchronize()
@@ -435,26 +555,24 @@ def run_multi(args, rank, world, local_rank):
             s.step()
         else:
             s._enqueue_work(st)
-            moco.index = (moco.index + s.N) % K
+            s.moco.index = (s.moco.index + s.N) % K
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for i in range(args.warmup):
-        flush.fill_(i & 1)
         one(i)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if sampler:
         sampler.wait_first_sample()
     n0 = lib.gca_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     dist.barrier()
     if sampler:
         sampler.mark_start()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 1)
-        ev[i][0].record()
+    ev0.record()
+    for i in range(args.steps):                              # EXACTLY K steps, back to back, between one event pair per rank
         one(args.warmup + i)
-        ev[i][1].record()
+    ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
     wall = time.perf_counter() - t0
@@ -462,12 +580,27 @@ def run_multi(args, rank, world, local_rank):
         sampler.mark_end()
     clocks = sampler.stop() if sampler else None
     launches = (steps_g[0].launches_per_step * args.steps) if graphed else int(lib.gca_launch_count() - n0)
-    tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev)
+    tot = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(tot, op=dist.ReduceOp.MAX)              # max over ranks of the device-timed total
     ms_per_step = float(tot) / args.steps
     loss_last = float(steps_g[(args.warmup + args.steps - 1) % pool].loss)
-    # replicas must stay bit-identical: compare a checksum of the queue and the ring pointer across ranks
-    chk = torch.stack([moco.memory.float().sum().double(), state[0].double()])
+    # round 1's figure for continuity: one step between its own event pair after an L2 flush, max over ranks (it contains
+    # the launch skew between the ranks: a rank whose peers start the step later waits for their keys)
+    iso = []
+    for i in range(40):
+        flush.fill_(i & 1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        one(i)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 8:
+            iso.append(a.elapsed_time(b))
+    iso_t = torch.tensor([sum(iso) / len(iso)], device=dev)
+    dist.all_reduce(iso_t, op=dist.ReduceOp.MAX)
+    # replicas must stay bit-identical: compare a checksum of every queue replica and its ring pointer across ranks
+    chk = torch.stack([torch.stack([m.memory.float().sum().double() for m in mocos]).sum(),
+                       torch.stack([st_[0].double() for st_ in states]).sum()])
     chk_all = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(chk_all, chk)
     consistent = all(torch.equal(c, chk_all[0]) for c in chk_all)
@@ -524,7 +657,11 @@ def run_multi(args, rank, world, local_rank):
             sys.stdout.flush()
             sys.stderr.flush()
             os.execv(sys.executable, [sys.executable] + sys.argv)
-    sharded = time_sharded_k1m(rank, world, dev, flush) if not args.no_sharded else None
+    sharded = sharded_strong = None
+    if not args.no_sharded:
+        sharded = time_sharded_k1m(rank, world, dev, flush)
+        if B % world == 0:
+            sharded_strong = time_sharded_k1m(rank, world, dev, flush, steps=100, rows_per_gpu=B // world)
     if rank == 0:
         line = {
             "metric": METRIC, "value": world * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -538,10 +675,13 @@ def run_multi(args, rank, world, local_rank):
                                          "NVLink peer-memory stores fused into the step's own launches" if xmode == "fused" else
                                          "gca_keys_exchange: one NVLink peer-memory kernel per step", B * world),
                        "key_exchange": "nccl" if exchange is None else ("fused_p2p" if xmode == "fused" else "p2p_kernel"),
-                       "cuda_graph": graphed, "l2": "flushed between timed iterations (256 MiB write, outside the per-step events)",
-                       "timing": "per-step CUDA events, total = max over ranks; value = n_gpus * 1000 / ms_per_step "
-                                 "(each global step processes n_gpus x 256 rows)"},
-            "wall_s_total": wall, "loss_last": loss_last, "replicas_consistent": consistent, "clocks": clocks,
+                       "cuda_graph": graphed, "queue_pool": QPOOL,
+                       "outputs": "loss, dq[256,128], top-1/top-5 hit counts (rank_gt = NULL), enqueue + pointer",
+                       "l2": "no flush needed: consecutive steps use %d distinct queue replicas + workspaces per rank (> 126 MB L2)" % QPOOL,
+                       "timing": "EXACTLY `steps` steps back to back between ONE CUDA event pair per rank, barrier + synchronise on "
+                                 "both sides, max over ranks; value = n_gpus * steps / elapsed (each global step processes "
+                                 "n_gpus x 256 rows)"},
+            "ms_per_step_isolated": float(iso_t), "wall_s_total": wall, "loss_last": loss_last, "replicas_consistent": consistent, "clocks": clocks,
             "e2e": {"value": world * 1e3 / float(e2e), "unit": UNIT, "h2d_bytes_per_step": 2 * B * D * 4,
                     "d2h_bytes_per_step": g0.outputs.numel() * 4, "ms_per_step": float(e2e),
                     "path": "GraphedReplicaStep.step_host_io(): one graph launch per step, q|k read from / results stored to pinned "
@@ -549,6 +689,7 @@ def run_multi(args, rank, world, local_rank):
                             "H2D copy -> step -> D2H copy, host barrier + stream sync every step"},
             "gpu_launches": launches,
             "sharded_k1m": sharded,
+            "sharded_k1m_strong": sharded_strong,
         }
         print(json.dumps(line), flush=True)
     # Leave without tearing the communicator down: destroy_process_group() after NCCL work was captured into CUDA graphs
@@ -560,25 +701,27 @@ def run_multi(args, rank, world, local_rank):
     os._exit(0)
 
 
-def time_sharded_k1m(rank, world, dev, flush, steps=200, warmup=10):
-    """BASELINE config 4: queue 2^20 x 128 (bf16) split along K over the ranks, 256 rows per GPU; per-shard online-softmax
-    partials merged with NCCL.  One CUDA graph per step (gca_b200.graphed.GraphedShardedStep: 3 collectives + kernels);
-    the first step is cross-checked against the eager ShardedRGBMoCo path.  Per-step device time with an L2 flush
-    before every step, max over ranks."""
+def time_sharded_k1m(rank, world, dev, flush, steps=200, warmup=10, rows_per_gpu=B):
+    """BASELINE config 4: queue 2^20 x 128 (bf16) split along K over the ranks, `rows_per_gpu` query rows per GPU (256: the
+    weak-scaling series, constant work per GPU; 256 / world: the strong-scaling series with B_global = 256, SURVEY 8d c4);
+    per-shard online-softmax partials merged with NCCL.  One CUDA graph per step (gca_b200.graphed.GraphedShardedStep);
+    the first step is cross-checked against the eager ShardedRGBMoCo path (tests/sharded_graph_worker.py checks both against
+    the oracle).  Per-step device time with an L2 flush before every step, max over ranks."""
     import torch
     import torch.distributed as dist
     import gca_b200
     from gca_b200.dist import ShardedRGBMoCo
     from gca_b200.graphed import GraphedShardedStep
     K1 = 1 << 20
+    Bl = int(rows_per_gpu)
     torch.manual_seed(1)
     moco = ShardedRGBMoCo(D, K=K1, T=T, queue_dtype="bf16", device=dev)
     crit = gca_b200.NCESoftmaxLoss()
-    batches = synthetic_batches(300 + rank, 2, B, 0, device=dev)
+    batches = synthetic_batches(300 + rank, 2, Bl, 0, device=dev)
     # eager reference step on a copy of the shard
     shard0 = moco.memory.clone()
-    q = batches[0][:B].clone().requires_grad_(True)
-    out, _ = moco(q, batches[0][B:2 * B])
+    q = batches[0][:Bl].clone().requires_grad_(True)
+    out, _ = moco(q, batches[0][Bl:2 * Bl])
     loss_eager = crit(out)
     loss_eager.backward()
     torch.cuda.synchronize()
@@ -586,8 +729,8 @@ def time_sharded_k1m(rank, world, dev, flush, steps=200, warmup=10):
     moco.memory.copy_(shard0)
     moco.index = 0
     del shard0
-    gs = GraphedShardedStep(moco, B).capture()
-    gs.step(batches[0][:B], batches[0][B:2 * B])
+    gs = GraphedShardedStep(moco, Bl).capture()
+    gs.step(batches[0][:Bl], batches[0][Bl:2 * Bl])
     torch.cuda.synchronize()
     same = bool(torch.equal(gs.loss, loss_eager.detach().reshape(1)) and torch.equal(gs.dq, q.grad)
                 and torch.equal(moco.memory, mem_eager))
@@ -596,8 +739,8 @@ def time_sharded_k1m(rank, world, dev, flush, steps=200, warmup=10):
     for i in range(warmup + steps):
         flush.fill_(i & 1)
         pk = batches[i % 2]
-        gs.q.copy_(pk[:B])
-        gs.k.copy_(pk[B:2 * B])
+        gs.q.copy_(pk[:Bl])
+        gs.k.copy_(pk[Bl:2 * Bl])
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         gs.step()
@@ -610,9 +753,9 @@ def time_sharded_k1m(rank, world, dev, flush, steps=200, warmup=10):
     ok = torch.tensor([1 if same else 0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     ms = float(tot) / steps
-    flops = 4.0 * (B * world) * (K1 / world) * D
-    return {"K": K1, "rows_per_gpu": B, "rows_global": B * world, "shard_rows": K1 // world, "ms_per_step": ms,
-            "global_rows_per_s": B * world / ms * 1e3, "per_gpu_tflops": flops / (ms * 1e-3) / 1e12, "cuda_graph": True,
+    flops = 4.0 * (Bl * world) * (K1 / world) * D
+    return {"K": K1, "rows_per_gpu": Bl, "rows_global": Bl * world, "shard_rows": K1 // world, "ms_per_step": ms,
+            "global_rows_per_s": Bl * world / ms * 1e3, "per_gpu_tflops": flops / (ms * 1e-3) / 1e12, "cuda_graph": True,
             "launches_per_step": gs.launches_per_step, "collectives_per_step": 3,
             "graph_equals_eager_path": bool(int(ok))}
 
@@ -625,6 +768,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the extra K-sharded 2^20-row measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="N = 1: skip the secondary figures (fp32 mode, K = 2^20, graph head, retrieval)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -244,9 +244,11 @@ int gca_sim_topk(const float* queries, const float* gallery, int Nq, int Ng, int
  *   chunk_table : DEVICE array of nchunks descriptors {float* ema; const float* src; long long n;}
  *                 (gca_ema_chunk_bytes() each), built once per model by the caller; a descriptor covers at most
  *                 a few thousand contiguous elements of one parameter tensor
+ *   one_minus_momentum : the reference's `alpha = 1 - m`, a Python double rounded ONCE to fp32 -- the caller passes
+ *                 (float)(1.0 - m); computing 1.f - momentum in fp32 is off by up to 5e-5 relative for m = 0.999
  * --------------------------------------------------------------------------------------------------------- */
 size_t gca_ema_chunk_bytes(void);
-int gca_ema_update(const void* chunk_table, int nchunks, float momentum, void* stream);
+int gca_ema_update(const void* chunk_table, int nchunks, float momentum, float one_minus_momentum, void* stream);
 
 #ifdef __cplusplus
 }

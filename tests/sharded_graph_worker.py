@@ -10,6 +10,7 @@ import torch.distributed as dist
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(os.path.dirname(HERE), "video-graph-ssl_b200"))
+sys.path.insert(0, os.path.dirname(HERE))                              # the oracle (checker only)
 
 
 def main():
@@ -38,6 +39,7 @@ def main():
             q = torch.nn.functional.normalize(torch.randn(Bl, d, generator=gen)).to(dev)
             k = torch.nn.functional.normalize(torch.randn(Bl, d, generator=gen)).to(dev)
             qa = q.clone().requires_grad_(True)
+            full_before = a.gather_full_queue().double().cpu()          # the queue one replica of the reference would hold
             out, _ = a(qa, k)
             la = crit(out)
             la.backward()
@@ -48,7 +50,24 @@ def main():
             assert torch.equal(out.rank, gs.rank) and torch.equal(out.lse, gs.lse), step
             assert a.index == b.index and int(gs.state[0]) == b.index, step
             assert torch.equal(a.memory, b.memory), step
+            # ... and against the ORACLE: the reference step of this rank's rows on the full (replicated) queue
+            import oracle
+            if qdt == "bf16":
+                c2 = torch.tensor(1.0 / T, dtype=torch.float32) * torch.tensor(1.4426950408889634, dtype=torch.float32)
+                rq = (q.cpu() * c2).to(torch.bfloat16).double() / c2.double()
+                ltol, gtol = 2e-3, 1e-2
+            else:
+                rq, ltol, gtol = q.cpu().double(), 1e-5, 1e-3
+            o = oracle.infonce_step(rq, k.cpu().double(), full_before.clone(), 0, T)
+            assert abs(float(lb) - float(o["loss"])) <= ltol * abs(float(o["loss"])), (step, float(lb), float(o["loss"]))
+            err = float((gs.dq.cpu().double() - o["dq"]).abs().max() / o["dq"].abs().max())
+            assert err <= gtol, (step, err)
+            neg = oracle.logits_full(rq, k.cpu().double(), full_before, T)[:, 1:]
+            pos = ((q.cpu().double() * k.cpu().double()).sum(1) / T)[:, None]   # the kernels take the positive from the fp32 q.k
+            ok = (neg - pos).abs().min(1).values > 3e-4
+            assert torch.equal(gs.rank.cpu().long()[ok], (neg > pos).sum(1)[ok]), step
         assert gs.launches_per_step >= 5
+    assert gs.launches_per_step >= 5
     dist.barrier()
     torch.cuda.synchronize()
     if rank == 0:

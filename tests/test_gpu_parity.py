@@ -265,6 +265,95 @@ def test_infonce_tcgen05_unnormalised_inputs_leave_the_packed_loss_word(GF):
         assert r["hits"].cpu().tolist() == [int((rank < 1).sum()), int((rank < 5).sum())]
 
 
+def _rank_band_check(rank, neg, pos, band):
+    """Ranks are integers, but a rank computed from fp32 tensor-core sums can only be pinned up to the negatives that sit
+    within the accumulation noise of the positive: |rank - rank_ref| <= #{j : |neg_bj - pos_b| <= band} for every row.
+    Returns (rows whose band is empty, mean band population)."""
+    rank_ref = (neg > pos[:, None]).sum(1)
+    inband = ((neg - pos[:, None]).abs() <= band).sum(1)
+    diff = (rank.cpu().long() - rank_ref).abs()
+    assert bool((diff <= inband).all()), (int((diff - inband).max()), int(inband.max()))
+    exact_rows = inband == 0
+    assert torch.equal(rank.cpu().long()[exact_rows], rank_ref[exact_rows])
+    return int(exact_rows.sum()), float(inband.float().mean())
+
+
+@pytest.mark.parametrize("algo,qdt", [("tcgen05", torch.bfloat16), ("ffma", torch.float32)])
+def test_infonce_rank_and_hits_at_the_headline_shape(GF, algo, qdt):
+    """(B, K) = (256, 65536): the rank of the positive in EVERY row against the fp64 oracle fed the kernel's own inputs,
+    within the noise band of fp32 accumulation (4e-7 in dot-product units -- the 65536 negatives of a row are ~3e-6 apart
+    around a random positive, so about one row in four has a negative inside the band),
+    and the top-1 / top-5 hit counts the step reports.  Half of the positives are made hard (rank < 50) so that top-5 is
+    not trivially empty."""
+    gen = torch.Generator().manual_seed(4242)
+    B, K, T = 256, 65536, 0.07
+    mem = unit_rows(K, 128, gen).to(qdt)
+    q = unit_rows(B, 128, gen)
+    k = unit_rows(B, 128, gen)
+    k[::2] = F.normalize(q[::2] * 0.42 + k[::2])                          # cos ~ 0.39: around the top few of 65536 negatives
+    rq = tcq(q, T) if algo == "tcgen05" else q.double()
+    pos = (q.double() * k.double()).sum(1) / T
+    neg = (rq @ mem.double().t()) / T
+    r = GF.infonce_forward(cu(q), cu(k), cu(mem), T, algo=algo, want_grad=True)
+    torch.cuda.synchronize()
+    exact, mean_band = _rank_band_check(r["rank"], neg, pos, 4e-7 / T)
+    assert exact >= B // 2 and mean_band < 1.0, (exact, mean_band)       # the check is not vacuous
+    rank_ref = (neg > pos[:, None]).sum(1)
+    assert 0 < int((rank_ref < 5).sum()) < B
+    rank = r["rank"].cpu().long()
+    assert r["hits"].cpu().tolist() == [int((rank < 1).sum()), int((rank < 5).sum())]
+    sure = ((neg - pos[:, None]).abs() <= 4e-7 / T).sum(1) == 0
+    hits_ref = [int((rank_ref < 1).sum()), int((rank_ref < 5).sum())]
+    slack = int((~sure).sum())
+    assert all(abs(a - b) <= slack for a, b in zip(r["hits"].cpu().tolist(), hits_ref))
+
+
+def test_infonce_tcgen05_top_hits_only_mode(lib, GF):
+    """rank_gt == NULL (include/gca_b200.h): the caller wants the top-1 / top-5 hit counts only, so a warp may stop counting
+    once all of its rows are past GCA_TOPK_RANK_CAP.  Hits, loss and gradient must equal the exact-rank call."""
+    from gca_b200 import _lib
+    from gca_b200._lib import ptr
+    import ctypes
+    gen = torch.Generator().manual_seed(77)
+    B, K, T = 256, 16384, 0.07
+    mem = cu(unit_rows(K, 128, gen).to(torch.bfloat16))
+    q, k = unit_rows(B, 128, gen), unit_rows(B, 128, gen)
+    k[::3] = F.normalize(q[::3] * 0.5 + k[::3])
+    q, k = cu(q), cu(k)
+    full = GF.infonce_forward(q, k, mem, T, algo="tcgen05", want_grad=True)
+    ws = GF.workspace(q.device, GF.infonce_workspace_bytes(B, K, 128, 1, "tcgen05"), "hits_only")
+    f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=q.device)
+    loss, rows, lse, pos, dq = f32(1), f32(B), f32(B), f32(B), f32(B, 128)
+    hits = torch.zeros(2, dtype=torch.int32, device=q.device)
+    _lib.call("gca_infonce_fwd", ptr(q), ptr(k), ptr(mem), 1, B, K, 128, 1.0 / T, 2, ptr(loss), ptr(rows), ptr(lse), ptr(pos),
+              None, ptr(hits), ptr(dq), None, ptr(ws), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert hits.cpu().tolist() == full["hits"].cpu().tolist() and 0 < int(hits[1]) < B
+    assert torch.equal(loss.view(()), full["loss"].view(())) and torch.equal(dq, full["dq_unit"]) and torch.equal(lse, full["lse"])
+
+
+@pytest.mark.parametrize("T", [0.011, 0.005])
+def test_infonce_tcgen05_tiny_temperature(GF, T):
+    """1/T beyond 60 log2 units: the first sweep's reference exponent is no longer 0 (T = 0.005: 1/T - 100 log2 units) and
+    rows whose best key is far below 1/T leave the validity window, so their CTA redoes the range with the exact row max."""
+    gen = torch.Generator().manual_seed(5)
+    B, K = 128, 4096
+    mem = unit_rows(K, 128, gen).to(torch.bfloat16)
+    q, k = unit_rows(B, 128, gen), unit_rows(B, 128, gen)
+    k[:32] = q[:32]
+    rq = tcq(q, T)
+    pos = (q.double() * k.double()).sum(1) / T
+    neg = (rq @ mem.double().t()) / T
+    lse = torch.logsumexp(torch.cat([pos[:, None], neg], 1), 1)
+    dq_ref = ((torch.exp(pos - lse) - 1)[:, None] * k.double() + torch.exp(neg - lse[:, None]) @ mem.double()) / (T * B)
+    r = GF.infonce_forward(cu(q), cu(k), cu(mem), T, algo="tcgen05", want_grad=True)
+    torch.cuda.synchronize()
+    assert rel_max(r["lse"], lse) <= 2e-5
+    assert abs(float(r["loss"]) - float((lse - pos).mean())) <= 3e-5 * float((lse - pos).mean())
+    assert rel_max(r["dq_unit"], dq_ref) <= 5e-3
+    _rank_band_check(r["rank"], neg, pos, 1e-6 / T)
+
+
 @pytest.mark.parametrize("B,K", [(32, 4096), (256, 65536)])
 def test_infonce_bf16_mode_within_baseline_tolerance(GF, B, K):
     """bf16 mode against the fp32 reference arithmetic on UNrounded inputs: loss 2e-3, gradient 1e-2 (BASELINE.json)."""
@@ -398,6 +487,65 @@ def test_rgbmoco_all_k_and_jig(lib, golden):
     assert moco.index == int(g["index_after0"]) and out_jig.shape == out.shape
 
 
+@pytest.mark.parametrize("queue_dtype", ["fp32", "bf16"])
+def test_rgbmoco_jig_head_against_reference_fixture(lib, golden, queue_dtype):
+    """`RGBMoCo.forward(q, k, q_jig=...)` (mem_moco.py:73-76, 85-86): BOTH heads' losses and gradients against the values
+    the reference's own module + NCESoftmaxLoss produced (oracle/gen_golden_cmc.py)."""
+    import gca_b200
+    j = golden("rgb_jig")
+    moco = gca_b200.RGBMoCo(128, K=int(j["K"]), T=float(j["T"]), queue_dtype=queue_dtype).cuda()
+    moco.load_state_dict({"memory": T_(j["memory_before"])})
+    crit = gca_b200.NCESoftmaxLoss()
+    ltol, gtol = (LOSS_RTOL_FP32, 1e-4) if queue_dtype == "fp32" else (LOSS_RTOL_BF16, GRAD_RTOL)
+    for st in range(int(j["steps"])):
+        q, qj = cu(T_(j[f"q{st}"])).requires_grad_(True), cu(T_(j[f"q_jig{st}"])).requires_grad_(True)
+        out, out_jig, labels = moco(q, cu(T_(j[f"k{st}"])), q_jig=qj)
+        l0, l1 = crit(out), crit(out_jig)
+        (l0 + l1).backward()
+        for l, x, name in ((l0, q, ""), (l1, qj, "_jig")):
+            assert abs(float(l.detach()) - float(j[f"loss{name}{st}"])) <= ltol * float(j[f"loss{name}{st}"])
+            assert rel_max(x.grad, T_(j[f"dq{name}{st}"])) <= gtol
+        assert moco.index == int(j[f"index_after{st}"]) and labels.shape == (q.shape[0],)
+    mem = moco.state_dict()["memory"].cpu()
+    ref = T_(j["memory_after"])
+    assert torch.equal(mem, ref if queue_dtype == "fp32" else bf16r(ref))
+
+
+@pytest.mark.parametrize("queue_dtype", ["fp32", "bf16"])
+def test_cmcmoco_against_reference_fixture(lib, golden, queue_dtype):
+    """`CMCMoCo` (mem_moco.py:91-142): two queues, cross-modal positives, jig heads, gathered keys crossing the end of the
+    ring -- every head's loss and gradient, both queues' contents and the shared pointer against the reference's module."""
+    import gca_b200
+    g = golden("cmc_moco")
+    K, T = int(g["K"]), float(g["T"])
+    m = gca_b200.CMCMoCo(128, K=K, T=T, queue_dtype=queue_dtype).cuda()
+    m.load_state_dict({"memory_1": T_(g["memory_1_before"]), "memory_2": T_(g["memory_2_before"])})
+    m.index = int(g["start_index"])
+    crit = gca_b200.NCESoftmaxLoss()
+    ltol, gtol = (LOSS_RTOL_FP32, 1e-4) if queue_dtype == "fp32" else (LOSS_RTOL_BF16, GRAD_RTOL)
+    for st in range(int(g["steps"])):
+        nh = 4 if f"q{st}_3" in g else 2
+        qs = [cu(T_(g[f"q{st}_{i}"])).requires_grad_(True) for i in range(nh)]
+        kw = {}
+        if nh == 4:
+            kw.update(q1_jig=qs[2], q2_jig=qs[3])
+        if f"all_k1_{st}" in g:
+            kw.update(all_k1=cu(T_(g[f"all_k1_{st}"])), all_k2=cu(T_(g[f"all_k2_{st}"])))
+        out = m(qs[0], cu(T_(g[f"k1_{st}"])), qs[1], cu(T_(g[f"k2_{st}"])), **kw)
+        heads, labels = out[:-1], out[-1]
+        assert len(heads) == nh and labels.dtype == torch.int64 and int(labels.abs().sum()) == 0
+        losses = [crit(h) for h in heads]
+        sum(losses).backward()
+        for i in range(nh):
+            assert abs(float(losses[i].detach()) - float(g[f"loss{st}_{i}"])) <= ltol * float(g[f"loss{st}_{i}"]), (st, i)
+            assert rel_max(qs[i].grad, T_(g[f"dq{st}_{i}"])) <= gtol, (st, i)
+        assert m.index == int(g[f"index_after{st}"])                                    # integer: exact
+    sd = m.state_dict()
+    for name in ("memory_1", "memory_2"):
+        ref = T_(g[name + "_after"])
+        assert torch.equal(sd[name].cpu(), ref if queue_dtype == "fp32" else bf16r(ref))  # slot contents: exact
+
+
 def test_materialized_logits_mode(lib, golden):
     import gca_b200
     g = golden("infonce_small")
@@ -483,9 +631,12 @@ def test_graph_module_draws_like_reference_rsample(lib):
 
 
 @pytest.mark.parametrize("shape,sub", [((3, 32, 8, 28, 28), True), ((2, 24, 16, 14, 14), False), ((2, 8, 32, 6, 6), False),
-                                       ((5, 64, 8, 7, 7), False), ((130, 256, 8, 1, 1), False)])
+                                       ((5, 64, 8, 7, 7), False), ((130, 256, 8, 1, 1), False),
+                                       ((128, 192, 8, 14, 14), True), ((128, 1024, 8, 1, 1), False)])
 def test_graph_core_random_shapes(GF, shape, sub):
-    """Large feature maps (split adjacency + grid aggregation path), odd spatial sizes, T up to 32."""
+    """Large feature maps (split adjacency + grid aggregation path), odd spatial sizes, T up to 32; the last two are
+    BASELINE config 3 at full size: the S3D base.5 feature map [128, 192, 8, 14, 14] with sub-sampled projections and
+    the embedding-level head [128, 1024, 8, 1, 1]."""
     B, C, T, H, W = shape
     gen = torch.Generator().manual_seed(sum(shape))
     x = torch.randn(*shape, generator=gen)
@@ -631,6 +782,7 @@ def test_graphed_step_matches_oracle_over_a_lap(lib, queue_dtype, B, N, K):
     assert step.launches_per_step == (3 if queue_dtype == "bf16" else 2)
     for it in range(K // N + 3):
         q, k, all_k = unit_rows(B, 128, gen), unit_rows(B, 128, gen), unit_rows(N, 128, gen)
+        prev_mem = ref_mem.clone()
         loss = step.step(cu(q), cu(k), cu(all_k))
         rq = tcq(q, moco.T) if queue_dtype == "bf16" else q
         o = oracle.infonce_step(rq.double(), k.double(), ref_mem.double(), 0, 0.07)
@@ -640,6 +792,16 @@ def test_graphed_step_matches_oracle_over_a_lap(lib, queue_dtype, B, N, K):
         assert rel_max(step.dq, o["dq"]) <= GRAD_RTOL
         hits = step.hits.cpu().tolist()
         assert hits[0] <= hits[1] <= B
+        # top-1 / top-5 hit counts (what `accuracy` reports, train...:428) against the oracle's ranks, up to the rows whose
+        # nearest negative sits inside the accumulation noise of the positive
+        # (the kernels take the positive from the unrounded fp32 q.k, the negatives from the bf16-rounded queries)
+        neg = oracle.logits_full(rq.double(), k.double(), prev_mem.double(), 0.07)[:, 1:]
+        pos = ((q.double() * k.double()).sum(1) / 0.07)[:, None]
+        rank_ref = (neg > pos).sum(1)
+        clear = (neg - pos).abs().min(1).values > 3e-4
+        unsure = int((~clear).sum())
+        assert abs(hits[0] - int((rank_ref < 1).sum())) <= unsure and abs(hits[1] - int((rank_ref < 5).sum())) <= unsure
+        assert torch.equal(step.rank.cpu().long()[clear], rank_ref[clear])
         assert moco.index == idx
     torch.cuda.synchronize()
     assert int(step.state[0]) == idx and int(step.state[1]) == 0           # device pointer == host pointer == oracle
@@ -832,3 +994,29 @@ def test_peer_key_exchange_single_rank():
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "peer_exchange_worker.py")],
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and "PEER_EXCHANGE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+def _torchrun(worker, nproc, port, timeout=600):
+    import subprocess
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(os.path.dirname(os.path.abspath(__file__)), worker)]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL)")
+def test_shuffle_bn_over_nccl_against_reference_fixture():
+    """`gca_b200.dist.ShuffleBN` on two GPUs over NCCL against the fixture produced by the reference's `_shuffle_bn`."""
+    r = _torchrun("shuffle_bn_worker.py", 2, 29731)
+    assert r.returncode == 0 and "SHUFFLE_BN_NCCL_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL + NVLink peer memory)")
+@pytest.mark.parametrize("worker,token", [("sharded_graph_worker.py", "SHARDED_GRAPH_OK"), ("peer_exchange_worker.py", "PEER_EXCHANGE_OK")])
+def test_multi_gpu_workers(worker, token):
+    """The K-sharded step (eager == graph == ORACLE) and the peer-memory key exchange on every visible GPU (2, 4 or 8)."""
+    n = 8 if torch.cuda.device_count() >= 8 else 4 if torch.cuda.device_count() >= 4 else 2
+    r = _torchrun(worker, n, 29741 + len(worker))
+    assert r.returncode == 0 and token in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])

@@ -167,3 +167,37 @@ def test_projection_tail_oracle_matches_reference_fixture(golden):
     assert float((o["dz"] - torch.from_numpy(g["dz"])).abs().max()) <= 1e-4 * float(np.abs(g["dz"]).max())
     assert o["index"] == int(g["index_after"])
     assert torch.equal(mem[:zq.shape[0]], torch.from_numpy(g["enqueued_rows"]))        # slot contents: exact
+
+
+def test_cmc_moco_and_jig_heads_match_reference(golden):
+    """Fixtures from the reference's CMCMoCo / RGBMoCo(q_jig=...) (oracle/gen_golden_cmc.py): every head is the ordinary
+    InfoNCE step against the OTHER modality's keys and queue (mem_moco.py:120-125); both queues take the same slots."""
+    g = golden("cmc_moco")
+    K, T = int(g["K"]), float(g["T"])
+    m1, m2, idx = T_(g["memory_1_before"]).clone(), T_(g["memory_2_before"]).clone(), int(g["start_index"])
+    for st in range(int(g["steps"])):
+        k1, k2 = T_(g[f"k1_{st}"]), T_(g[f"k2_{st}"])
+        nheads = 4 if f"q{st}_3" in g else 2
+        for i in range(nheads):
+            k, mem = ((k2, m2), (k1, m1))[i % 2]
+            o = oracle.infonce_step(T_(g[f"q{st}_{i}"]), k, mem.clone(), 0, T)
+            assert abs(float(o["loss"]) - float(g[f"loss{st}_{i}"])) <= 1e-5 * abs(float(g[f"loss{st}_{i}"]))
+            np.testing.assert_allclose(o["dq"].numpy(), g[f"dq{st}_{i}"], rtol=1e-4, atol=1e-7)
+        new1 = T_(g[f"all_k1_{st}"]) if f"all_k1_{st}" in g else k1
+        new2 = T_(g[f"all_k2_{st}"]) if f"all_k2_{st}" in g else k2
+        oracle.enqueue(m1, new1, idx)
+        idx = oracle.enqueue(m2, new2, idx)
+        assert idx == int(g[f"index_after{st}"])
+    assert idx < 20                                                       # the ring wrapped
+    assert torch.equal(m1, T_(g["memory_1_after"])) and torch.equal(m2, T_(g["memory_2_after"]))
+    j = golden("rgb_jig")
+    mem, idx = T_(j["memory_before"]).clone(), 0
+    for st in range(int(j["steps"])):
+        k = T_(j[f"k{st}"])
+        for name in ("", "_jig"):
+            o = oracle.infonce_step(T_(j[f"q{name}{st}"]), k, mem.clone(), 0, float(j["T"]))
+            assert abs(float(o["loss"]) - float(j[f"loss{name}{st}"])) <= 1e-5 * abs(float(j[f"loss{name}{st}"]))
+            np.testing.assert_allclose(o["dq"].numpy(), j[f"dq{name}{st}"], rtol=1e-4, atol=1e-7)
+        idx = oracle.enqueue(mem, k, idx)
+        assert idx == int(j[f"index_after{st}"])
+    assert torch.equal(mem, T_(j["memory_after"]))

@@ -41,7 +41,7 @@ ema_update_kernel(const EmaChunk* __restrict__ chunks, int nchunks, float m, flo
 
 extern "C" size_t gca_ema_chunk_bytes(void) { return sizeof(gca::EmaChunk); }
 
-extern "C" int gca_ema_update(const void* chunk_table, int nchunks, float momentum, void* stream)
+extern "C" int gca_ema_update(const void* chunk_table, int nchunks, float momentum, float one_minus_momentum, void* stream)
 {
     using namespace gca;
     GCA_CHECK_ARG(chunk_table || nchunks == 0, "gca_ema_update: null chunk table");
@@ -51,7 +51,7 @@ extern "C" int gca_ema_update(const void* chunk_table, int nchunks, float moment
     int sms = sm_count_cached();
     if (sms < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
     int blocks = nchunks < sms * 8 ? nchunks : sms * 8;
-    ema_update_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const EmaChunk*)chunk_table, nchunks, momentum, 1.f - momentum);
+    ema_update_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const EmaChunk*)chunk_table, nchunks, momentum, one_minus_momentum);
     GCA_LAUNCH_CHECK("ema_update_kernel");
     count_launch(1);
     return GCA_OK;

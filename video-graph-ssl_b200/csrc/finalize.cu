@@ -51,16 +51,21 @@ __device__ __forceinline__ void enqueue_rows(const FinalizeParams& F, int blk, i
     const float4* keys = reinterpret_cast<const float4*>(F.enq_keys);
     const bool peer = F.xchg.mailboxes != nullptr;
     unsigned long long xstep = 0;
+    bool timed_out = false;
     if (peer) {
         // the gathered keys are this rank's mailbox slots of the current parity: [W][B*d] == all_k, pushed by the peers'
         // prep kernels while the queue was being swept.  Wait for every (rank, slice) flag, then read around L1.
         xstep = *reinterpret_cast<volatile unsigned long long*>(F.xchg.xstate);
+        int ok = 1;
         if ((int)threadIdx.x < F.xchg.W * XCHG_SLICES)
-            xchg_wait_slice(F.xchg, xstep, threadIdx.x / XCHG_SLICES, threadIdx.x % XCHG_SLICES);
-        __syncthreads();
+            ok = xchg_wait_slice(F.xchg, xstep, threadIdx.x / XCHG_SLICES, threadIdx.x % XCHG_SLICES) ? 1 : 0;
+        // a peer that did not deliver within the timeout (xstate[2] is raised, sticky): this CTA writes nothing -- the mailbox
+        // holds stale rows -- and the last CTA below leaves the ring pointer where it was.  The step's loss and gradient do not
+        // depend on the gathered keys; the caller polls the flag (PeerKeyExchange.check(), GraphedReplicaStep.step()).
+        timed_out = (__syncthreads_and(ok) == 0);
         keys = xchg_slot(F.xchg.mailboxes[F.xchg.rank], F.xchg, (int)(xstep & 1ull), 0);
     }
-    for (long long i = (long long)blk * FIN_THREADS + threadIdx.x; i < total; i += (long long)nblk * FIN_THREADS) {
+    for (long long i = (long long)blk * FIN_THREADS + threadIdx.x; !timed_out && i < total; i += (long long)nblk * FIN_THREADS) {
         const int row = (int)(i / d4), c4 = (int)(i - (long long)row * d4);
         long long slot = index + row;
         if (slot >= F.enq_K) slot -= F.enq_K;
@@ -85,7 +90,9 @@ __device__ __forceinline__ void enqueue_rows(const FinalizeParams& F, int blk, i
         if (last && threadIdx.x == 0) {
             long long nx = index + F.enq_N;
             if (nx >= F.enq_K) nx -= F.enq_K;
-            F.enq_state[0] = nx;
+            // (every enqueue CTA raised the flag before taking its ticket if its wait expired)
+            const bool failed = peer && *reinterpret_cast<volatile unsigned long long*>(F.xchg.xstate + 2) != 0ull;
+            if (!failed) F.enq_state[0] = nx;
             F.enq_state[1] = 0;
             if (peer) F.xchg.xstate[0] = xstep + 1;       // every enqueue CTA has read the step before taking its ticket
         }

@@ -103,7 +103,7 @@ static int nsplit_for(int algo, int B, long long K, int d)
 static int run_stream(const float* q, const float* k, const void* queue, int dtype_queue, int B, long long K, int d,
                       float inv_T, int algo, const float* lse_fixed, bool want_acc, float* pos_out, float* logits_out,
                       void* workspace, size_t workspace_bytes, InfoNceWs* ws_out, cudaStream_t st, bool skip_prep = false,
-                      FinalizeParams* fuse = nullptr, const PeerXchg* px = nullptr, float* proj_k_hat = nullptr,
+                      const PeerXchg* px = nullptr, float* proj_k_hat = nullptr,
                       bool proj = false, int rank_cap = 0)
 {
     const int a = pick_algo(algo, dtype_queue, d);
@@ -133,11 +133,6 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
     }
     *ws_out = ws;
     count_launch(1);
-    if (fuse) {                                         // single-launch path: the stream kernel finalizes (and enqueues) itself
-        fuse->counter = ws.counter; fuse->part_max = ws.part_max; fuse->part_sum = ws.part_sum; fuse->part_cnt = ws.part_cnt;
-        fuse->part_acc = ws.part_acc; fuse->nsplit = ws.nsplit; fuse->Bpad = ws.Bpad;
-        return infonce_tc_launch(P, false, st, fuse);
-    }
     if (a == GCA_ALGO_TCGEN05) return infonce_tc_launch(P, lse_fixed != nullptr, st);
     return infonce_ffma_launch(P, dtype_queue, lse_fixed != nullptr, st);
 }
@@ -188,16 +183,8 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
         F.enq_index = enq_index; F.enq_state = enq_state;
         if (px) F.xchg = *px;
     }
-    // tcgen05 with gradient and no materialised logits: one launch does stream + finalize (+ enqueue) behind a grid barrier.
-    // (an enqueue that has to wait for an event on another stream keeps the two-kernel path: the wait sits between them)
-    const bool fused = pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05 && dq_unit != nullptr && logits_out == nullptr &&
-                       keys_ready_event == nullptr && px == nullptr && !proj && infonce_tc_can_fuse(B, K);
-    if (fused) {
-        return run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, true, pos_logit, nullptr, workspace,
-                          workspace_bytes, &ws, st, false, &F);
-    }
     rc = run_stream(q, k, queue, dtype_queue, B, K, d, inv_T, algo, nullptr, dq_unit != nullptr, pos_logit, logits_out,
-                    workspace, workspace_bytes, &ws, st, false, nullptr, px, k_hat_out, proj, rank_gt ? 0 : GCA_TOPK_RANK_CAP);
+                    workspace, workspace_bytes, &ws, st, false, px, k_hat_out, proj, rank_gt ? 0 : GCA_TOPK_RANK_CAP);
     if (rc != GCA_OK) return rc;
     if (proj) {                                          // the finalize kernel works on the normalised keys and maps dq to dzq
         const float* kh = k_hat_out ? k_hat_out : ws.k_hat;

@@ -43,9 +43,7 @@ int infonce_ffma_nsplit(int B, long long K, int d);
 int infonce_ffma_launch(const InfoNceStreamParams& P, int dtype_queue, bool fixed_max, cudaStream_t st);
 // tcgen05 family (infonce_tc.cu)
 int infonce_tc_nsplit(int B, long long K);
-struct FinalizeParams;
-int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t st, const FinalizeParams* fuse = nullptr);
-bool infonce_tc_can_fuse(int B, long long K);
+int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t st);
 
 // finalize.cu
 enum FinalizeMode { FIN_FULL = 0, FIN_SHARD = 1, FIN_BWD = 2 };

@@ -13,9 +13,6 @@
 #include "infonce_params.cuh"
 #include "tc_ptx.cuh"
 #include <stdlib.h>
-#ifndef GCA_TC_FUSED_SWEEP
-#define GCA_TC_FUSED_SWEEP 0      // experimental one-pass softmax sweep (see the stream kernel); 0 = product path
-#endif
 
 namespace gca {
 
@@ -66,209 +63,10 @@ struct TcBarriers {
     uint32_t tmem_base;
 };
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Fused finalize (called by the 256 softmax threads of every CTA once their split partial is written).
-//   grid barrier   : all CTAs are co-resident (grid <= #SMs, one CTA per SM; cooperative launch), so a generation-counting
-//                    barrier in the workspace control block is safe; it also marks the point after which nobody reads the
-//                    queue any more
-//   rows           : CTA c merges query rows c, c + nCTA, ... two at a time: every thread first puts its share of the
-//                    gradient partials of both rows in flight, warps 0 / 1 merge the split statistics of row a / b with
-//                    shuffles, then fixed-order sums (deterministic) -- same arithmetic as infonce_finalize_kernel
-//   enqueue        : CTA c copies key rows c, c + nCTA, ... into the ring (mem_moco.py:17-27)
-//   tail           : exact 64-bit fixed-point loss accumulator + hit counters + a ticket; the last CTA converts, advances the
-//                    device-resident ring pointer and re-arms the control block
-// control block words: [0] ticket, [2..3] loss accumulator, [4] top-1, [5] top-5, [8] barrier arrivals, [9] barrier generation
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int FZ_CHUNK = 40;           // gradient partials per row a thread keeps in flight (2 groups x 40 = 80 splits per pass)
-
-__device__ __forceinline__ void grid_barrier_256(unsigned int* ctl, unsigned int ncta)
-{
-    __threadfence();                                   // this thread's partial-result stores are visible device-wide
-    ptx::named_barrier_sync(1, 256);
-    if (threadIdx.x == 0) {
-        volatile unsigned int* gen = ctl + 9;
-        const unsigned int my_gen = *gen;
-        __threadfence();
-        if (atomicAdd(ctl + 8, 1u) == ncta - 1) {
-            ctl[8] = 0u;
-            __threadfence();
-            atomicAdd(ctl + 9, 1u);                    // release everybody
-        } else {
-            unsigned int spins = 0;
-            while (*gen == my_gen) {
-                __nanosleep(64);
-                if (++spins > (1u << 24)) { asm volatile("trap;"); }     // a broken barrier fails loudly instead of hanging
-            }
-        }
-        __threadfence();
-    }
-    ptx::named_barrier_sync(1, 256);
-}
-
-__device__ void fused_finalize(const FinalizeParams& F, float* scratch, const TcDebug& dbg)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;       // tid < 256
-    const unsigned int ncta = gridDim.x * gridDim.y;
-    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-    grid_barrier_256(F.counter, ncta);
-    if (tid == 0) tc_stamp(dbg, 13);
-
-    float* w_s = scratch;                         // [2][FIN_MAXS] split weights exp(part_max - lse)
-    constexpr int FIN_MAXS = 160;
-    float* colsum = w_s + 2 * FIN_MAXS;           // [2 rows][2 groups][128]
-    float* rstat = colsum + 2 * 2 * 128;          // [2 rows][lse, pos]
-    const int ns = F.nsplit, grp = tid >> 7, col = tid & 127;
-    const size_t stride = (size_t)F.Bpad * TC_D;
-    const float scale = F.inv_T / (float)F.B;
-
-    for (int r0 = cta; r0 < F.B; r0 += 2 * ncta) {
-        const int rows[2] = {r0, r0 + (int)ncta};
-        const bool has_b = rows[1] < F.B;
-        // ---- loads first: split statistics (warp 0 -> row a, warp 1 -> row b), then the gradient partials of both rows
-        float st_m[5], st_s[5]; int st_c[5];
-        const int my_row = (warp == 0) ? rows[0] : rows[1];
-        const bool stat_warp = (warp == 0) || (warp == 1 && has_b);
-        if (stat_warp) {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int sp = lane + 32 * i;
-                const size_t o = (size_t)(sp < ns ? sp : 0) * F.Bpad + my_row;
-                st_m[i] = (sp < ns) ? __ldcg(F.part_max + o) : -INFINITY;
-                st_s[i] = (sp < ns) ? __ldcg(F.part_sum + o) : 0.f;
-                st_c[i] = (sp < ns) ? __ldcg(F.part_cnt + o) : 0;
-            }
-        }
-        float va[FZ_CHUNK], vb[FZ_CHUNK];
-        {
-            const float* sa = F.part_acc + (size_t)rows[0] * TC_D + col;
-            const float* sb = F.part_acc + (size_t)(has_b ? rows[1] : rows[0]) * TC_D + col;
-#pragma unroll
-            for (int i = 0; i < FZ_CHUNK; ++i) {
-                const int sp = grp + 2 * i;
-                va[i] = (sp < ns) ? __ldcg(sa + sp * stride) : 0.f;
-                vb[i] = (sp < ns && has_b) ? __ldcg(sb + sp * stride) : 0.f;
-            }
-        }
-        if (stat_warp) {
-            const int w = warp;                                            // row slot
-            const float pos = F.pos[my_row];
-            float m = -INFINITY, part = 0.f;
-            int cnt = 0;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) m = fmaxf(m, st_m[i]);
-            m = fmaxf(warp_max(m), pos);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int sp = lane + 32 * i;
-                const float e = (st_m[i] == -INFINITY) ? 0.f : __expf(st_m[i] - m);
-                if (sp < ns) w_s[w * FIN_MAXS + sp] = e;
-                part += st_s[i] * e;
-                cnt += st_c[i];
-            }
-            const float S = warp_sum(part) + __expf(pos - m);
-            cnt = warp_sum_i(cnt);
-            const float lse = m + logf(S);
-            const float corr = __expf(m - lse);
-            for (int sp = lane; sp < ns; sp += 32) w_s[w * FIN_MAXS + sp] *= corr;
-            if (lane == 0) {
-                F.lse[my_row] = lse;
-                F.loss_rows[my_row] = lse - pos;
-                if (F.rank_gt) F.rank_gt[my_row] = cnt;
-                rstat[2 * w] = lse; rstat[2 * w + 1] = pos;
-                // exact, order-independent accumulators (see infonce_finalize_kernel)
-                unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(F.counter + 2);
-                atomicAdd(acc64, (unsigned long long)__double2ll_rn((double)(lse - pos) * 68719476736.0));
-                if (cnt < 1) atomicAdd(F.counter + 4, 1u);
-                if (cnt < 5) atomicAdd(F.counter + 5, 1u);
-            }
-        }
-        ptx::named_barrier_sync(1, 256);
-        // ---- fixed-order accumulation: each group over its interleaved splits, then group 0 + group 1
-        {
-            float aa = 0.f, ab = 0.f;
-#pragma unroll
-            for (int i = 0; i < FZ_CHUNK; ++i) {
-                const int sp = grp + 2 * i;
-                if (sp < ns) { aa = fmaf(w_s[sp], va[i], aa); ab = fmaf(w_s[FIN_MAXS + sp], vb[i], ab); }
-            }
-            for (int base = 2 * FZ_CHUNK; base < ns; base += 2 * FZ_CHUNK) {       // more than 80 splits (B <= 128): second pass
-                const float* sa = F.part_acc + (size_t)rows[0] * TC_D + col;
-                const float* sb = F.part_acc + (size_t)(has_b ? rows[1] : rows[0]) * TC_D + col;
-#pragma unroll
-                for (int i = 0; i < FZ_CHUNK; ++i) {
-                    const int sp = base + grp + 2 * i;
-                    va[i] = (sp < ns) ? __ldcg(sa + sp * stride) : 0.f;
-                    vb[i] = (sp < ns && has_b) ? __ldcg(sb + sp * stride) : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < FZ_CHUNK; ++i) {
-                    const int sp = base + grp + 2 * i;
-                    if (sp < ns) { aa = fmaf(w_s[sp], va[i], aa); ab = fmaf(w_s[FIN_MAXS + sp], vb[i], ab); }
-                }
-            }
-            colsum[(0 * 2 + grp) * 128 + col] = aa;
-            colsum[(1 * 2 + grp) * 128 + col] = ab;
-        }
-        ptx::named_barrier_sync(1, 256);
-        {
-            // 256 threads = 2 rows x 128 columns
-            const int w = tid >> 7;
-            const int row = rows[w];
-            if (w == 0 || has_b) {
-                const float lse = rstat[2 * w], pos = rstat[2 * w + 1];
-                const float t = colsum[(w * 2 + 0) * 128 + col] + colsum[(w * 2 + 1) * 128 + col];
-                F.dq[(size_t)row * TC_D + col] = scale * fmaf(__expf(pos - lse) - 1.f, F.k[(size_t)row * TC_D + col], t);
-            }
-        }
-        ptx::named_barrier_sync(1, 256);
-    }
-
-    // ---- enqueue: this CTA's share of the key rows (the grid barrier above ordered it after every read of the queue)
-    long long index = 0;
-    if (F.enq_queue != nullptr) {
-        index = F.enq_state ? *reinterpret_cast<volatile long long*>(F.enq_state) : F.enq_index;
-        const int rpp = 256 / 32;                                         // 8 key rows per pass, one warp (32 x float4) each
-        for (int r = cta * rpp + warp; r < F.enq_N; r += ncta * rpp) {
-            long long slot = index + r;
-            if (slot >= F.enq_K) slot -= F.enq_K;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(F.enq_keys + (size_t)r * TC_D) + lane);
-            if (F.enq_dtype == GCA_F32) {
-                reinterpret_cast<float4*>(F.enq_queue)[slot * 32 + lane] = v;
-            } else {
-                uint2 pk;
-                pk.x = ptx::pack_bf16(v.x, v.y);
-                pk.y = ptx::pack_bf16(v.z, v.w);
-                reinterpret_cast<uint2*>(F.enq_queue)[slot * 32 + lane] = pk;
-            }
-        }
-    }
-    // ---- tail: one ticket per CTA
-    __threadfence();
-    ptx::named_barrier_sync(1, 256);
-    if (tid == 0) {
-        if (atomicAdd(F.counter, 1u) == ncta - 1) {
-            __threadfence();
-            unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(F.counter + 2);
-            const long long tot = (long long)atomicAdd(acc64, 0ull);
-            if (F.loss_mean) *F.loss_mean = (float)((double)tot / 68719476736.0 / (double)F.B);
-            if (F.top_hits) { F.top_hits[0] = (int)atomicAdd(F.counter + 4, 0u); F.top_hits[1] = (int)atomicAdd(F.counter + 5, 0u); }
-            if (F.enq_queue != nullptr && F.enq_state) {
-                long long nx = index + F.enq_N;
-                if (nx >= F.enq_K) nx -= F.enq_K;
-                F.enq_state[0] = nx;
-            }
-            F.counter[0] = 0u; F.counter[2] = 0u; F.counter[3] = 0u; F.counter[4] = 0u; F.counter[5] = 0u;
-        }
-        tc_stamp(dbg, 14);
-    }
-}
-
-// kFuse: the split partials are merged by this same launch (grid barrier, then every CTA finalizes a few query rows and
-// enqueues a few key rows) instead of by a second kernel -- see fused_finalize() below.
-template <bool kWantAcc, bool kFixedMax, bool kFuse>
+template <bool kWantAcc, bool kFixedMax>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap qmap,
-                  const InfoNceStreamParams P, const TcDebug dbg, const FinalizeParams F)
+                  const InfoNceStreamParams P, const TcDebug dbg)
 {
     using namespace ptx;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -373,114 +171,6 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < TC_SUB; ++j) if (j >= nvalid) sv[j] = -INFINITY;   // TMA zero-filled rows past K
             }
-#if GCA_TC_FUSED_SWEEP
-            // EXPERIMENTAL (off by default, not yet measured): one sweep computes p with the row max of the PREVIOUS steps and
-            // tracks this step's row max alongside, so the max / count / exp work shares one instruction stream (more ALU work
-            // between consecutive MUFU.EX2) instead of a separate, serialised max pass.  If the new max exceeds the old one by
-            // more than the lazy-rescale threshold in some row, the step is redone with the new max (rare after the first
-            // few steps).  The first step of a CTA (no previous max) and fixed-max mode take the two-pass path below.
-            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-            float cf0 = 0.f, cf1 = 0.f, cf2 = 0.f, cf3 = 0.f;
-            uint32_t pk[32];
-            const bool one_pass = !kFixedMax && v > 0 && !__any_sync(0xffffffffu, m_run == -INFINITY);
-            if (one_pass) {
-                float tm0 = -INFINITY, tm1 = -INFINITY, tm2 = -INFINITY, tm3 = -INFINITY;
-                float neg_m = -m_run;
-#pragma unroll
-                for (int j = 0; j < TC_SUB; j += 4) {
-                    cf0 += (sv[j] > pos_dot) ? 1.f : 0.f;
-                    cf1 += (sv[j + 1] > pos_dot) ? 1.f : 0.f;
-                    cf2 += (sv[j + 2] > pos_dot) ? 1.f : 0.f;
-                    cf3 += (sv[j + 3] > pos_dot) ? 1.f : 0.f;
-                    const float p0 = ex2(fmaf(sv[j], c2, neg_m)), p1 = ex2(fmaf(sv[j + 1], c2, neg_m));
-                    const float p2 = ex2(fmaf(sv[j + 2], c2, neg_m)), p3 = ex2(fmaf(sv[j + 3], c2, neg_m));
-                    if ((j & 4) == 0) { tm0 = max3(tm0, sv[j], sv[j + 1]); tm1 = max3(tm1, sv[j + 2], sv[j + 3]); }
-                    else              { tm2 = max3(tm2, sv[j], sv[j + 1]); tm3 = max3(tm3, sv[j + 2], sv[j + 3]); }
-                    rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-                    pk[j >> 1] = pack_bf16(p0, p1);
-                    pk[(j >> 1) + 1] = pack_bf16(p2, p3);
-                }
-                const float xm = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3)) * c2;
-                const bool need = xm > m_run + TC_RESCALE_LOG2;
-                if (__any_sync(0xffffffffu, need)) {                        // rare: rescale, then redo the step with the new max
-                    const float m_new = need ? xm : m_run;
-                    const float sc = ex2(m_run - m_new);
-                    s_run *= sc;
-                    m_run = m_new;
-                    if (kWantAcc) {
-                        mbar_wait(&bar->o_done[g], (v - 1) & 1);
-                        tc_fence_after();
-#pragma unroll
-                        for (int ch = 0; ch < 4; ++ch) {
-                            uint32_t t[32];
-                            tmem_ld32(o_addr + 32 * ch, t);
-                            tc_wait_ld();
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) t[j] = __float_as_uint(__uint_as_float(t[j]) * sc);
-                            tmem_st32(o_addr + 32 * ch, t);
-                        }
-                        tc_wait_st();
-                    }
-                    neg_m = -m_run;
-                    rs0 = rs1 = rs2 = rs3 = 0.f;
-#pragma unroll
-                    for (int j = 0; j < TC_SUB; j += 4) {
-                        const float p0 = ex2(fmaf(sv[j], c2, neg_m)), p1 = ex2(fmaf(sv[j + 1], c2, neg_m));
-                        const float p2 = ex2(fmaf(sv[j + 2], c2, neg_m)), p3 = ex2(fmaf(sv[j + 3], c2, neg_m));
-                        rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-                        pk[j >> 1] = pack_bf16(p0, p1);
-                        pk[(j >> 1) + 1] = pack_bf16(p2, p3);
-                    }
-                }
-            } else {
-                if (!kFixedMax) {
-                    float tm0 = -INFINITY, tm1 = -INFINITY, tm2 = -INFINITY, tm3 = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < TC_SUB; j += 8) {
-                        tm0 = max3(tm0, sv[j], sv[j + 1]);
-                        tm1 = max3(tm1, sv[j + 2], sv[j + 3]);
-                        tm2 = max3(tm2, sv[j + 4], sv[j + 5]);
-                        tm3 = max3(tm3, sv[j + 6], sv[j + 7]);
-                    }
-                    const float xm = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3)) * c2;
-                    const bool need = xm > m_run + TC_RESCALE_LOG2;
-                    if (__any_sync(0xffffffffu, need)) {
-                        const float m_new = need ? xm : m_run;
-                        const float sc = (m_run == -INFINITY) ? 0.f : ex2(m_run - m_new);
-                        s_run *= sc;
-                        m_run = m_new;
-                        if (kWantAcc && v > 0) {
-                            mbar_wait(&bar->o_done[g], (v - 1) & 1);
-                            tc_fence_after();
-#pragma unroll
-                            for (int ch = 0; ch < 4; ++ch) {
-                                uint32_t t[32];
-                                tmem_ld32(o_addr + 32 * ch, t);
-                                tc_wait_ld();
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) t[j] = __float_as_uint(__uint_as_float(t[j]) * sc);
-                                tmem_st32(o_addr + 32 * ch, t);
-                            }
-                            tc_wait_st();
-                        }
-                    }
-                }
-                if (v == 0) { if (g == 0) named_barrier_arrive(2, 256); }
-                const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
-#pragma unroll
-                for (int j = 0; j < TC_SUB; j += 4) {
-                    cf0 += (sv[j] > pos_dot) ? 1.f : 0.f;
-                    cf1 += (sv[j + 1] > pos_dot) ? 1.f : 0.f;
-                    cf2 += (sv[j + 2] > pos_dot) ? 1.f : 0.f;
-                    cf3 += (sv[j + 3] > pos_dot) ? 1.f : 0.f;
-                    const float p0 = ex2(fmaf(sv[j], c2, neg_m)), p1 = ex2(fmaf(sv[j + 1], c2, neg_m));
-                    const float p2 = ex2(fmaf(sv[j + 2], c2, neg_m)), p3 = ex2(fmaf(sv[j + 3], c2, neg_m));
-                    rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-                    pk[j >> 1] = pack_bf16(p0, p1);
-                    pk[(j >> 1) + 1] = pack_bf16(p2, p3);
-                }
-            }
-#else
             bool count_step = true;
             if (!kFixedMax) {
                 // row max with four independent chains
@@ -552,7 +242,6 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     pk[(j >> 1) + 1] = pack_bf16(p2, p3);
                 }
             }
-#endif
             cnt += (int)((cf0 + cf1) + (cf2 + cf3));
             s_run += (rs0 + rs1) + (rs2 + rs3);
             if (threadIdx.x == 0 && v == 2) tc_cstamp(dbg, 20);
@@ -625,10 +314,6 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 const int r = warp * 16 + rr;
                 if (r < nrows) gdst[r * 32 + lane] = *reinterpret_cast<const float4*>(ost + (size_t)r * TC_OST_STRIDE + lane * 4);
             }
-        }
-        if constexpr (kFuse) {
-            if (threadIdx.x == 0) tc_stamp(dbg, 12);
-            fused_finalize(F, reinterpret_cast<float*>(qtile), dbg);     // scratch: the q tile region (dead since the last S GEMM)
         }
     } else if (warp == TC_WARP_TMA) {
         // =============================================================== TMA producer
@@ -872,7 +557,7 @@ unsigned long long* debug_timebuf()
 
 static TcDebug tc_debug_knobs() { return TcDebug{debug_timebuf()}; }
 
-int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_t st, const FinalizeParams* fuse)
+int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_t st)
 {
     InfoNceStreamParams P = P_;
     P.q_scale = P.inv_T * 1.4426950408889634f;        // every kernel of this family works on log2-domain S tiles
@@ -888,7 +573,7 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
     if (P.normalize && (P.xchg.mailboxes || P.skip_prep))
         return set_err(GCA_ERR_UNSUPPORTED, "projection-tail fusion cannot be combined with the peer exchange or skip_prep");
     // loss + gradient in one sweep (the product path): second-generation stream kernel (infonce_tcx.cu)
-    const bool use_tcx = P.part_acc != nullptr && !fixed_max && !fuse && P.logits_out == nullptr && infonce_tcx_enabled();
+    const bool use_tcx = P.part_acc != nullptr && !fixed_max && P.logits_out == nullptr && infonce_tcx_enabled();
     if (!P.skip_prep) {
         const int nprep = (P.Bpad + 7) / 8;
         const int npush = P.xchg.mailboxes ? P.xchg.W * XCHG_SLICES : 0;
@@ -913,44 +598,23 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
     dim3 grid(P.nsplit, P.Bpad / TC_BM);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = st;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     int na = 0;
     if (pdl_enabled()) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;    // PDL: overlap this kernel's setup with the prep kernel
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
     }
-    FinalizeParams F{};
-    if (fuse) {
-        F = *fuse;
-        attr[na].id = cudaLaunchAttributeCooperative;                       // the fused finalize uses a grid-wide barrier
-        attr[na].val.cooperative = 1;
-        ++na;
-    }
     cfg.attrs = attr; cfg.numAttrs = na;
-#define GCA_TC_LAUNCH(ACC, FIX, FUSE) do { \
-        auto kern = infonce_tc_kernel<ACC, FIX, FUSE>; \
+#define GCA_TC_LAUNCH(ACC, FIX) do { \
+        auto kern = infonce_tc_kernel<ACC, FIX>; \
         GCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES)); \
-        GCA_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, qmap, P, dbg, F)); } while (0)
-    if (fuse) { GCA_TC_LAUNCH(true, false, true); }
-    else if (want_acc) { if (fixed_max) GCA_TC_LAUNCH(true, true, false); else GCA_TC_LAUNCH(true, false, false); }
-    else               { if (fixed_max) GCA_TC_LAUNCH(false, true, false); else GCA_TC_LAUNCH(false, false, false); }
+        GCA_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, qmap, P, dbg)); } while (0)
+    if (want_acc) { if (fixed_max) GCA_TC_LAUNCH(true, true); else GCA_TC_LAUNCH(true, false); }
+    else          { if (fixed_max) GCA_TC_LAUNCH(false, true); else GCA_TC_LAUNCH(false, false); }
 #undef GCA_TC_LAUNCH
     GCA_LAUNCH_CHECK("infonce_tc_kernel");
     return GCA_OK;
-}
-
-// Single-launch variant (stream + grid barrier + finalize + enqueue in one cooperative kernel).  Measured on B200 (r01):
-// 35.3 us/step against 30.7 us for prep + stream + finalize -- the grid barrier costs ~3.2 us (a kernel boundary ~1 us) and
-// two rows per CTA finalize no faster than the 256-CTA finalize kernel -- so it is OFF unless GCA_FUSE=1 (kept for round 2).
-bool infonce_tc_can_fuse(int B, long long K)
-{
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("GCA_FUSE"); on = (e && e[0] == '1') ? 1 : 0; }
-    if (!on) return false;
-    const int ns = infonce_tc_nsplit(B, K);
-    const int nblk = infonce_bpad(B) / TC_BM;
-    return ns <= 160 && ns * nblk <= sm_count_cached();
 }
 
 }  // namespace gca

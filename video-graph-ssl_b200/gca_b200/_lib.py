@@ -6,6 +6,7 @@ and if no CUDA device is present the library's compute entry points return GCA_E
 """
 import ctypes
 import os
+import threading
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -65,7 +66,7 @@ SIGNATURES = {
                                    c_void_p]),
     "gca_negcos_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gca_ema_chunk_bytes": (c_size_t, []),
-    "gca_ema_update": (c_int, [c_void_p, c_int, c_float, c_void_p]),
+    "gca_ema_update": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p]),
     "gca_keys_exchange_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gca_keys_exchange": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gca_moco_step_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
@@ -110,11 +111,31 @@ def check(fn_name, rc):
         raise GcaError(fn_name, rc, last_error())
 
 
+_pending = threading.local()          # device of the first CUDA tensor handed to ptr() since the last call()
+
+
 def ptr(t):
-    """Device pointer of a torch tensor (None -> NULL)."""
-    return None if t is None else c_void_p(t.data_ptr())
+    """Device pointer of a torch tensor (None -> NULL).  Remembers the tensor's CUDA device for the next `call`."""
+    if t is None:
+        return None
+    if t.is_cuda and getattr(_pending, "dev", None) is None:
+        _pending.dev = t.device.index
+    return c_void_p(t.data_ptr())
 
 
 def call(name, *args):
-    rc = getattr(load(), name)(*args)
+    """Invoke a library entry point and raise on a non-zero code.  The library sizes its launches for the CURRENT device
+    (SM count, workspace carve) and launches on it, so the call runs with the device of its tensor arguments current --
+    the arguments are built with `ptr()` right before the call, which is where the device is picked up."""
+    dev = getattr(_pending, "dev", None)
+    _pending.dev = None
+    fn = getattr(load(), name)
+    if dev is not None:
+        import torch
+        if torch.cuda.current_device() != dev:
+            with torch.cuda.device(dev):
+                rc = fn(*args)
+            check(name, rc)
+            return
+    rc = fn(*args)
     check(name, rc)

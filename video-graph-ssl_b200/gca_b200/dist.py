@@ -254,11 +254,16 @@ class ShuffleBN(object):
     the reference for the same generator state.
     """
 
-    def __init__(self, local_group=None, global_group=None, node_rank=0):
+    def __init__(self, local_group=None, global_group=None, node_rank=0, payload_dtype=None):
+        """payload_dtype: None -> the clips travel in their own dtype (bit-identical to the reference's gather + index);
+        torch.bfloat16 -> rows are rounded to bf16 for the NVLink hop and widened again on arrival (half the bytes of the
+        largest exchange of the step; the momentum encoder then sees bf16-rounded pixels -- opt-in, it changes bits)."""
         self.local_group = local_group if local_group is not None else dist.group.WORLD
         self.global_group = global_group if global_group is not None else dist.group.WORLD
         self.node_rank = node_rank
+        self.payload_dtype = payload_dtype
         self.last_shuffle_ids = None
+        self._side = None
 
     def exchange(self, x, shuffle_ids):
         """Rows `shuffle_ids[rank*bsz:(rank+1)*bsz]` of the (virtual) concatenation of every rank's x."""
@@ -268,10 +273,12 @@ class ShuffleBN(object):
         send_rows, send_counts, recv_counts, place = shuffle_plan(shuffle_ids, bsz, W, r)
         x2 = x.contiguous().view(bsz, -1)
         send = x2.index_select(0, send_rows.to(x.device))
-        recv = torch.empty_like(x2)
+        if self.payload_dtype is not None:
+            send = send.to(self.payload_dtype)
+        recv = torch.empty_like(send)
         dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=g)
         out = torch.empty_like(x2)
-        out.index_copy_(0, place.to(x.device), recv)
+        out.index_copy_(0, place.to(x.device), recv.to(x2.dtype))
         return out.view(x.shape)
 
     def __call__(self, x, model_ema):
@@ -279,11 +286,12 @@ class ShuffleBN(object):
         W, r = dist.get_world_size(g), dist.get_rank(g)
         bsz = x.shape[0]
         shuffle_ids = torch.randperm(bsz * W).to(x.device)                 # train...:208 (CPU generator, as upstream)
-        reverse_ids = torch.argsort(shuffle_ids)
         gg = self.global_group
         root = 0 if gg is dist.group.WORLD else dist.get_global_rank(gg, 0)
         dist.broadcast(shuffle_ids, root, group=gg)                         # rank 0's draw wins (train...:210-211)
-        dist.broadcast(reverse_ids, root, group=gg)
+        # ONE broadcast: the inverse permutation is a function of the permutation, so every rank sorts rank 0's ids itself
+        # (integer work, identical everywhere) instead of receiving rank 0's argsort in a second collective (train...:209, 211)
+        reverse_ids = torch.argsort(shuffle_ids)
         self.last_shuffle_ids = shuffle_ids
         with torch.no_grad():
             this_x = self.exchange(x, shuffle_ids)
@@ -291,3 +299,32 @@ class ShuffleBN(object):
         all_k = _all_gather_rows(k.contiguous(), self.global_group)
         node_k = all_k[self.node_rank * W * bsz:(self.node_rank + 1) * W * bsz]
         return node_k[reverse_ids[r * bsz:(r + 1) * bsz]], all_k
+
+    def launch(self, x, model_ema):
+        """The whole key branch -- clip exchange, momentum-encoder forward, key gather, un-shuffle -- on a side CUDA stream,
+        so that it overlaps the caller's `model(x1)` on the current stream: nothing in it depends on the online encoder
+        (train...:407-410 run the two branches back to back).  Returns a handle; `handle.wait()` orders the current stream
+        after the branch and gives `(k, all_k)`."""
+        dev = x.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            k, all_k = self(x, model_ema)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        x.record_stream(self._side)
+        return _PendingKeys(k, all_k, done, dev)
+
+
+class _PendingKeys(object):
+    def __init__(self, k, all_k, done, dev):
+        self.k, self.all_k, self.done, self.dev = k, all_k, done, dev
+
+    def wait(self):
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.done)
+        self.k.record_stream(cur)
+        self.all_k.record_stream(cur)
+        return self.k, self.all_k

@@ -54,7 +54,8 @@ class MomentumUpdater(object):
         self._keep = pairs                                            # keeps the storages (and their addresses) alive
 
     def step(self, m):
-        _lib.call("gca_ema_update", ptr(self.table), self.nchunks, float(m),
+        # alpha = 1 - m is formed in double and rounded once, like the reference's `add_(p1, alpha=1 - m)` (train...:179)
+        _lib.call("gca_ema_update", ptr(self.table), self.nchunks, float(m), float(1.0 - float(m)),
                   ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
 
 

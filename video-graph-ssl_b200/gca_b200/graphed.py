@@ -176,6 +176,22 @@ class GraphedReplicaStep(GraphedMoCoStep):
         self.keys_ready = torch.cuda.Event()
         self.exchange = exchange
         self.fuse_exchange = bool(fuse_exchange) and exchange is not None
+        # a peer that misses the exchange timeout leaves this rank's queue un-updated (the kernel skips the enqueue and
+        # raises a sticky device flag): poll it every `check_every` replays (one small device->host read) and in check()
+        self.check_every = 256
+        self._replays = 0
+
+    def check(self):
+        """Raise if a peer ever missed the key-exchange timeout (the replicas' queues have diverged since)."""
+        if self.exchange is not None:
+            self.exchange.check()
+
+    def step(self, q=None, k=None, all_k=None):
+        loss = super(GraphedReplicaStep, self).step(q, k, all_k)
+        self._replays += 1
+        if self.exchange is not None and self.exchange.timeout_ms > 0 and self._replays % self.check_every == 0:
+            self.exchange.check()
+        return loss
 
     def _enqueue_work(self, stream):
         import torch.distributed as dist
