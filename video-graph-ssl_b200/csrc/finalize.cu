@@ -132,7 +132,8 @@ infonce_finalize_kernel(const FinalizeParams F)
     float* out = (kMode == FIN_SHARD) ? F.out_acc : F.dq;
     const bool want_acc = (out != nullptr && F.part_acc != nullptr);
     const int grp = tid / FIN_COLS, col = tid % FIN_COLS;
-    const size_t stride = (size_t)F.Bpad * F.d;
+    const size_t stride = F.split_stride ? (size_t)F.split_stride : (size_t)F.Bpad * F.d;     // floats between splits (acc)
+    const size_t sstride = F.split_stride ? (size_t)F.split_stride : (size_t)F.Bpad;          // floats between splits (stats)
 
     // Loads first, arithmetic later: warp 0 puts the split statistics of its row in flight (they head the memory queue),
     // then every thread puts its share of the gradient partials in flight (raw values: the split weights are not needed to
@@ -147,7 +148,7 @@ infonce_finalize_kernel(const FinalizeParams F)
 #pragma unroll
         for (int i = 0; i < FIN_STAT; ++i) {
             const int sp = lane + 32 * i;
-            const size_t o = (size_t)(sp < ns ? sp : 0) * F.Bpad + b;
+            const size_t o = (size_t)(sp < ns ? sp : 0) * sstride + b;
             st_m[i] = (sp < ns) ? __ldcg(F.part_max + o) : -INFINITY;
             st_s[i] = (sp < ns) ? __ldcg(F.part_sum + o) : 0.f;
             st_c[i] = (sp < ns) ? __ldcg(F.part_cnt + o) : 0;
@@ -198,11 +199,11 @@ infonce_finalize_kernel(const FinalizeParams F)
                     cnt += st_c[i];
                 }
             } else {                                           // many splits: two dependent passes over the statistics
-                for (int sp = lane; sp < ns; sp += 32) m = fmaxf(m, F.part_max[(size_t)sp * F.Bpad + b]);
+                for (int sp = lane; sp < ns; sp += 32) m = fmaxf(m, F.part_max[(size_t)sp * sstride + b]);
                 m = warp_max(m);
                 if (kMode == FIN_FULL) m = fmaxf(m, pos);
                 for (int sp = lane; sp < ns; sp += 32) {
-                    const size_t o = (size_t)sp * F.Bpad + b;
+                    const size_t o = (size_t)sp * sstride + b;
                     const float pm = F.part_max[o];
                     const float e = (pm == -INFINITY) ? 0.f : __expf(pm - m);
                     w_s[sp] = e;

@@ -67,6 +67,11 @@ struct FinalizeParams {
     PeerXchg xchg;                 // enq_keys == NULL and xchg on: the rows come from this rank's mailbox (all W*B of them)
     unsigned long long* timebuf;   // bring-up only (tools/tc_timeline.py): entry / exit time stamps
     const float* zq; const float* inv_nq;   // projection-tail fusion: dq is pushed back through q = zq / ||zq|| (NULL = off)
+    // K-sharded step over peer memory (gca_infonce_shard_merge_peer): the "splits" are the W ranks' partials of this rank's
+    // rows, sitting in this rank's mailbox; push CTAs at the head of the launch deliver the local partials to their owners
+    PeerXchg merge_xchg;           // off if mailboxes == nullptr
+    const float* push_acc; const float* push_max; const float* push_sum; const int* push_cnt;   // local partials [W * B, ...]
+    long long split_stride;        // floats between two splits of part_max / part_sum / part_cnt / part_acc (0 = dense layout)
     int range_checked;             // the stream kernel reports out-of-range logits in control word 6 (tcgen05 family)
     int pk_nb, pk_frac;            // set by infonce_finalize_launch: packed loss/hits/ticket word (0 = unpacked path)
 };
