@@ -23,7 +23,9 @@ def main():
     from gca_b200.dist import ShardedRGBMoCo
     from gca_b200.graphed import GraphedShardedStep
     from gca_b200.memory.losses import NCESoftmaxLoss
+    from gca_b200.peer import PeerShardLink
     K, d, T, Bl = 8192 * world, 128, 0.07, 128
+    link = PeerShardLink(Bl, d, device=dev)            # one mailbox for every peer-memory step of this process
     for qdt in ("bf16", "fp32"):
         torch.manual_seed(3)
         a = ShardedRGBMoCo(d, K=K, T=T, queue_dtype=qdt, device=dev)
@@ -33,6 +35,12 @@ def main():
         a.index = b.index = K - 3 * Bl * world + 64                  # the third step wraps around the ring
         gs = GraphedShardedStep(b, Bl).capture()
         assert torch.equal(a.memory, b.memory) and b.index == a.index   # capture leaves queue and pointer untouched
+        # third copy: the same step with the q|k gather and the cross-rank merge over NVLink peer memory (no NCCL call)
+        torch.manual_seed(3)
+        c = ShardedRGBMoCo(d, K=K, T=T, queue_dtype=qdt, device=dev)
+        c.index = a.index
+        gp = GraphedShardedStep(c, Bl, link=link).capture()
+        assert torch.equal(a.memory, c.memory) and c.index == a.index
         crit = NCESoftmaxLoss()
         gen = torch.Generator().manual_seed(11 + rank)
         for step in range(4):
@@ -50,6 +58,18 @@ def main():
             assert torch.equal(out.rank, gs.rank) and torch.equal(out.lse, gs.lse), step
             assert a.index == b.index and int(gs.state[0]) == b.index, step
             assert torch.equal(a.memory, b.memory), step
+            # peer-memory variant: same kernels for the sweep, another (fixed) association order in the cross-rank merge
+            lc = gp.step(q, k)
+            torch.cuda.synchronize()
+            link.check()
+            assert abs(float(lc) - float(lb)) <= 2e-6 * abs(float(lb)), (step, float(lc), float(lb))
+            assert float((gp.dq - gs.dq).abs().max()) <= 2e-5 * float(gs.dq.abs().max()), step
+            assert float((gp.lse - gs.lse).abs().max()) <= 1e-5, step
+            assert torch.equal(gp.rank, gs.rank), step
+            assert c.index == b.index and int(gp.state[0]) == b.index, step
+            assert torch.equal(c.memory, b.memory), step
+            hits_ref = [int((gs.rank < 1).sum()), int((gs.rank < 5).sum())]
+            assert gp.hits.tolist() == hits_ref, (step, gp.hits.tolist(), hits_ref)
             # ... and against the ORACLE: the reference step of this rank's rows on the full (replicated) queue
             import oracle
             if qdt == "bf16":
@@ -66,12 +86,15 @@ def main():
             pos = ((q.cpu().double() * k.cpu().double()).sum(1) / T)[:, None]   # the kernels take the positive from the fp32 q.k
             ok = (neg - pos).abs().min(1).values > 3e-4
             assert torch.equal(gs.rank.cpu().long()[ok], (neg > pos).sum(1)[ok]), step
+            assert abs(float(lc) - float(o["loss"])) <= ltol * abs(float(o["loss"])), (step, float(lc), float(o["loss"]))
+            err = float((gp.dq.cpu().double() - o["dq"]).abs().max() / o["dq"].abs().max())
+            assert err <= gtol, (step, err)
         assert gs.launches_per_step >= 5
-    assert gs.launches_per_step >= 5
+    assert gp.launches_per_step == 4, gp.launches_per_step
     dist.barrier()
     torch.cuda.synchronize()
     if rank == 0:
-        print("SHARDED_GRAPH_OK world=%d launches_per_step=%d" % (world, gs.launches_per_step), flush=True)
+        print("SHARDED_GRAPH_OK world=%d launches_per_step=%d peer_launches_per_step=%d" % (world, gs.launches_per_step, gp.launches_per_step), flush=True)
     os._exit(0)
 
 

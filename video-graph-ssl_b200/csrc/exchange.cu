@@ -22,7 +22,7 @@ namespace gca {
 constexpr int XCHG_THREADS = 512;
 
 __global__ void __launch_bounds__(XCHG_THREADS)
-keys_exchange_kernel(const float4* __restrict__ keys_local, const PeerXchg X, float4* __restrict__ all_k)
+keys_exchange_kernel(const float4* __restrict__ keys_local, const PeerXchg X, float4* __restrict__ all_k, const int parts)
 {
     const int p = blockIdx.x;                         // peer this CTA talks to
     const int c = blockIdx.y;                         // slice of the key block
@@ -35,8 +35,17 @@ keys_exchange_kernel(const float4* __restrict__ keys_local, const PeerXchg X, fl
         const int per = (X.n4 + XCHG_SLICES - 1) / XCHG_SLICES;
         const int lo = c * per, hi = min(X.n4, lo + per);
         const float4* src = xchg_slot(X.mailboxes[X.rank], X, (int)(step & 1ull), p);
-        float4* out = all_k + (size_t)p * X.n4;
-        for (int i = lo + threadIdx.x; i < hi; i += XCHG_THREADS) out[i] = ld_cg_f4(src + i);
+        if (parts <= 1) {
+            float4* out = all_k + (size_t)p * X.n4;
+            for (int i = lo + threadIdx.x; i < hi; i += XCHG_THREADS) out[i] = ld_cg_f4(src + i);
+        } else {
+            // the local block is [parts][n4 / parts] (e.g. q rows | k rows); the output is part-major: [parts][W][n4 / parts]
+            const int pn = X.n4 / parts;
+            for (int i = lo + threadIdx.x; i < hi; i += XCHG_THREADS) {
+                const int h = i / pn, j = i - h * pn;
+                all_k[((size_t)h * X.W + p) * pn + j] = ld_cg_f4(src + i);
+            }
+        }
     }
     // step counter: the last CTA of this launch advances it (every CTA has read it before taking a ticket)
     __shared__ int last;
@@ -64,6 +73,24 @@ extern "C" size_t gca_keys_exchange_bytes(int B, int d, int W)
     return gca::align_up(slots + flags, 256);
 }
 
+namespace gca {
+// rows of every rank gathered through the mailboxes; parts > 1: the local block is [parts][B / parts, d] and the output is
+// part-major, [parts][W][B / parts, d] (the q | k gather of the K-sharded step)
+int keys_exchange_launch(const float* keys_local, int B, int d, int W, int rank, void* const* mailboxes, float* all_k,
+                         long long* xstate, int timeout_ms, int parts, cudaStream_t st)
+{
+    PeerXchg X{};
+    X.mailboxes = (char* const*)mailboxes; X.W = W; X.rank = rank; X.n4 = B * d / 4;
+    X.xstate = (unsigned long long*)xstate;
+    X.timeout_ns = timeout_ms > 0 ? (unsigned long long)timeout_ms * 1000000ull : 0ull;
+    dim3 grid(W, XCHG_SLICES);
+    keys_exchange_kernel<<<grid, XCHG_THREADS, 0, st>>>((const float4*)keys_local, X, (float4*)all_k, parts);
+    GCA_LAUNCH_CHECK("keys_exchange_kernel");
+    count_launch(1);
+    return GCA_OK;
+}
+}  // namespace gca
+
 extern "C" int gca_keys_exchange(const float* keys_local, int B, int d, int W, int rank, void* const* mailboxes,
                                  float* all_k, long long* xstate, int timeout_ms, void* stream)
 {
@@ -71,13 +98,5 @@ extern "C" int gca_keys_exchange(const float* keys_local, int B, int d, int W, i
     GCA_CHECK_ARG(keys_local && mailboxes && all_k && xstate, "gca_keys_exchange: null pointer");
     GCA_CHECK_ARG(B > 0 && d > 0 && d % 4 == 0, "gca_keys_exchange: need B > 0 and d %% 4 == 0 (B=%d d=%d)", B, d);
     GCA_CHECK_ARG(W >= 1 && W <= 64 && rank >= 0 && rank < W, "gca_keys_exchange: bad rank %d of %d", rank, W);
-    PeerXchg X{};
-    X.mailboxes = (char* const*)mailboxes; X.W = W; X.rank = rank; X.n4 = B * d / 4;
-    X.xstate = (unsigned long long*)xstate;
-    X.timeout_ns = timeout_ms > 0 ? (unsigned long long)timeout_ms * 1000000ull : 0ull;
-    dim3 grid(W, XCHG_SLICES);
-    keys_exchange_kernel<<<grid, XCHG_THREADS, 0, (cudaStream_t)stream>>>((const float4*)keys_local, X, (float4*)all_k);
-    GCA_LAUNCH_CHECK("keys_exchange_kernel");
-    count_launch(1);
-    return GCA_OK;
+    return keys_exchange_launch(keys_local, B, d, W, rank, mailboxes, all_k, xstate, timeout_ms, 1, (cudaStream_t)stream);
 }

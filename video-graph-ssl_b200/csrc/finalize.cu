@@ -69,6 +69,10 @@ __device__ __forceinline__ void enqueue_rows(const FinalizeParams& F, int blk, i
         const int row = (int)(i / d4), c4 = (int)(i - (long long)row * d4);
         long long slot = index + row;
         if (slot >= F.enq_K) slot -= F.enq_K;
+        if (F.enq_kend > 0) {                                 // K-sharded queue: this rank stores only the slots it owns
+            if (slot < F.enq_kbegin || slot >= F.enq_kend) continue;
+            slot -= F.enq_kbegin;
+        }
         const float4 v = peer ? ld_cg_f4(keys + i) : __ldg(keys + i);
         const long long off = slot * d4 + c4;
         if constexpr (sizeof(QT) == 4) {
@@ -120,7 +124,7 @@ infonce_finalize_kernel(const FinalizeParams F)
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         atomicMin(F.timebuf + 32 * 1000 + 0, t);
-        F.timebuf[32 * 400 + 4 * blockIdx.x] = t;
+        F.timebuf[32 * 400 + 4 * (blockIdx.x & 255)] = t;
     }
     if (kMode == FIN_FULL && (int)blockIdx.x >= F.B) {        // fused enqueue CTAs
         if (F.enq_dtype == GCA_F32) enqueue_rows<float>(F, blockIdx.x - F.B, gridDim.x - F.B);
@@ -128,12 +132,43 @@ infonce_finalize_kernel(const FinalizeParams F)
         return;
     }
     const int b = blockIdx.x;
-    const int ns = F.nsplit;
-    float* out = (kMode == FIN_SHARD) ? F.out_acc : F.dq;
-    const bool want_acc = (out != nullptr && F.part_acc != nullptr);
+    int ns = F.nsplit;
     const int grp = tid / FIN_COLS, col = tid % FIN_COLS;
-    const size_t stride = F.split_stride ? (size_t)F.split_stride : (size_t)F.Bpad * F.d;     // floats between splits (acc)
-    const size_t sstride = F.split_stride ? (size_t)F.split_stride : (size_t)F.Bpad;          // floats between splits (stats)
+    size_t stride = (size_t)F.Bpad * F.d;                      // floats between two splits of the accumulator partials
+    size_t sstride = (size_t)F.Bpad;                           // ... of the statistics
+    const float* p_max = F.part_max; const float* p_sum = F.part_sum; const int* p_cnt = F.part_cnt; const float* p_acc = F.part_acc;
+    float* out_row = (kMode == FIN_SHARD) ? (F.out_acc ? F.out_acc + (size_t)b * F.d : nullptr) : (F.dq ? F.dq + (size_t)b * F.d : nullptr);
+    float* o_max = F.out_max ? F.out_max + b : nullptr; float* o_sum = F.out_sum ? F.out_sum + b : nullptr;
+    int* o_cnt = F.out_cnt ? F.out_cnt + b : nullptr;
+    // K-sharded step over peer memory (PeerMerge, gca_common.cuh)
+    const bool peer_push = (kMode == FIN_SHARD) && F.merge.mailboxes != nullptr;
+    const bool peer_merge = (kMode == FIN_FULL) && F.merge.mailboxes != nullptr && F.merge.wait != 0;
+    unsigned long long mstep = 0ull;
+    unsigned long long* push_counter = nullptr;
+    if (peer_push || peer_merge) {
+        const PeerMerge& M = F.merge;
+        mstep = *reinterpret_cast<volatile unsigned long long*>(M.mstate);
+        const int par = (int)(mstep & 1ull);
+        if (peer_push) {
+            // row b belongs to rank b / Bl: its merged partial (relative to its max) is stored straight into the owner's mailbox
+            const int owner = b / M.Bl, lr = b - owner * M.Bl;
+            float* base = pm_slot(M.mailboxes[owner], M, par, M.rank);
+            out_row = F.part_acc ? base + (size_t)lr * M.d : nullptr;
+            o_max = base + (size_t)M.Bl * M.d + lr; o_sum = o_max + M.Bl; o_cnt = reinterpret_cast<int*>(o_sum + M.Bl);
+            push_counter = pm_counter(M.mailboxes[owner], M, par, M.rank);
+        } else {
+            // the W sources' partials of my row sit in my own mailbox: wait for all of their rows of this step
+            int ok = 1;
+            if (tid < M.W) ok = pm_wait(M, par, tid, ((mstep >> 1) + 1ull) * (unsigned long long)M.Bl) ? 1 : 0;
+            (void)__syncthreads_and(ok);                       // on a timeout mstate[2] is raised (sticky) and the row is garbage
+            const float* base = pm_slot(M.mailboxes[M.rank], M, par, 0);
+            p_acc = F.dq ? base : nullptr; p_max = base + (size_t)M.Bl * M.d; p_sum = p_max + M.Bl;
+            p_cnt = reinterpret_cast<const int*>(p_sum + M.Bl);
+            stride = sstride = pm_slot_floats(M);
+            ns = M.W;
+        }
+    }
+    const bool want_acc = (out_row != nullptr && p_acc != nullptr);
 
     // Loads first, arithmetic later: warp 0 puts the split statistics of its row in flight (they head the memory queue),
     // then every thread puts its share of the gradient partials in flight (raw values: the split weights are not needed to
@@ -149,16 +184,16 @@ infonce_finalize_kernel(const FinalizeParams F)
         for (int i = 0; i < FIN_STAT; ++i) {
             const int sp = lane + 32 * i;
             const size_t o = (size_t)(sp < ns ? sp : 0) * sstride + b;
-            st_m[i] = (sp < ns) ? __ldcg(F.part_max + o) : -INFINITY;
-            st_s[i] = (sp < ns) ? __ldcg(F.part_sum + o) : 0.f;
-            st_c[i] = (sp < ns) ? __ldcg(F.part_cnt + o) : 0;
+            st_m[i] = (sp < ns) ? __ldcg(p_max + o) : -INFINITY;
+            st_s[i] = (sp < ns) ? __ldcg(p_sum + o) : 0.f;
+            st_c[i] = (sp < ns) ? __ldcg(p_cnt + o) : 0;
         }
     }
     float v[kVec ? 1 : FIN_CHUNK];
     float4 v4[kVec ? FIN_VCH : 1];
     if constexpr (kVec) {
         if (want_acc) {
-            const float4* src4 = reinterpret_cast<const float4*>(F.part_acc + (size_t)b * FIN_COLS) + lane;
+            const float4* src4 = reinterpret_cast<const float4*>(p_acc + (size_t)b * FIN_COLS) + lane;
 #pragma unroll
             for (int i = 0; i < FIN_VCH; ++i) {
                 const int sp = warp + i * (FIN_THREADS / 32);
@@ -166,7 +201,7 @@ infonce_finalize_kernel(const FinalizeParams F)
             }
         }
     } else if (want_acc && col < F.d) {
-        const float* src = F.part_acc + (size_t)b * F.d + col;
+        const float* src = p_acc + (size_t)b * F.d + col;
 #pragma unroll
         for (int i = 0; i < FIN_CHUNK; ++i) {
             const int sp = grp + i * FIN_GROUPS;
@@ -199,16 +234,16 @@ infonce_finalize_kernel(const FinalizeParams F)
                     cnt += st_c[i];
                 }
             } else {                                           // many splits: two dependent passes over the statistics
-                for (int sp = lane; sp < ns; sp += 32) m = fmaxf(m, F.part_max[(size_t)sp * sstride + b]);
+                for (int sp = lane; sp < ns; sp += 32) m = fmaxf(m, __ldcg(p_max + (size_t)sp * sstride + b));
                 m = warp_max(m);
                 if (kMode == FIN_FULL) m = fmaxf(m, pos);
                 for (int sp = lane; sp < ns; sp += 32) {
                     const size_t o = (size_t)sp * sstride + b;
-                    const float pm = F.part_max[o];
+                    const float pm = __ldcg(p_max + o);
                     const float e = (pm == -INFINITY) ? 0.f : __expf(pm - m);
                     w_s[sp] = e;
-                    part += F.part_sum[o] * e;
-                    cnt += F.part_cnt[o];
+                    part += __ldcg(p_sum + o) * e;
+                    cnt += __ldcg(p_cnt + o);
                 }
             }
             float S = warp_sum(part);
@@ -225,7 +260,7 @@ infonce_finalize_kernel(const FinalizeParams F)
                 const float corr = __expf(m - lse);            // = 1 / S
                 for (int sp = lane; sp < ns; sp += 32) w_s[sp] *= corr;
             } else if (lane == 0) {                            // FIN_SHARD: keep the merged partial relative to m
-                F.out_max[b] = m; F.out_sum[b] = S; F.out_cnt[b] = cnt;
+                *o_max = m; *o_sum = S; *o_cnt = cnt;
             }
         }
         if (lane == 0) { row_stat[0] = lse; row_stat[1] = pos; }
@@ -246,7 +281,7 @@ infonce_finalize_kernel(const FinalizeParams F)
                   ((unsigned long long)__double2ll_rn((double)lrow * (double)(1ull << F.pk_frac)) << (3 * nb));
         pk_old = atomicAdd(reinterpret_cast<unsigned long long*>(F.counter + 2), pk_mine);
     }
-    if (F.timebuf && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.timebuf[32 * 400 + 4 * blockIdx.x + 1] = t; }
+    if (F.timebuf && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.timebuf[32 * 400 + 4 * (blockIdx.x & 255) + 1] = t; }
 
     // Gradient accumulator: each of the FIN_GROUPS thread groups sums its interleaved splits in order, then the groups are
     // added in order: deterministic for a given split count.
@@ -280,7 +315,7 @@ infonce_finalize_kernel(const FinalizeParams F)
             } else {
             float a = 0.f;
             if (c < F.d) {
-                const float* src = F.part_acc + (size_t)b * F.d + c;
+                const float* src = p_acc + (size_t)b * F.d + c;
                 for (int base = 0; base < ns; base += FIN_CHUNK * FIN_GROUPS) {
                     if (c0 > 0 || base > 0) {                  // beyond what was preloaded above
 #pragma unroll
@@ -315,12 +350,23 @@ infonce_finalize_kernel(const FinalizeParams F)
                 const float dot = block_sum<FIN_THREADS>(t * qh, red);
                 t = (t - dot * qh) * inv;
             }
-            if (grp == 0 && c < F.d) out[(size_t)b * F.d + c] = t;
+            if (grp == 0 && c < F.d) out_row[c] = t;
             __syncthreads();
         }
     }
+    if (peer_push) {
+        // every thread's remote stores of this row are ordered before thread 0's system-scope release (bar.sync + fence:
+        // cumulativity, as in xchg_push_slice); the owner counts rows per source rank
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            red_release_sys_add_u64(push_counter, 1ull);
+            if (F.timebuf) atomicMax(F.timebuf + 32 * 1000 + 3, globaltimer_ns());      // bring-up only
+        }
+        return;
+    }
 
-    if (F.timebuf && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.timebuf[32 * 400 + 4 * blockIdx.x + 2] = t; }
+    if (F.timebuf && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.timebuf[32 * 400 + 4 * (blockIdx.x & 255) + 2] = t; atomicMax(F.timebuf + 32 * 1000 + 3, t); }
     // counter layout (gca_common.cuh): [0] ticket, [2..3] loss accumulator (or the packed word), [4] top-1, [5] top-5.
     if (pk_on) {
         const int nb = F.pk_nb;
@@ -330,6 +376,10 @@ infonce_finalize_kernel(const FinalizeParams F)
             if (F.loss_mean) *F.loss_mean = (float)((double)(tot >> (3 * nb)) / (double)(1ull << F.pk_frac) / (double)F.B);
             if (F.top_hits) { F.top_hits[0] = (int)((tot >> nb) & mask); F.top_hits[1] = (int)((tot >> (2 * nb)) & mask); }
             *reinterpret_cast<unsigned long long*>(F.counter + 2) = 0ull;   // re-arm for the next launch on this workspace
+            if (peer_merge) {                                               // every row CTA read the step before its ticket
+                F.merge.mstate[0] = mstep + 1ull;
+                if (F.merge.gather_state) F.merge.gather_state[0] = mstep + 1ull;
+            }
             if (F.timebuf) {
                 unsigned long long tt;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
@@ -353,6 +403,10 @@ infonce_finalize_kernel(const FinalizeParams F)
             if (F.top_hits) { F.top_hits[0] = (int)atomicAdd(F.counter + 4, 0u); F.top_hits[1] = (int)atomicAdd(F.counter + 5, 0u); }
             F.counter[0] = 0u; F.counter[2] = 0u; F.counter[3] = 0u; F.counter[4] = 0u; F.counter[5] = 0u;
             F.counter[6] = 0u;
+            if (peer_merge) {
+                F.merge.mstate[0] = mstep + 1ull;
+                if (F.merge.gather_state) F.merge.gather_state[0] = mstep + 1ull;
+            }
             if (F.timebuf) {
                 unsigned long long tt;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
@@ -366,6 +420,7 @@ int infonce_finalize_launch(const FinalizeParams& F_, int mode, cudaStream_t st)
 {
     FinalizeParams F = F_;
     F.timebuf = debug_timebuf();
+    if (F.timebuf && mode == FIN_FULL && F.merge.mailboxes && F.merge.wait) F.timebuf += 8;   // the merge launch stamps its own words
     if (F.nsplit > FIN_MAX_SPLITS) return set_err(GCA_ERR_UNSUPPORTED, "finalize: %d splits > %d", F.nsplit, FIN_MAX_SPLITS);
     F.pk_nb = 0; F.pk_frac = 0;
     if (mode == FIN_FULL && F.range_checked) {
@@ -391,8 +446,16 @@ int infonce_finalize_launch(const FinalizeParams& F_, int mode, cudaStream_t st)
     cudaLaunchConfig_t cfg{};
     static int vec_on = -1;                                   // GCA_FIN_NOVEC=1: column-per-thread loads everywhere (A/B timing)
     if (vec_on < 0) { const char* e = getenv("GCA_FIN_NOVEC"); vec_on = (e && e[0] == '1') ? 0 : 1; }
-    const bool vec = vec_on && F.d == FIN_COLS && F.nsplit <= 8 * FIN_VCH && F.part_acc != nullptr &&
-                     ((mode == FIN_SHARD) ? F.out_acc != nullptr : F.dq != nullptr);
+    const bool peer_merge = mode == FIN_FULL && F.merge.mailboxes != nullptr && F.merge.wait != 0;
+    const bool peer_push = mode == FIN_SHARD && F.merge.mailboxes != nullptr;
+    if ((peer_merge || peer_push) && (F.merge.W > FIN_THREADS || F.merge.d != F.d))
+        return set_err(GCA_ERR_UNSUPPORTED, "finalize: peer merge over %d ranks / d = %d", F.merge.W, F.merge.d);
+    if (peer_merge && F.loss_mean == nullptr && F.top_hits == nullptr)
+        return set_err(GCA_ERR_BAD_ARG, "finalize: the peer merge needs loss_mean (its ticket advances the step counter)");
+    const int ns_eff = peer_merge ? F.merge.W : F.nsplit;
+    const bool vec = vec_on && F.d == FIN_COLS && ns_eff <= 8 * FIN_VCH &&
+                     (peer_merge ? F.dq != nullptr
+                                 : F.part_acc != nullptr && ((mode == FIN_SHARD) ? (F.out_acc != nullptr || peer_push) : F.dq != nullptr));
     cfg.gridDim = dim3(F.B + enq_blocks); cfg.blockDim = dim3(FIN_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;    // PDL: be resident when the stream kernel drains

@@ -104,7 +104,7 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
                       float inv_T, int algo, const float* lse_fixed, bool want_acc, float* pos_out, float* logits_out,
                       void* workspace, size_t workspace_bytes, InfoNceWs* ws_out, cudaStream_t st, bool skip_prep = false,
                       const PeerXchg* px = nullptr, float* proj_k_hat = nullptr,
-                      bool proj = false, int rank_cap = 0)
+                      bool proj = false, int rank_cap = 0, int gather_Bl = 0)
 {
     const int a = pick_algo(algo, dtype_queue, d);
     if (sm_count_cached() < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
@@ -130,6 +130,7 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
         if (a != GCA_ALGO_TCGEN05)
             return set_err(GCA_ERR_UNSUPPORTED, "the peer-fused step exists for the tcgen05 family only (bf16 queue, d == 128)");
         P.xchg = *px;
+        P.gather_Bl = gather_Bl;
     }
     *ws_out = ws;
     count_launch(1);
@@ -309,4 +310,78 @@ extern "C" int gca_infonce_shard_fwd(const float* q, const float* k, const void*
     F.nsplit = ws.nsplit; F.Bpad = ws.Bpad; F.B = B; F.d = d; F.inv_T = inv_T; F.k = k; F.pos = pos_logit;
     F.out_max = part_max; F.out_sum = part_sum; F.out_cnt = part_cnt; F.out_acc = part_acc;
     return infonce_finalize_launch(F, FIN_SHARD, st);
+}
+
+extern "C" size_t gca_shard_peer_bytes(int B_loc, int d, int W)
+{
+    if (B_loc <= 0 || d <= 0 || W <= 0) return 0;
+    const size_t gather = gca_keys_exchange_bytes(2 * B_loc, d, W);
+    const size_t slots = (size_t)2 * W * B_loc * (size_t)(d + 4) * sizeof(float);
+    const size_t counters = (size_t)2 * W * sizeof(unsigned long long);
+    return gather + gca::align_up(slots + counters, 256);
+}
+
+extern "C" int gca_shard_step_peer(const float* qk_loc, void* shard, int dtype_queue, int B_loc, long long K, int d,
+                                   float inv_T, int algo, int W, int rank, void* const* mailboxes, long long* pstate,
+                                   int timeout_ms, long long* enq_state, float* qk_all, float* loss_mean, float* loss_rows,
+                                   float* lse, float* pos_logit_all, int* rank_gt, int* top_hits, float* dq_unit,
+                                   void* workspace, size_t workspace_bytes, void* stream)
+{
+    using namespace gca;
+    GCA_CHECK_ARG(qk_loc && mailboxes && pstate && enq_state && qk_all, "gca_shard_step_peer: null pointer");
+    GCA_CHECK_ARG(loss_mean && loss_rows && lse && pos_logit_all && rank_gt, "gca_shard_step_peer: null output pointer");
+    GCA_CHECK_ARG(W >= 1 && W <= 64 && rank >= 0 && rank < W, "gca_shard_step_peer: bad rank %d of %d", rank, W);
+    GCA_CHECK_ARG(B_loc >= 1 && K >= 1 && K % W == 0, "gca_shard_step_peer: K=%lld must divide evenly over %d ranks", K, W);
+    GCA_CHECK_ARG((long long)W * B_loc <= K, "gca_shard_step_peer: %d x %d rows do not fit a ring of %lld slots", W, B_loc, K);
+    const int Bg = W * B_loc;
+    const long long Ks = K / W;
+    const bool tc = pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05;
+    GCA_CHECK_ARG(tc || qk_all, "gca_shard_step_peer: qk_all is required outside the tcgen05 family");
+    const float* q_all = tc ? qk_loc : qk_all;                          // (tcgen05 family: only the pointer check sees these)
+    const float* k_all = tc ? qk_loc : qk_all + (size_t)Bg * d;
+    int rc = check_infonce_args("gca_shard_step_peer", q_all, k_all, shard, dtype_queue, Bg, Ks, d, inv_T, algo);
+    if (rc != GCA_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    PeerXchg X{};
+    X.mailboxes = (char* const*)mailboxes; X.W = W; X.rank = rank; X.n4 = 2 * B_loc * d / 4;
+    X.xstate = (unsigned long long*)pstate;
+    X.timeout_ns = timeout_ms > 0 ? (unsigned long long)timeout_ms * 1000000ull : 0ull;
+    // 1. q|k of every rank.  tcgen05 family: rides in the prep launch (push CTAs + row warps reading the mailbox);
+    //    otherwise the stand-alone exchange kernel, output part-major (all q rows, then all k rows, rank-major inside)
+    if (!tc) {
+        rc = keys_exchange_launch(qk_loc, 2 * B_loc, d, W, rank, mailboxes, qk_all, pstate, timeout_ms, 2, st);
+        if (rc != GCA_OK) return rc;
+    }
+    // 2. all rows against the local shard
+    InfoNceWs ws;
+    rc = run_stream(q_all, k_all, shard, dtype_queue, Bg, Ks, d, inv_T, algo, nullptr, dq_unit != nullptr, pos_logit_all,
+                    nullptr, workspace, workspace_bytes, &ws, st, false, tc ? &X : nullptr, nullptr, false, 0, tc ? B_loc : 0);
+    if (rc != GCA_OK) return rc;
+    PeerMerge M{};
+    M.mailboxes = (char* const*)mailboxes; M.off = gca_keys_exchange_bytes(2 * B_loc, d, W);
+    M.W = W; M.rank = rank; M.Bl = B_loc; M.d = d;
+    M.mstate = (unsigned long long*)pstate + 4;
+    M.gather_state = tc ? (unsigned long long*)pstate : nullptr;
+    M.timeout_ns = X.timeout_ns;
+    // 3. split merge; every row's partial goes to its owner's mailbox
+    FinalizeParams F{};
+    F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
+    F.part_acc = dq_unit ? ws.part_acc : nullptr;
+    F.nsplit = ws.nsplit; F.Bpad = ws.Bpad; F.B = Bg; F.d = d; F.inv_T = inv_T; F.k = k_all; F.pos = pos_logit_all;
+    F.merge = M;
+    rc = infonce_finalize_launch(F, FIN_SHARD, st);
+    if (rc != GCA_OK) return rc;
+    // 4. cross-rank merge of the local rows; extra CTAs of the same launch enqueue the gathered keys that land in this
+    //    rank's slots (tcgen05 family: the keys staged by the prep kernel)
+    const float* keys = tc ? ws.k_hat : k_all;
+    FinalizeParams G{};
+    G.counter = ws.counter; G.nsplit = W; G.Bpad = ws.Bpad; G.B = B_loc; G.d = d; G.inv_T = inv_T;
+    G.k = keys + (size_t)rank * B_loc * d;
+    G.pos = pos_logit_all + (size_t)rank * B_loc;
+    G.lse = lse; G.loss_rows = loss_rows; G.rank_gt = rank_gt; G.dq = dq_unit; G.loss_mean = loss_mean; G.top_hits = top_hits;
+    G.range_checked = tc ? 1 : 0;
+    G.merge = M; G.merge.wait = 1;
+    G.enq_queue = shard; G.enq_dtype = dtype_queue; G.enq_K = K; G.enq_keys = keys; G.enq_N = Bg; G.enq_state = enq_state;
+    G.enq_kbegin = (long long)rank * Ks; G.enq_kend = (long long)(rank + 1) * Ks;
+    return infonce_finalize_launch(G, FIN_FULL, st);
 }

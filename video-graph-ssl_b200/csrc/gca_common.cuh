@@ -62,9 +62,27 @@ struct PeerXchg {
     unsigned long long timeout_ns;   // 0 = wait for ever
 };
 
+// Cross-rank merge of the K-sharded step through the same kind of mailbox (finalize.cu).  Region of every rank's mailbox at
+// byte offset `off`:   slots [2 parities][W source ranks][Bl * (d + 4) floats]   then   counters [2][W] (u64)
+// A slot holds one source rank's partials of the OWNER's Bl rows: acc [Bl, d], then max [Bl], sum [Bl], count [Bl] (int
+// bits), pad [Bl].  Step s uses parity s & 1 (the q|k gather at the head of every step keeps the ranks within one step of
+// each other).  Every row CTA of the source's FIN_SHARD launch stores its row remotely and adds 1 (release, system scope) to
+// counter[par][source] in the owner's mailbox; the owner's merge CTAs wait for ((s >> 1) + 1) * Bl rows from every source.
+struct PeerMerge {
+    char* const* mailboxes;          // device array [W]; nullptr = off
+    unsigned long long off;          // byte offset of the merge region inside every mailbox
+    int W, rank, Bl, d;
+    unsigned long long* mstate;      // device memory: [0] merge step counter, [2] timeout flag
+    unsigned long long* gather_state;   // non-null: the q|k gather rode in the prep launch; its step counter advances with mstate
+    unsigned long long timeout_ns;   // 0 = wait for ever
+    int wait;                        // FIN_FULL launch: wait for the W sources, then merge them
+};
+
 static inline int infonce_bpad(int B) { return (B + 127) / 128 * 128; }
 // upper bound on the number of K-splits any kernel family uses (2 CTAs worth per SM, at least 1)
 int infonce_max_splits(int B);
+int keys_exchange_launch(const float* keys_local, int B, int d, int W, int rank, void* const* mailboxes, float* all_k,
+                         long long* xstate, int timeout_ms, int parts, cudaStream_t st);      // exchange.cu
 InfoNceWs infonce_ws_carve(void* base, int B, int d, int nsplit);
 
 }  // namespace gca
@@ -154,6 +172,29 @@ __device__ __forceinline__ bool xchg_wait_slice(const PeerXchg& X, unsigned long
     const unsigned long long t0 = globaltimer_ns();
     while (ld_acquire_sys_u64(f) < step + 1) {
         if (X.timeout_ns && globaltimer_ns() - t0 > X.timeout_ns) { atomicExch(X.xstate + 2, 1ull); return false; }
+    }
+    return true;
+}
+
+// ---- cross-rank merge region (PeerMerge)
+__device__ __forceinline__ size_t pm_slot_floats(const PeerMerge& M) { return (size_t)M.Bl * (size_t)(M.d + 4); }
+__device__ __forceinline__ float* pm_slot(char* box, const PeerMerge& M, int par, int from) {
+    return reinterpret_cast<float*>(box + M.off) + ((size_t)par * M.W + from) * pm_slot_floats(M);
+}
+__device__ __forceinline__ unsigned long long* pm_counter(char* box, const PeerMerge& M, int par, int from) {
+    return reinterpret_cast<unsigned long long*>(box + M.off + (size_t)2 * M.W * pm_slot_floats(M) * sizeof(float)) + (size_t)par * M.W + from;
+}
+__device__ __forceinline__ void red_release_sys_add_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// One thread: wait until source rank `from` has delivered `need` rows (monotone counter) into my mailbox.  False on timeout.
+__device__ __forceinline__ bool pm_wait(const PeerMerge& M, int par, int from, unsigned long long need)
+{
+    const unsigned long long* f = pm_counter(M.mailboxes[M.rank], M, par, from);
+    if (ld_acquire_sys_u64(f) >= need) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys_u64(f) < need) {
+        if (M.timeout_ns && globaltimer_ns() - t0 > M.timeout_ns) { atomicExch(M.mstate + 2, 1ull); return false; }
     }
     return true;
 }

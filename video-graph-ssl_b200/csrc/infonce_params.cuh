@@ -35,6 +35,8 @@ struct InfoNceStreamParams {
     float* inv_nq;           // [Bpad] out: 1 / max(||q||, 1e-12) (normalize only)
     int    normalize;
     int    rank_cap;         // tcgen05 single-pass kernel: > 0 = the caller only needs ranks below this value (top-k hits)
+    int    gather_Bl;        // > 0 (K-sharded step over peer memory): q = this rank's [q_loc; k_loc] block of 2 * gather_Bl rows;
+                             // the prep launch pushes it to every peer and reads all B = W * gather_Bl rows from the mailbox
     float  q_scale;          // factor folded into the bf16 queries by the prep kernel (1, or log2(e)/T for infonce_tcx)
 };
 
@@ -64,14 +66,14 @@ struct FinalizeParams {
     // optional fused enqueue (FIN_FULL): keys [enq_N, d] into the full ring queue [enq_K, d]
     void* enq_queue; int enq_dtype; long long enq_K; const float* enq_keys; int enq_N;
     long long enq_index; long long* enq_state;
+    long long enq_kbegin, enq_kend;   // enq_kend > 0: enq_queue is the shard holding global slots [enq_kbegin, enq_kend)
     PeerXchg xchg;                 // enq_keys == NULL and xchg on: the rows come from this rank's mailbox (all W*B of them)
     unsigned long long* timebuf;   // bring-up only (tools/tc_timeline.py): entry / exit time stamps
     const float* zq; const float* inv_nq;   // projection-tail fusion: dq is pushed back through q = zq / ||zq|| (NULL = off)
-    // K-sharded step over peer memory (gca_infonce_shard_merge_peer): the "splits" are the W ranks' partials of this rank's
-    // rows, sitting in this rank's mailbox; push CTAs at the head of the launch deliver the local partials to their owners
-    PeerXchg merge_xchg;           // off if mailboxes == nullptr
-    const float* push_acc; const float* push_max; const float* push_sum; const int* push_cnt;   // local partials [W * B, ...]
-    long long split_stride;        // floats between two splits of part_max / part_sum / part_cnt / part_acc (0 = dense layout)
+    // K-sharded step over peer memory (gca_shard_step_peer; protocol at PeerMerge in gca_common.cuh).  FIN_SHARD launch: row
+    // b's merged partial goes straight into its OWNER's mailbox (remote stores + one released row count per CTA).  FIN_FULL
+    // launch with merge.wait: the "splits" are the W ranks' partials of this rank's rows, read from this rank's mailbox.
+    PeerMerge merge;               // off if mailboxes == nullptr
     int range_checked;             // the stream kernel reports out-of-range logits in control word 6 (tcgen05 family)
     int pk_nb, pk_frac;            // set by infonce_finalize_launch: packed loss/hits/ticket word (0 = unpacked path)
 };

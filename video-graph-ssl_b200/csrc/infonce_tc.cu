@@ -430,27 +430,33 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
                     __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ pos_ws, float* __restrict__ pos_out,
                     unsigned long long* timebuf, const PeerXchg X, int nprep, unsigned int* range_flag,
                     float* __restrict__ k_hat, float* __restrict__ inv_nq, int normalize,
-                    const char* __restrict__ pf_base, unsigned long long pf_bytes, float q_scale)
+                    const char* __restrict__ pf_base, unsigned long long pf_bytes, float q_scale, const int npush,
+                    const int gather_Bl)
 {
     ptx::pdl_launch_dependents();            // the streaming kernel may start its setup and its first queue-tile loads
     // warm the L2 with the head of the queue (the first tile waves of the stream kernel): this launch starts ~1 us before
     // the stream kernel's TMA producer can, and a cold queue tile costs a full HBM round trip at the head of every CTA's
     // pipeline.  32 KB bulk prefetches, dealt round-robin over the CTAs of this launch (a few per SM).
-    if (pf_base != nullptr && (int)blockIdx.x < nprep) {
-        const unsigned long long off = ((unsigned long long)blockIdx.x + (unsigned long long)nprep * threadIdx.x) * 32768ull;
+    // the push CTAs of a peer exchange are the FIRST blocks of the launch: a row CTA that waits for a peer's rows (gather
+    // mode) can never keep them from being scheduled
+    const int rb = (int)blockIdx.x - npush;                                 // row block of this CTA (< 0: push CTA)
+    if (pf_base != nullptr && rb >= 0) {
+        const unsigned long long off = ((unsigned long long)rb + (unsigned long long)nprep * threadIdx.x) * 32768ull;
         if (off < pf_bytes) {
             const unsigned long long rest = pf_bytes - off;
             const unsigned int nb = rest < 32768ull ? (unsigned int)rest : 32768u;
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(pf_base + off), "r"(nb) : "memory");
         }
     }
-    if ((int)blockIdx.x >= nprep) {          // key exchange riding in this launch: push slice c of k to rank p (exchange.cu)
-        const int e = blockIdx.x - nprep;
+    if (rb < 0) {
+        // exchange riding in this launch: push slice c of the local rows to rank p (exchange.cu).  Replica step: the keys k
+        // [B, d]; gather mode (K-sharded step): q holds this rank's [q_loc; k_loc] block of 2 * gather_Bl rows
+        const int e = blockIdx.x;
         const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(X.xstate);
-        xchg_push_slice(X, reinterpret_cast<const float4*>(k), step, e / XCHG_SLICES, e % XCHG_SLICES);
+        xchg_push_slice(X, reinterpret_cast<const float4*>(gather_Bl > 0 ? q : k), step, e / XCHG_SLICES, e % XCHG_SLICES);
         return;
     }
-    const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, row = rb * 8 + (threadIdx.x >> 5);
     if (timebuf && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -458,7 +464,24 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
     }
     if (row >= Bpad) return;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (row < B) {
+    if (row < B && gather_Bl > 0) {
+        // gather mode: global row `row` is row lr of rank p; its q and k rows arrive in slot p of this rank's mailbox
+        // ([q rows; k rows] of that rank).  Wait for the two slices that hold them, then read around L1.
+        const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(X.xstate);
+        const int p = row / gather_Bl, lr = row - p * gather_Bl;
+        const int per = (X.n4 + XCHG_SLICES - 1) / XCHG_SLICES;
+        const int iq = lr * (TC_D / 4), ik = (gather_Bl + lr) * (TC_D / 4);
+        if (lane == 0) {
+            xchg_wait_slice(X, step, p, iq / per);
+            xchg_wait_slice(X, step, p, (iq + TC_D / 4 - 1) / per);
+            xchg_wait_slice(X, step, p, ik / per);
+            xchg_wait_slice(X, step, p, (ik + TC_D / 4 - 1) / per);
+        }
+        __syncwarp();
+        const float4* slot = xchg_slot(X.mailboxes[X.rank], X, (int)(step & 1ull), p);
+        a = ld_cg_f4(slot + iq + lane);
+        b = ld_cg_f4(slot + ik + lane);
+    } else if (row < B) {
         a = __ldg(reinterpret_cast<const float4*>(q + (size_t)row * TC_D) + lane);
         b = __ldg(reinterpret_cast<const float4*>(k + (size_t)row * TC_D) + lane);
     }
@@ -486,6 +509,7 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
         if (pos_out && row < B) pos_out[row] = dsum;
         if (fabsf(dsum) > 1.0625f * inv_T) range_flag[0] = 1u;        // see the partial write of the stream kernel
     }
+    if (timebuf && threadIdx.x == 0) atomicMax(timebuf + 32 * 1000 + 4, globaltimer_ns());       // bring-up only
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -588,7 +612,7 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
                                                            P.pos_ws, P.pos_out, debug_timebuf(), P.xchg, nprep, P.counter + 6,
                                                            P.k_hat, P.inv_nq, P.normalize,
                                                            pf_on ? (const char*)P.queue : nullptr, pf_bytes,
-                                                           P.q_scale);
+                                                           P.q_scale, npush, P.gather_Bl);
         GCA_LAUNCH_CHECK("infonce_prep_kernel");
         count_launch(1);
     }

@@ -73,6 +73,11 @@ SIGNATURES = {
                                    c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_size_t, c_void_p]),
+    "gca_shard_peer_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gca_shard_step_peer": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
+                                    c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_size_t, c_void_p]),
     "gca_moco_step_proj": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_float, c_int,
                                    c_void_p, c_int, c_longlong, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -231,12 +231,16 @@ class GraphedShardedStep(object):
     issued operations.  Same arithmetic as ShardedRGBMoCo.forward + NCESoftmaxLoss + backward with grad_output = 1;
     results for the LOCAL rows: .loss (mean over local rows), .dq, .rank, .lse, .loss_rows."""
 
-    def __init__(self, moco, batch_local, algo=None):
+    def __init__(self, moco, batch_local, algo=None, link=None):
+        """`link`: a gca_b200.peer.PeerShardLink (shared by every captured step of this process) -> the q|k gather and the
+        cross-rank merge travel through NVLink peer memory inside the step's own launches (gca_shard_step_peer: 4 launches,
+        no collective call) instead of three captured NCCL collectives."""
         import torch.distributed as dist
         mem = moco.memory
         if not mem.is_cuda:
             raise RuntimeError("GraphedShardedStep needs the shard on a CUDA device; there is no CPU path")
         self.moco, self.group = moco, moco.group
+        self.link = link
         self.W, self.r = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.Bl, self.Bg = int(batch_local), int(batch_local) * self.W
         self.Ks, self.d = mem.shape
@@ -267,12 +271,26 @@ class GraphedShardedStep(object):
                               dtype=torch.uint8, device=dev)
         self.graph = None
         self.launches_per_step = 0
+        if link is not None:
+            if (link.W, link.r, link.Bl, link.d) != (self.W, self.r, self.Bl, self.d):
+                raise ValueError("PeerShardLink was built for another shape / group")
+            # local-row outputs of the fused call (the NCCL path slices them out of the global-row buffers)
+            self.lse, self.loss_rows = f32(self.Bl), f32(self.Bl)
+            self.rank = torch.zeros(self.Bl, dtype=torch.int32, device=dev)
+            self.hits = torch.zeros(2, dtype=torch.int32, device=dev)
 
     def _enqueue_work(self):
         import torch.distributed as dist
         m, sl = self.moco, self._sl
         dev = m.memory.device
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if self.link is not None:
+            x = self.link
+            _lib.call("gca_shard_step_peer", ptr(self.inputs), ptr(m.memory), self.qd, self.Bl, m.K, self.d, 1.0 / m.T,
+                      _lib.ALGO[self.algo], self.W, self.r, ptr(x.table), ptr(x.pstate), x.timeout_ms, ptr(self.state),
+                      ptr(self.qk_all), ptr(self.loss), ptr(self.loss_rows), ptr(self.lse), ptr(self.pos), ptr(self.rank),
+                      ptr(self.hits), ptr(self.dq), ptr(self.ws), self.ws.numel(), stream)
+            return
         dist.all_gather_into_tensor(self.gathered, self.inputs, group=self.group)
         self.qk_all.view(2, self.W, self.Bl, self.d).copy_(self.gathered.transpose(0, 1))
         q_all, k_all = self.qk_all[0], self.qk_all[1]

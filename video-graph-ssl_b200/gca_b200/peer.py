@@ -63,3 +63,37 @@ class PeerKeyExchange(object):
     def check(self):
         if int(self.xstate[2]) != 0:
             raise RuntimeError("gca_keys_exchange: a peer did not deliver its keys within %d ms" % self.timeout_ms)
+
+
+class PeerShardLink(object):
+    """Symmetric-memory mailbox + device state for the K-sharded head step over peer memory (gca_shard_step_peer): the q|k
+    gather and the cross-rank merge of the partials both travel through it, no NCCL call on the data path.
+    Collective constructor (every rank of `group`, same local batch and d); all ranks must issue the same step sequence."""
+
+    def __init__(self, batch_local, n_dim, group=None, device=None, timeout_ms=10000):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.W, self.r = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.Bl, self.d = int(batch_local), int(n_dim)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("PeerShardLink moves rows between GPUs; there is no CPU path")
+        self.device = dev
+        nbytes = int(_lib.load().gca_shard_peer_bytes(self.Bl, self.d, self.W))
+        self.mailbox = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.mailbox.zero_()
+        self.handle = symm_mem.rendezvous(self.mailbox, self.group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != self.W or ptrs[self.r] != self.mailbox.data_ptr():
+            raise RuntimeError("symmetric-memory rendezvous returned an unexpected peer table: %r" % (ptrs,))
+        self.table = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self.pstate = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.timeout_ms = int(timeout_ms)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)                       # every mailbox is zeroed before anyone pushes
+
+    def check(self):
+        st = self.pstate.cpu()
+        if int(st[2]) != 0 or int(st[6]) != 0:
+            raise RuntimeError("gca_shard_step_peer: a peer did not deliver within %d ms (gather flag %d, merge flag %d)"
+                               % (self.timeout_ms, int(st[2]), int(st[6])))
