@@ -220,6 +220,21 @@ int gca_shard_step_peer(const float* qk_loc, void* shard, int dtype_queue, int B
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * BatchNorm1d (+ ReLU) epilogue of the SimSiam projection / prediction MLPs (replaces the nn.BatchNorm1d -> nn.ReLU pairs
+ * of ProjectionMLP / PredictionMLP, lib/modeling/project_head.py:36-76; the nn.Linear in front stays a library GEMM).
+ * x, y, dy, dx: [B, C] fp32 row-major; gamma, beta, running_*, save_*, dgamma, dbeta: [C] (gamma / beta NULL = 1 / 0).
+ * Training mode (use_running = 0): batch statistics (biased variance normalises, the unbiased one feeds running_var with
+ * `momentum`, exactly nn.BatchNorm1d); eval mode (use_running = 1): the running statistics normalise, nothing is updated.
+ * save_mean / save_invstd are what the backward needs; relu != 0 applies max(., 0) to y and its mask to dy.
+ * One launch each; deterministic (fixed reduction order). */
+int gca_bn1d_fwd(const float* x, int B, int C, const float* gamma, const float* beta, float eps, float momentum, int relu,
+                 int use_running, float* running_mean, float* running_var, float* y, float* save_mean, float* save_invstd,
+                 void* stream);
+int gca_bn1d_bwd(const float* x, const float* dy, int B, int C, const float* gamma, const float* beta,
+                 const float* save_mean, const float* save_invstd, int relu, int use_running, float* dx, float* dgamma,
+                 float* dbeta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Temporal clip-graph head.  Replaces, for one GCN layer (the shipped default), the part of
  * TemporalGraphAug.forward (lib/ops/module_wrappers/temporal_graph.py:227-239) between the 1x1x1 convolutions:
  * similarity + row softmax (:161-176), hop mask and theta(hop) weights (:25-36, :204-210), relaxed-Bernoulli

@@ -970,6 +970,78 @@ def test_momentum_update_matches_reference_loop(lib, layout):
         MomentumUpdater(make(), make().to(memory_format=torch.channels_last_3d))
 
 
+@pytest.mark.parametrize("name", ["proj", "pred"])
+def test_simsiam_mlp_against_reference_fixture(lib, golden, name):
+    """gca_b200.ProjectionMLP / PredictionMLP (library GEMM + fused BatchNorm1d/ReLU launches) against the outputs, gradients
+    and running statistics of the reference's own modules (lib/modeling/project_head.py:36-76; oracle/gen_golden_mlp.py)."""
+    import gca_b200
+    g = golden("simsiam_mlp")
+    sd = {k[len(name) + 8:]: T_(v) for k, v in g.items() if k.startswith(name + ".before.")}
+    x = T_(g[name + ".x"])
+    hid = sd["l1.0.weight"].shape[0]
+    m = (gca_b200.ProjectionMLP(x.shape[1], hid, sd["l3.0.weight"].shape[0]) if name == "proj"
+         else gca_b200.PredictionMLP(x.shape[1], hid, sd["l2.weight"].shape[0]))
+    assert set(m.state_dict().keys()) == set(sd.keys())                     # same checkpoint layout as upstream
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    y = m(xg)
+    (y * T_(g[name + ".w"]).cuda()).sum().backward()
+    assert rel_max(y, T_(g[name + ".y"])) <= 2e-5
+    assert rel_max(xg.grad, T_(g[name + ".dx"])) <= 1e-4
+    for k, p_ in m.named_parameters():
+        ref = T_(g[name + ".grad." + k])
+        # (a bias in front of a BatchNorm has a mathematically zero gradient: only fp32 noise, compared absolutely)
+        tol = 1e-4 if k.endswith(".0.bias") else 1e-4 * max(float(ref.abs().max()), 1e-3)
+        assert float((p_.grad.cpu() - ref).abs().max()) <= tol, k
+    for k, v in m.state_dict().items():
+        ref = T_(g[name + ".after." + k])
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(ref)
+        elif "running" in k:
+            assert float((v.cpu() - ref).abs().max()) <= 1e-5, k
+    # eval mode: the running statistics normalise and nothing moves (same as the torch modules on the same state)
+    m.eval()
+    rm = m.l1[1].running_mean.clone()
+    with torch.no_grad():
+        ye = m(x.cuda())
+    ref_m = torch.nn.Sequential()
+    import torch.nn as nn
+    l1 = nn.Sequential(nn.Linear(x.shape[1], hid), nn.BatchNorm1d(hid), nn.ReLU()).cuda().eval()
+    l1.load_state_dict({k[3:]: v for k, v in m.state_dict().items() if k.startswith("l1.")})
+    with torch.no_grad():
+        h_ref = l1(x.cuda())
+        h = gca_b200.functional.bn1d(torch.nn.functional.linear(x.cuda(), m.l1[0].weight, m.l1[0].bias), m.l1[1], relu=True)
+    assert rel_max(h, h_ref) <= 1e-5 and torch.equal(rm, m.l1[1].running_mean) and ye.shape == y.shape
+
+
+@pytest.mark.parametrize("B,C,relu", [(128, 2048, True), (256, 512, False), (300, 96, True), (2, 33, True), (1024, 64, True)])
+def test_bn1d_random_shapes(GF, B, C, relu):
+    """gca_bn1d_fwd / gca_bn1d_bwd against torch's own BatchNorm1d (+ ReLU) in fp64 on the CPU: cached (B <= 256) and
+    re-reading (B > 256) variants, column tails (C % 32 != 0)."""
+    import torch.nn as nn
+    torch.manual_seed(B * 7 + C)
+    bn = nn.BatchNorm1d(C)
+    bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.uniform_(-0.3, 0.3)
+    ref = nn.BatchNorm1d(C).double()
+    ref.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in bn.state_dict().items()})
+    x = torch.randn(B, C) * 1.7 + 0.4
+    w = torch.randn(B, C)
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr)
+    yr = torch.relu(yr) if relu else yr
+    (yr * w.double()).sum().backward()
+    bn = bn.cuda()
+    xg = x.cuda().requires_grad_(True)
+    y = GF.bn1d(xg, bn, relu=relu)
+    (y * w.cuda()).sum().backward()
+    assert rel_max(y, yr.detach()) <= 1e-5
+    assert rel_max(xg.grad, xr.grad) <= 2e-4
+    assert rel_max(bn.weight.grad, ref.weight.grad) <= 1e-4 and rel_max(bn.bias.grad, ref.bias.grad) <= 1e-4
+    assert rel_max(bn.running_var, ref.running_var) <= 1e-5 and float((bn.running_mean.cpu() - ref.running_mean).abs().max()) <= 1e-6
+    assert int(bn.num_batches_tracked) == 1
+
+
 def test_graphed_sharded_step_matches_eager_path():
     """GraphedShardedStep (NCCL collectives + kernels in one CUDA graph) == the eager ShardedRGBMoCo path, bit for bit.
     World size 1 here (the suite sees one GPU); `torchrun --nproc-per-node N tests/sharded_graph_worker.py` runs the

@@ -201,3 +201,31 @@ def test_cmc_moco_and_jig_heads_match_reference(golden):
         idx = oracle.enqueue(mem, k, idx)
         assert idx == int(j[f"index_after{st}"])
     assert torch.equal(mem, T_(j["memory_after"]))
+
+
+@pytest.mark.parametrize("name", ["proj", "pred"])
+def test_simsiam_mlp_restatement_matches_reference(golden, name):
+    """oracle.mlp (Linear + BatchNorm1d [+ ReLU] forward / backward by hand, fp64) against the outputs, gradients and running
+    statistics of the reference's ProjectionMLP / PredictionMLP (oracle/gen_golden_mlp.py)."""
+    from oracle import mlp as om
+    g = golden("simsiam_mlp")
+    p = {k[len(name) + 8:]: np.asarray(v, dtype=np.float64) for k, v in g.items() if k.startswith(name + ".before.")}
+    x, w = np.asarray(g[name + ".x"], np.float64), np.asarray(g[name + ".w"], np.float64)
+    if name == "proj":
+        y, caches = om.projection_mlp(x, p)
+        dx, grads = om.projection_mlp_backward(w, caches)
+    else:
+        y, caches = om.prediction_mlp(x, p)
+        dx, grads = om.prediction_mlp_backward(w, caches)
+    np.testing.assert_allclose(y, g[name + ".y"], rtol=0, atol=2e-5 * np.abs(y).max())
+    np.testing.assert_allclose(dx, g[name + ".dx"], rtol=0, atol=1e-4 * np.abs(dx).max())
+    for i, blk in enumerate(("l1", "l2", "l3")[:len(grads) if name == "proj" else 1]):
+        gr = grads[i]
+        for key, ref in (("dW", blk + ".0.weight"), ("db", blk + ".0.bias"), ("dgamma", blk + ".1.weight"), ("dbeta", blk + ".1.bias")):
+            r = g[name + ".grad." + ref]
+            # (the bias in front of a BatchNorm has a mathematically zero gradient: fp32 autograd leaves ~1e-5 of noise there)
+            np.testing.assert_allclose(gr[key], r, rtol=0, atol=1e-4 if key == "db" else 1e-4 * max(np.abs(r).max(), 1e-3))
+        c = caches[i]
+        np.testing.assert_allclose(0.9 * p[blk + ".1.running_mean"] + 0.1 * c["mean"], g[name + ".after." + blk + ".1.running_mean"], atol=1e-5)
+        np.testing.assert_allclose(0.9 * p[blk + ".1.running_var"] + 0.1 * c["var_unb"], g[name + ".after." + blk + ".1.running_var"], atol=1e-5)
+        assert int(g[name + ".after." + blk + ".1.num_batches_tracked"]) == 1

@@ -6,7 +6,7 @@ interfaces runs in libgca_b200.so (hand-written CUDA, C ABI in include/gca_b200.
 """
 from . import _lib, functional                                   # noqa: F401
 from .memory import (RGBMoCo, CMCMoCo, NCESoftmaxLoss, D, FusedLogits, create_contrast, create_criterion)  # noqa: F401
-from .ops import TemporalGraphAug, build_aug_block, get_agg       # noqa: F401
+from .ops import TemporalGraphAug, build_aug_block, get_agg, ProjectionMLP, PredictionMLP       # noqa: F401
 
 __all__ = ["RGBMoCo", "CMCMoCo", "NCESoftmaxLoss", "D", "FusedLogits", "create_contrast", "create_criterion",
-           "TemporalGraphAug", "build_aug_block", "get_agg", "functional"]
+           "TemporalGraphAug", "build_aug_block", "get_agg", "ProjectionMLP", "PredictionMLP", "functional"]

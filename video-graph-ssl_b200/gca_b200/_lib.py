@@ -82,6 +82,10 @@ SIGNATURES = {
                                    c_void_p, c_int, c_longlong, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_size_t, c_void_p]),
+    "gca_bn1d_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gca_bn1d_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                             c_void_p, c_void_p, c_void_p, c_void_p]),
     "gca_sim_topk_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gca_sim_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_size_t, c_void_p]),

@@ -271,6 +271,56 @@ def neg_cosine(p, z):
 
 
 # --------------------------------------------------------------------------------------------- retrieval
+class _BN1d(torch.autograd.Function):
+    """BatchNorm1d (+ ReLU) on a [B, C] GEMM output: one launch forward, one backward (csrc/bn1d.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, relu, training):
+        _need_cuda(x)
+        x = _f32c(x)
+        B, C = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty_like(mean)
+        use_running = 0 if training else 1
+        _lib.call("gca_bn1d_fwd", ptr(x), B, C, ptr(gamma), ptr(beta), float(eps), float(momentum), 1 if relu else 0,
+                  use_running, ptr(running_mean), ptr(running_var), ptr(y), ptr(mean), ptr(invstd), _stream(x))
+        ctx.save_for_backward(x, gamma, beta, mean, invstd)
+        ctx.cfg = (1 if relu else 0, use_running)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, invstd = ctx.saved_tensors
+        relu, use_running = ctx.cfg
+        B, C = x.shape
+        dy = _f32c(dy)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dg = torch.empty(C, dtype=torch.float32, device=x.device) if gamma is not None else None
+        db = torch.empty(C, dtype=torch.float32, device=x.device) if beta is not None else None
+        _lib.call("gca_bn1d_bwd", ptr(x), ptr(dy), B, C, ptr(gamma), ptr(beta), ptr(mean), ptr(invstd), relu, use_running,
+                  ptr(dx), ptr(dg), ptr(db), _stream(x))
+        return dx, dg, db, None, None, None, None, None, None
+
+
+def bn1d(x, bn, relu=False):
+    """`relu(bn(x))` for an `nn.BatchNorm1d` module `bn` on a [B, C] tensor, with the module's own semantics: batch
+    statistics + running-statistics update in training mode (or when it tracks none), running statistics in eval mode."""
+    if x.dim() != 2:
+        raise ValueError("bn1d expects [B, C], got %r" % (tuple(x.shape),))
+    training = bn.training or bn.running_mean is None
+    if training and x.shape[0] < 2:
+        raise ValueError("Expected more than 1 value per channel when training, got input size %r" % (tuple(x.shape),))
+    momentum = 0.0
+    rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        momentum = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else bn.momentum
+    if not bn.training:
+        momentum = 0.0
+    return _BN1d.apply(x, bn.weight, bn.bias, rm, rv, bn.eps, momentum, relu, training)
+
+
 def cosine_topk(queries, gallery, k, normalize=True):
     """Indices [Nq, k] (int32) and cosine similarities of the k nearest gallery rows of every query."""
     _need_cuda(queries, gallery)
