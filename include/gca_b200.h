@@ -197,19 +197,22 @@ int gca_moco_step_peer(const float* q, const float* k, void* queue, int dtype_qu
 /* The K-sharded head step with every exchange over NVLink peer memory (the partition of SURVEY.md section 8e; replaces the
  * replicated queue + key gather of tools/train_video_contrast_dis.py:182-187, 222, 233-242 and the three NCCL collectives
  * of the gca_infonce_shard_* sequence above).  One call per step and rank launches
- *   1. the q|k gather            qk_loc [2, B_loc, d] of every rank -> qk_all [2, W*B_loc, d] (the gca_keys_exchange
- *                                protocol on rows 2*B_loc; head of every mailbox)
+ *   1. the q|k gather            qk_loc [2, B_loc, d] of every rank through the mailboxes (the gca_keys_exchange protocol on
+ *                                rows 2*B_loc; head of every mailbox).  tcgen05 family: rides in the prep launch (push CTAs
+ *                                + row warps that read their q, k rows from the mailbox; qk_all unused, may be NULL);
+ *                                otherwise one exchange launch into qk_all [2, W*B_loc, d]
  *   2. the shard sweep           all W*B_loc rows against this rank's [K/W, d] shard (prep + stream kernel)
- *   3. the split merge           one CTA per row; the merged partial of row b (acc, max, sum, count) is stored straight into
- *                                the mailbox of the rank that owns the row, followed by one released row count
- *   4. the cross-rank merge      one CTA per LOCAL row waits for the W sources' rows, merges them in rank order (fixed
- *                                association: every rank computes bit-identical statistics), adds the positive and writes
- *                                loss rows, lse, rank, dq_unit [B_loc, d] (scaled by 1 / (T * B_loc)) and the local mean loss
- *   5. the sharded enqueue       every rank writes the gathered keys that land in its slots; `enq_state` = device ring
- *                                pointer over the GLOBAL ring of K slots (gca_enqueue_devptr)
+ *   3. the split merge           one CTA per row; the merged partials of ALL rows (acc, max, sum, count) stay in this rank's
+ *                                own mailbox; the last CTA publishes the step to every peer (one release store each)
+ *   4. the cross-rank merge      one CTA per LOCAL row waits for the W flags, pulls the row's W partials from the peers'
+ *                                mailboxes (remote loads, all in flight at once), merges them in rank order (fixed
+ *                                association: deterministic), adds the positive and writes loss rows, lse, rank,
+ *                                dq_unit [B_loc, d] (scaled by 1 / (T * B_loc)) and the local mean loss
+ *      + the sharded enqueue     extra CTAs of launch 4 write the gathered keys that land in this rank's slots;
+ *                                `enq_state` = device ring pointer over the GLOBAL ring of K slots
  * No collective call; CUDA-graph capturable.  Mailboxes: symmetric memory of gca_shard_peer_bytes() bytes per rank, zeroed
  * before the first step; `pstate`: 8 x int64 device words, zero-initialised ([0..2] gather step / ticket / timeout flag,
- * [4] merge step, [6] merge timeout flag).  pos_logit_all [W*B_loc]; loss_rows, lse, rank_gt [B_loc] (local rows);
+ * [4..6] merge step / ticket / timeout flag).  pos_logit_all [W*B_loc]; loss_rows, lse, rank_gt [B_loc] (local rows);
  * top_hits [2] may be NULL.  Sharding changes no result: same outputs as gca_moco_step on the concatenated queue up to
  * the association order of the fp32 merges (tests/sharded_graph_worker.py). */
 size_t gca_shard_peer_bytes(int B_loc, int d, int W);

@@ -144,30 +144,37 @@ infonce_finalize_kernel(const FinalizeParams F)
     const bool peer_push = (kMode == FIN_SHARD) && F.merge.mailboxes != nullptr;
     const bool peer_merge = (kMode == FIN_FULL) && F.merge.mailboxes != nullptr && F.merge.wait != 0;
     unsigned long long mstep = 0ull;
-    unsigned long long* push_counter = nullptr;
+    int mpar = 0;
+    int brow = b;                                              // row index inside a split's partial arrays
     if (peer_push || peer_merge) {
         const PeerMerge& M = F.merge;
         mstep = *reinterpret_cast<volatile unsigned long long*>(M.mstate);
-        const int par = (int)(mstep & 1ull);
+        mpar = (int)(mstep & 1ull);
+        const size_t Bg = (size_t)M.W * M.Bl;
         if (peer_push) {
-            // row b belongs to rank b / Bl: its merged partial (relative to its max) is stored straight into the owner's mailbox
-            const int owner = b / M.Bl, lr = b - owner * M.Bl;
-            float* base = pm_slot(M.mailboxes[owner], M, par, M.rank);
-            out_row = F.part_acc ? base + (size_t)lr * M.d : nullptr;
-            o_max = base + (size_t)M.Bl * M.d + lr; o_sum = o_max + M.Bl; o_cnt = reinterpret_cast<int*>(o_sum + M.Bl);
-            push_counter = pm_counter(M.mailboxes[owner], M, par, M.rank);
+            // the merged partial of global row b (relative to its max) goes into this rank's own rows block
+            float* base = pm_rows(M.mailboxes[M.rank], M, mpar);
+            out_row = F.part_acc ? base + (size_t)b * M.d : nullptr;
+            o_max = base + Bg * M.d + b; o_sum = o_max + Bg; o_cnt = reinterpret_cast<int*>(o_sum + Bg);
         } else {
-            // the W sources' partials of my row sit in my own mailbox: wait for all of their rows of this step
+            // wait until every rank has published its rows block of this step, then pull my row from each of them
             int ok = 1;
-            if (tid < M.W) ok = pm_wait(M, par, tid, ((mstep >> 1) + 1ull) * (unsigned long long)M.Bl) ? 1 : 0;
+            if (tid < M.W) ok = pm_wait(M, mpar, tid, mstep) ? 1 : 0;
             (void)__syncthreads_and(ok);                       // on a timeout mstate[2] is raised (sticky) and the row is garbage
-            const float* base = pm_slot(M.mailboxes[M.rank], M, par, 0);
-            p_acc = F.dq ? base : nullptr; p_max = base + (size_t)M.Bl * M.d; p_sum = p_max + M.Bl;
-            p_cnt = reinterpret_cast<const int*>(p_sum + M.Bl);
-            stride = sstride = pm_slot_floats(M);
+            brow = M.rank * M.Bl + b;
             ns = M.W;
         }
     }
+    // base pointers of split sp: accumulator rows, max / sum / count arrays
+    auto acc_of = [&](int sp) -> const float* {
+        return peer_merge ? pm_rows(F.merge.mailboxes[sp], F.merge, mpar) : p_acc + (size_t)sp * stride;
+    };
+    auto max_of = [&](int sp) -> const float* {
+        return peer_merge ? pm_rows(F.merge.mailboxes[sp], F.merge, mpar) + (size_t)F.merge.W * F.merge.Bl * F.merge.d
+                          : p_max + (size_t)sp * sstride;
+    };
+    const size_t stat_gap = peer_merge ? (size_t)F.merge.W * F.merge.Bl : 0;     // merge: max -> sum -> count arrays of a block
+    if (peer_merge) p_acc = F.dq ? reinterpret_cast<const float*>(F.merge.mailboxes) : nullptr;      // (non-null marker only)
     const bool want_acc = (out_row != nullptr && p_acc != nullptr);
 
     // Loads first, arithmetic later: warp 0 puts the split statistics of its row in flight (they head the memory queue),
@@ -183,29 +190,30 @@ infonce_finalize_kernel(const FinalizeParams F)
 #pragma unroll
         for (int i = 0; i < FIN_STAT; ++i) {
             const int sp = lane + 32 * i;
-            const size_t o = (size_t)(sp < ns ? sp : 0) * sstride + b;
-            st_m[i] = (sp < ns) ? __ldcg(p_max + o) : -INFINITY;
-            st_s[i] = (sp < ns) ? __ldcg(p_sum + o) : 0.f;
-            st_c[i] = (sp < ns) ? __ldcg(p_cnt + o) : 0;
+            const float* pm_ = max_of(sp < ns ? sp : 0) + brow;
+            const float* ps_ = peer_merge ? pm_ + stat_gap : p_sum + (size_t)(sp < ns ? sp : 0) * sstride + brow;
+            const int* pc_ = peer_merge ? reinterpret_cast<const int*>(ps_ + stat_gap) : p_cnt + (size_t)(sp < ns ? sp : 0) * sstride + brow;
+            st_m[i] = (sp < ns) ? ld_part(pm_, peer_merge) : -INFINITY;
+            st_s[i] = (sp < ns) ? ld_part(ps_, peer_merge) : 0.f;
+            st_c[i] = (sp < ns) ? ld_part(pc_, peer_merge) : 0;
         }
     }
     float v[kVec ? 1 : FIN_CHUNK];
     float4 v4[kVec ? FIN_VCH : 1];
     if constexpr (kVec) {
         if (want_acc) {
-            const float4* src4 = reinterpret_cast<const float4*>(p_acc + (size_t)b * FIN_COLS) + lane;
 #pragma unroll
             for (int i = 0; i < FIN_VCH; ++i) {
                 const int sp = warp + i * (FIN_THREADS / 32);
-                v4[i] = (sp < ns) ? __ldcg(src4 + (size_t)sp * (stride / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v4[i] = (sp < ns) ? ld_part(reinterpret_cast<const float4*>(acc_of(sp) + (size_t)brow * FIN_COLS) + lane, peer_merge)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     } else if (want_acc && col < F.d) {
-        const float* src = p_acc + (size_t)b * F.d + col;
 #pragma unroll
         for (int i = 0; i < FIN_CHUNK; ++i) {
             const int sp = grp + i * FIN_GROUPS;
-            v[i] = (sp < ns) ? __ldcg(src + sp * stride) : 0.f;
+            v[i] = (sp < ns) ? ld_part(acc_of(sp) + (size_t)brow * F.d + col, peer_merge) : 0.f;
         }
     }
 
@@ -234,16 +242,18 @@ infonce_finalize_kernel(const FinalizeParams F)
                     cnt += st_c[i];
                 }
             } else {                                           // many splits: two dependent passes over the statistics
-                for (int sp = lane; sp < ns; sp += 32) m = fmaxf(m, __ldcg(p_max + (size_t)sp * sstride + b));
+                for (int sp = lane; sp < ns; sp += 32) m = fmaxf(m, ld_part(max_of(sp) + brow, peer_merge));
                 m = warp_max(m);
                 if (kMode == FIN_FULL) m = fmaxf(m, pos);
                 for (int sp = lane; sp < ns; sp += 32) {
-                    const size_t o = (size_t)sp * sstride + b;
-                    const float pm = __ldcg(p_max + o);
+                    const float* pm_ = max_of(sp) + brow;
+                    const float* ps_ = peer_merge ? pm_ + stat_gap : p_sum + (size_t)sp * sstride + brow;
+                    const int* pc_ = peer_merge ? reinterpret_cast<const int*>(ps_ + stat_gap) : p_cnt + (size_t)sp * sstride + brow;
+                    const float pm = ld_part(pm_, peer_merge);
                     const float e = (pm == -INFINITY) ? 0.f : __expf(pm - m);
                     w_s[sp] = e;
-                    part += __ldcg(p_sum + o) * e;
-                    cnt += __ldcg(p_cnt + o);
+                    part += ld_part(ps_, peer_merge) * e;
+                    cnt += ld_part(pc_, peer_merge);
                 }
             }
             float S = warp_sum(part);
@@ -315,13 +325,12 @@ infonce_finalize_kernel(const FinalizeParams F)
             } else {
             float a = 0.f;
             if (c < F.d) {
-                const float* src = p_acc + (size_t)b * F.d + c;
                 for (int base = 0; base < ns; base += FIN_CHUNK * FIN_GROUPS) {
                     if (c0 > 0 || base > 0) {                  // beyond what was preloaded above
 #pragma unroll
                         for (int i = 0; i < FIN_CHUNK; ++i) {
                             const int sp = base + grp + i * FIN_GROUPS;
-                            v[i] = (sp < ns) ? __ldcg(src + sp * stride) : 0.f;
+                            v[i] = (sp < ns) ? ld_part(acc_of(sp) + (size_t)brow * F.d + c, peer_merge) : 0.f;
                         }
                     }
 #pragma unroll
@@ -355,13 +364,20 @@ infonce_finalize_kernel(const FinalizeParams F)
         }
     }
     if (peer_push) {
-        // every thread's remote stores of this row are ordered before thread 0's system-scope release (bar.sync + fence:
-        // cumulativity, as in xchg_push_slice); the owner counts rows per source rank
+        // last CTA of the launch (ticket): every row of this rank's block is written -> publish the step to every peer with one
+        // system-scope release store each (the fence + ticket orders the other CTAs' rows before it: cumulativity)
+        __shared__ int last_cta;
         __syncthreads();
         if (tid == 0) {
-            __threadfence_system();
-            red_release_sys_add_u64(push_counter, 1ull);
-            if (F.timebuf) atomicMax(F.timebuf + 32 * 1000 + 3, globaltimer_ns());      // bring-up only
+            __threadfence();
+            last_cta = (atomicAdd(F.merge.mstate + 1, 1ull) == (unsigned long long)gridDim.x - 1ull);
+        }
+        __syncthreads();
+        if (last_cta) {
+            if (tid == 0) { F.merge.mstate[1] = 0ull; __threadfence(); }
+            __syncthreads();
+            if (tid < F.merge.W) st_release_sys_u64(pm_flag(F.merge.mailboxes[tid], F.merge, mpar, F.merge.rank), mstep + 1ull);
+            if (F.timebuf && tid == 0) atomicMax(F.timebuf + 32 * 1000 + 3, globaltimer_ns());      // bring-up only
         }
         return;
     }

@@ -199,7 +199,9 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
     F.nsplit = ws.nsplit; F.Bpad = ws.Bpad;
     F.range_checked = (pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05 && logits_out == nullptr) ? 1 : 0;
     if (keys_ready_event) GCA_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)keys_ready_event, 0));
-    return infonce_finalize_launch(F, FIN_FULL, st);
+    rc = infonce_finalize_launch(F, FIN_FULL, st);
+    if (rc == GCA_OK && px && pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05) rc = keys_push_join(st);   // the side-stream key push
+    return rc;
 }
 
 extern "C" int gca_infonce_fwd(const float* q, const float* k, const void* queue, int dtype_queue, int B, long long K,
@@ -316,9 +318,9 @@ extern "C" size_t gca_shard_peer_bytes(int B_loc, int d, int W)
 {
     if (B_loc <= 0 || d <= 0 || W <= 0) return 0;
     const size_t gather = gca_keys_exchange_bytes(2 * B_loc, d, W);
-    const size_t slots = (size_t)2 * W * B_loc * (size_t)(d + 4) * sizeof(float);
-    const size_t counters = (size_t)2 * W * sizeof(unsigned long long);
-    return gather + gca::align_up(slots + counters, 256);
+    const size_t rows = (size_t)2 * W * B_loc * (size_t)(d + 4) * sizeof(float);       // [2 parities][Bg * (d + 4)]
+    const size_t flags = (size_t)2 * W * sizeof(unsigned long long);
+    return gather + gca::align_up(rows + flags, 256);
 }
 
 extern "C" int gca_shard_step_peer(const float* qk_loc, void* shard, int dtype_queue, int B_loc, long long K, int d,

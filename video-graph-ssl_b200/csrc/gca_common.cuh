@@ -53,7 +53,7 @@ struct InfoNceWs {
 // Key all-gather through peer "mailboxes" (exchange.cu has the protocol): either a stand-alone kernel
 // (gca_keys_exchange) or fused into the head step -- pushed by extra CTAs of the prep kernel, consumed directly by the
 // enqueue CTAs of the finalize kernel (gca_moco_step_peer).  mailboxes == nullptr: off.
-constexpr int XCHG_SLICES = 4;
+constexpr int XCHG_SLICES = 8;
 struct PeerXchg {
     char* const* mailboxes;          // device array [W]: every rank's mailbox as mapped into this process
     int W, rank;
@@ -62,25 +62,29 @@ struct PeerXchg {
     unsigned long long timeout_ns;   // 0 = wait for ever
 };
 
-// Cross-rank merge of the K-sharded step through the same kind of mailbox (finalize.cu).  Region of every rank's mailbox at
-// byte offset `off`:   slots [2 parities][W source ranks][Bl * (d + 4) floats]   then   counters [2][W] (u64)
-// A slot holds one source rank's partials of the OWNER's Bl rows: acc [Bl, d], then max [Bl], sum [Bl], count [Bl] (int
-// bits), pad [Bl].  Step s uses parity s & 1 (the q|k gather at the head of every step keeps the ranks within one step of
-// each other).  Every row CTA of the source's FIN_SHARD launch stores its row remotely and adds 1 (release, system scope) to
-// counter[par][source] in the owner's mailbox; the owner's merge CTAs wait for ((s >> 1) + 1) * Bl rows from every source.
+// Cross-rank merge of the K-sharded step over peer memory (finalize.cu).  Region of every rank's mailbox at byte offset `off`:
+//     rows [2 parities][Bg * (d + 4) floats]   then   flags [2][W] (u64),          Bg = W * Bl
+// A rows block holds THIS rank's merged partials of all Bg global rows against its shard: acc [Bg, d], then max [Bg],
+// sum [Bg], count [Bg] (int bits), pad [Bg].  Step s uses parity s & 1 (the q|k gather at the head of every step keeps the
+// ranks within one step of each other).  The split-merge launch (FIN_SHARD) writes the block locally; its last CTA (ticket)
+// publishes flag[par][rank] = s + 1 into every peer's mailbox -- ONE system-scope release per rank and step.  The merge CTA of
+// a local row waits for the W flags in its own mailbox and then PULLS that row's W partials straight from the peers'
+// mailboxes (remote loads over NVLink, all in flight at once) and merges them in rank order.
 struct PeerMerge {
     char* const* mailboxes;          // device array [W]; nullptr = off
     unsigned long long off;          // byte offset of the merge region inside every mailbox
     int W, rank, Bl, d;
-    unsigned long long* mstate;      // device memory: [0] merge step counter, [2] timeout flag
+    unsigned long long* mstate;      // device memory: [0] merge step counter, [1] ticket, [2] timeout flag
     unsigned long long* gather_state;   // non-null: the q|k gather rode in the prep launch; its step counter advances with mstate
     unsigned long long timeout_ns;   // 0 = wait for ever
-    int wait;                        // FIN_FULL launch: wait for the W sources, then merge them
+    int wait;                        // FIN_FULL launch: wait for the W ranks' flags, then pull and merge their partials
 };
 
 static inline int infonce_bpad(int B) { return (B + 127) / 128 * 128; }
 // upper bound on the number of K-splits any kernel family uses (2 CTAs worth per SM, at least 1)
 int infonce_max_splits(int B);
+int keys_push_fork(const float* keys_local, const PeerXchg& X, cudaStream_t st);              // exchange.cu: side-stream push ...
+int keys_push_join(cudaStream_t st);                                                          // ... joined after the step's last launch
 int keys_exchange_launch(const float* keys_local, int B, int d, int W, int rank, void* const* mailboxes, float* all_k,
                          long long* xstate, int timeout_ms, int parts, cudaStream_t st);      // exchange.cu
 InfoNceWs infonce_ws_carve(void* base, int B, int d, int nsplit);
@@ -159,10 +163,8 @@ __device__ __forceinline__ void xchg_push_slice(const PeerXchg& X, const float4*
     float4* dst = xchg_slot(peer, X, par, X.rank);
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = __ldg(keys_local + i);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        st_release_sys_u64(xchg_flag(peer, X, par, X.rank, c), step + 1);
-    }
+    // (st.release.sys is itself a system-scope release: no separate fence in front of it)
+    if (threadIdx.x == 0) st_release_sys_u64(xchg_flag(peer, X, par, X.rank, c), step + 1);
 }
 // One thread: wait until slice c of rank p's keys for `step` has landed in my mailbox.  Returns false on timeout.
 __device__ __forceinline__ bool xchg_wait_slice(const PeerXchg& X, unsigned long long step, int p, int c)
@@ -177,26 +179,42 @@ __device__ __forceinline__ bool xchg_wait_slice(const PeerXchg& X, unsigned long
 }
 
 // ---- cross-rank merge region (PeerMerge)
-__device__ __forceinline__ size_t pm_slot_floats(const PeerMerge& M) { return (size_t)M.Bl * (size_t)(M.d + 4); }
-__device__ __forceinline__ float* pm_slot(char* box, const PeerMerge& M, int par, int from) {
-    return reinterpret_cast<float*>(box + M.off) + ((size_t)par * M.W + from) * pm_slot_floats(M);
+__device__ __forceinline__ size_t pm_block_floats(const PeerMerge& M) { return (size_t)M.W * M.Bl * (size_t)(M.d + 4); }
+__device__ __forceinline__ float* pm_rows(char* box, const PeerMerge& M, int par) {
+    return reinterpret_cast<float*>(box + M.off) + (size_t)par * pm_block_floats(M);
 }
-__device__ __forceinline__ unsigned long long* pm_counter(char* box, const PeerMerge& M, int par, int from) {
-    return reinterpret_cast<unsigned long long*>(box + M.off + (size_t)2 * M.W * pm_slot_floats(M) * sizeof(float)) + (size_t)par * M.W + from;
+__device__ __forceinline__ unsigned long long* pm_flag(char* box, const PeerMerge& M, int par, int from) {
+    return reinterpret_cast<unsigned long long*>(box + M.off + (size_t)2 * pm_block_floats(M) * sizeof(float)) + (size_t)par * M.W + from;
 }
-__device__ __forceinline__ void red_release_sys_add_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// One thread: wait until source rank `from` has delivered `need` rows (monotone counter) into my mailbox.  False on timeout.
-__device__ __forceinline__ bool pm_wait(const PeerMerge& M, int par, int from, unsigned long long need)
+// One thread: wait until rank `from` has published its partials of `step` into my mailbox.  False on timeout.
+__device__ __forceinline__ bool pm_wait(const PeerMerge& M, int par, int from, unsigned long long step)
 {
-    const unsigned long long* f = pm_counter(M.mailboxes[M.rank], M, par, from);
-    if (ld_acquire_sys_u64(f) >= need) return true;
+    const unsigned long long* f = pm_flag(M.mailboxes[M.rank], M, par, from);
+    if (ld_acquire_sys_u64(f) >= step + 1) return true;
     const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys_u64(f) < need) {
+    while (ld_acquire_sys_u64(f) < step + 1) {
         if (M.timeout_ns && globaltimer_ns() - t0 > M.timeout_ns) { atomicExch(M.mstate + 2, 1ull); return false; }
     }
     return true;
+}
+// loads of split partials: L2 (same GPU) or system-scope relaxed (a peer's mailbox over NVLink)
+__device__ __forceinline__ float ld_part(const float* p, bool remote) {
+    if (!remote) return __ldcg(p);
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_part(const int* p, bool remote) {
+    if (!remote) return __ldcg(p);
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_part(const float4* p, bool remote) {
+    if (!remote) return __ldcg(p);
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ float ld_queue(const float* p) { return *p; }

@@ -471,11 +471,10 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
         const int p = row / gather_Bl, lr = row - p * gather_Bl;
         const int per = (X.n4 + XCHG_SLICES - 1) / XCHG_SLICES;
         const int iq = lr * (TC_D / 4), ik = (gather_Bl + lr) * (TC_D / 4);
-        if (lane == 0) {
-            xchg_wait_slice(X, step, p, iq / per);
-            xchg_wait_slice(X, step, p, (iq + TC_D / 4 - 1) / per);
-            xchg_wait_slice(X, step, p, ik / per);
-            xchg_wait_slice(X, step, p, (ik + TC_D / 4 - 1) / per);
+        // (four lanes poll the slices of the two rows side by side: one flag round trip instead of four)
+        if (lane < 4) {
+            const int i0 = (lane & 2) ? ik : iq;
+            xchg_wait_slice(X, step, p, ((lane & 1) ? i0 + TC_D / 4 - 1 : i0) / per);
         }
         __syncwarp();
         const float4* slot = xchg_slot(X.mailboxes[X.rank], X, (int)(step & 1ull), p);
@@ -600,7 +599,16 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
     const bool use_tcx = P.part_acc != nullptr && !fixed_max && P.logits_out == nullptr && infonce_tcx_enabled();
     if (!P.skip_prep) {
         const int nprep = (P.Bpad + 7) / 8;
-        const int npush = P.xchg.mailboxes ? P.xchg.W * XCHG_SLICES : 0;
+        // peer exchange: the q|k gather of the K-sharded step rides in this launch (its rows are needed by this very launch);
+        // the key push of the replica step goes out as its own small launch on a side stream (joined by the caller after the
+        // step's last launch, gca_api.cu)
+        const bool gather = P.xchg.mailboxes != nullptr && P.gather_Bl > 0;
+        const bool push_first = P.xchg.mailboxes != nullptr && !gather;
+        const int npush = gather ? P.xchg.W * XCHG_SLICES : 0;
+        if (push_first) {
+            rc = keys_push_fork(P.k, P.xchg, st);
+            if (rc != GCA_OK) return rc;
+        }
         // queue head to prefetch into L2 (at most 32 MB; GCA_NO_L2PF=1 turns it off for A/B timing)
         static int pf_on = -1;
         if (pf_on < 0) { const char* e = getenv("GCA_NO_L2PF"); pf_on = (e && e[0] == '1') ? 0 : 1; }
@@ -608,11 +616,17 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
         const unsigned long long pf_waves = 2ull * (unsigned long long)P.nsplit * TC_STAGE_BYTES;   // tiles 0 and 1 of every split
         if (pf_bytes > pf_waves) pf_bytes = pf_waves;
         if ((unsigned long long)nprep * 256ull * 32768ull < pf_bytes) pf_bytes = (unsigned long long)nprep * 256ull * 32768ull;
-        infonce_prep_kernel<<<nprep + npush, 256, 0, st>>>(P.q, P.k, P.B, P.Bpad, P.inv_T, (__nv_bfloat16*)P.q_bf16_ws,
-                                                           P.pos_ws, P.pos_out, debug_timebuf(), P.xchg, nprep, P.counter + 6,
-                                                           P.k_hat, P.inv_nq, P.normalize,
-                                                           pf_on ? (const char*)P.queue : nullptr, pf_bytes,
-                                                           P.q_scale, npush, P.gather_Bl);
+        cudaLaunchConfig_t pcfg{};
+        pcfg.gridDim = dim3(nprep + npush); pcfg.blockDim = dim3(256); pcfg.dynamicSmemBytes = 0; pcfg.stream = st;
+        cudaLaunchAttribute pattr[1];
+        pattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pattr[0].val.programmaticStreamSerializationAllowed = 1;
+        pcfg.attrs = pattr; pcfg.numAttrs = 0;
+        GCA_CUDA(cudaLaunchKernelEx(&pcfg, infonce_prep_kernel, P.q, P.k, P.B, P.Bpad, P.inv_T, (__nv_bfloat16*)P.q_bf16_ws,
+                                    P.pos_ws, P.pos_out, debug_timebuf(), P.xchg, nprep, P.counter + 6,
+                                    P.k_hat, P.inv_nq, P.normalize,
+                                    pf_on ? (const char*)P.queue : (const char*)nullptr, pf_bytes,
+                                    P.q_scale, npush, P.gather_Bl));
         GCA_LAUNCH_CHECK("infonce_prep_kernel");
         count_launch(1);
     }
