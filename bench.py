@@ -214,9 +214,12 @@ def secondary_measurements(dev, flush, pk):
     q, k = unit(B), unit(B)
     try:
         mem32 = unit(K)
-        ms = _time_graph(lambda: GF.infonce_forward(q, k, mem32, T, algo="ffma", want_grad=True), flush, iters=8, warm=2)
-        out["fp32_mode"] = {"what": "fused head, fp32 queue + fp32 FMA arithmetic (1e-5 parity mode), B=256 K=65536", "ms": ms,
-                            "steps_per_s": 1e3 / ms, "tflops_fp32": 4.0 * B * K * D / (ms * 1e-3) / 1e12}
+        ms = _time_graph(lambda: GF.infonce_forward(q, k, mem32, T, algo="tc32", want_grad=True), flush, iters=12, warm=3)
+        ms_ffma = _time_graph(lambda: GF.infonce_forward(q, k, mem32, T, algo="ffma", want_grad=True), flush, iters=6, warm=2)
+        out["fp32_mode"] = {"what": "fused head, fp32 queue, fp32-grade logits on tcgen05 (GCA_ALGO_TC32: exact 3-way bf16 split, 6 piece "
+                                    "products per logit; 1e-5 parity mode), B=256 K=65536; includes the per-call split of the queue",
+                            "ms": ms, "steps_per_s": 1e3 / ms, "tflops_bf16_mma": (6 * 2 + 2) * B * K * D / (ms * 1e-3) / 1e12,
+                            "cuda_core_ffma_ms": ms_ffma}
         del mem32
     except Exception as e:                                   # a secondary figure must never take the headline down
         out["fp32_mode"] = {"error": "%s: %s" % (type(e).__name__, e)}

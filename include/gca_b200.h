@@ -38,9 +38,13 @@ extern "C" {
 #define GCA_BF16 1
 
 /* kernel family for the InfoNCE stream */
-#define GCA_ALGO_AUTO    0   /* tcgen05 when (bf16 queue, d == 128), else ffma */
+#define GCA_ALGO_AUTO    0   /* d == 128: tcgen05 (bf16 queue) or tc32 (fp32 queue); other widths, materialised logits, two-pass backward: ffma */
 #define GCA_ALGO_FFMA    1   /* CUDA-core fp32 FMA, exact fp32 arithmetic (parity mode), any d % 32 == 0, d <= 1024 */
 #define GCA_ALGO_TCGEN05 2   /* TMA -> smem -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM); bf16 queue, d == 128 */
+#define GCA_ALGO_TC32    3   /* fp32 queue, d == 128, fp32-grade logits on tcgen05: exact 3-way bf16 split of q and the queue, six
+                                piece products per logit in one fp32 TMEM accumulator (loss within 1e-5 of the reference's fp32
+                                arithmetic); the gradient accumulates bf16 pieces (<= 1e-2).  gca_infonce_fwd / gca_moco_step only;
+                                the workspace grows by 6 * K * d bytes (gca_infonce_workspace_bytes with this algo) */
 
 /* ranks are exact below this value when the caller asks for top-k hit counts only (rank_gt == NULL) */
 #define GCA_TOPK_RANK_CAP 8

@@ -90,7 +90,7 @@ def main():
             err = float((gp.dq.cpu().double() - o["dq"]).abs().max() / o["dq"].abs().max())
             assert err <= gtol, (step, err)
         assert gs.launches_per_step >= 5
-    assert gp.launches_per_step == 4, gp.launches_per_step
+    assert gp.launches_per_step in (4, 6), gp.launches_per_step      # bf16: 4; fp32 (tc32 + stand-alone gather): 6
     dist.barrier()
     torch.cuda.synchronize()
     if rank == 0:

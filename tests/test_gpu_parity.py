@@ -17,6 +17,9 @@ pytestmark = pytest.mark.gpu
 LOSS_RTOL_FP32 = 1e-5
 LOSS_RTOL_BF16 = 2e-3
 GRAD_RTOL = 1e-2
+# fp32 mode at d == 128 (GCA_ALGO_TC32): fp32-grade logits on the tensor cores (six bf16 piece products), the gradient
+# accumulates two pieces of each factor (error ~2^-17): the same bar as the CUDA-core kernel (algo="ffma")
+GRAD_RTOL_FP32_TC = 1e-4
 
 
 def T_(a):
@@ -157,6 +160,37 @@ def test_infonce_ffma_sweep(GF, B, K, d, qdtype):
     ok = margin > 3e-5                                   # fp32 noise of a logit of magnitude <= 1/T
     assert ok.float().mean() >= 0.4
     assert torch.equal(r["rank"].cpu().long()[ok], o["rank"][ok])
+
+
+@pytest.mark.parametrize("B,K", [(64, 1024), (130, 1000), (32, 4096), (256, 65536)])
+def test_infonce_tc32_fp32_grade_on_tensor_cores(GF, B, K):
+    """GCA_ALGO_TC32: the fp32 parity mode on tcgen05 (exact 3-way bf16 split of q and the fp32 queue, six piece products
+    per logit).  Loss / lse within the fp32-mode bar of BASELINE.json (1e-5) against the fp64 oracle on the SAME fp32
+    inputs, gradient within 1e-4 (two bf16 pieces of P and of the queue), rank exact away from fp32-noise ties; ragged K (tile tail crosses into
+    the next plane of the split) and B (padding rows)."""
+    torch.manual_seed(B + K)
+    T = 0.07
+    mem = F.normalize(torch.randn(K, 128))
+    q, k = F.normalize(torch.randn(B, 128)), F.normalize(torch.randn(B, 128))
+    r, o = check_infonce(GF, q, k, mem, T, "tc32", LOSS_RTOL_FP32, GRAD_RTOL)
+    assert rel_max(r["dq_unit"], o["dq"]) <= 1e-4
+    neg = oracle.logits_full(q.double(), k.double(), mem.double(), T)[:, 1:]
+    pos = ((q.double() * k.double()).sum(1) / T)[:, None]
+    ok = (neg - pos).abs().min(1).values > 3e-5
+    assert int(ok.sum()) >= min(B // 2, 32)
+    assert torch.equal(r["rank"].cpu().long()[ok], (neg > pos).sum(1)[ok])
+    # same call through the ffma family: the two fp32 modes agree far inside the bar
+    r2 = GF.infonce_forward(cu(q), cu(k), cu(mem), T, algo="ffma", want_grad=True)
+    assert abs(float(r["loss"]) - float(r2["loss"])) <= 2e-6 * abs(float(r2["loss"]))
+
+
+def test_infonce_tc32_unnormalised_inputs_take_the_exact_max_pass(GF):
+    """Rows far from unit norm leave the fixed-reference window: the CTA redoes its keys with the exact row max."""
+    torch.manual_seed(9)
+    B, K, T = 96, 2048, 0.07
+    mem = torch.randn(K, 128) * 1.5
+    q, k = torch.randn(B, 128) * 2.0, torch.randn(B, 128)
+    check_infonce(GF, q, k, mem, T, "tc32", LOSS_RTOL_FP32, GRAD_RTOL)
 
 
 def test_infonce_ffma_unnormalised_inputs(GF):
@@ -451,7 +485,7 @@ def test_rgbmoco_module_steps_like_reference(lib, golden, queue_dtype):
     moco = gca_b200.RGBMoCo(128, K=256, T=float(g["T"]), queue_dtype=queue_dtype).cuda()
     moco.load_state_dict({"memory": T_(g["memory_before"])})
     crit = gca_b200.NCESoftmaxLoss()
-    ltol, gtol = (LOSS_RTOL_FP32, 1e-3) if queue_dtype == "fp32" else (LOSS_RTOL_BF16, GRAD_RTOL)
+    ltol, gtol = (LOSS_RTOL_FP32, GRAD_RTOL_FP32_TC) if queue_dtype == "fp32" else (LOSS_RTOL_BF16, GRAD_RTOL)
     for st in range(int(g["steps"])):
         q = cu(T_(g[f"q{st}"])).requires_grad_(True)
         k = cu(T_(g[f"k{st}"]))
@@ -496,7 +530,7 @@ def test_rgbmoco_jig_head_against_reference_fixture(lib, golden, queue_dtype):
     moco = gca_b200.RGBMoCo(128, K=int(j["K"]), T=float(j["T"]), queue_dtype=queue_dtype).cuda()
     moco.load_state_dict({"memory": T_(j["memory_before"])})
     crit = gca_b200.NCESoftmaxLoss()
-    ltol, gtol = (LOSS_RTOL_FP32, 1e-4) if queue_dtype == "fp32" else (LOSS_RTOL_BF16, GRAD_RTOL)
+    ltol, gtol = (LOSS_RTOL_FP32, GRAD_RTOL_FP32_TC) if queue_dtype == "fp32" else (LOSS_RTOL_BF16, GRAD_RTOL)
     for st in range(int(j["steps"])):
         q, qj = cu(T_(j[f"q{st}"])).requires_grad_(True), cu(T_(j[f"q_jig{st}"])).requires_grad_(True)
         out, out_jig, labels = moco(q, cu(T_(j[f"k{st}"])), q_jig=qj)
@@ -522,7 +556,7 @@ def test_cmcmoco_against_reference_fixture(lib, golden, queue_dtype):
     m.load_state_dict({"memory_1": T_(g["memory_1_before"]), "memory_2": T_(g["memory_2_before"])})
     m.index = int(g["start_index"])
     crit = gca_b200.NCESoftmaxLoss()
-    ltol, gtol = (LOSS_RTOL_FP32, 1e-4) if queue_dtype == "fp32" else (LOSS_RTOL_BF16, GRAD_RTOL)
+    ltol, gtol = (LOSS_RTOL_FP32, GRAD_RTOL_FP32_TC) if queue_dtype == "fp32" else (LOSS_RTOL_BF16, GRAD_RTOL)
     for st in range(int(g["steps"])):
         nh = 4 if f"q{st}_3" in g else 2
         qs = [cu(T_(g[f"q{st}_{i}"])).requires_grad_(True) for i in range(nh)]
@@ -779,7 +813,7 @@ def test_graphed_step_matches_oracle_over_a_lap(lib, queue_dtype, B, N, K):
     idx = moco.index
     step = GraphedMoCoStep(moco, B, N).capture()
     # bf16 (tcgen05): prep + streaming kernel + finalize (with the enqueue riding in it); fp32 (ffma family): no prep launch
-    assert step.launches_per_step == (3 if queue_dtype == "bf16" else 2)
+    assert step.launches_per_step == (3 if queue_dtype == "bf16" else (4 if moco.memory.shape[1] == 128 else 2))
     for it in range(K // N + 3):
         q, k, all_k = unit_rows(B, 128, gen), unit_rows(B, 128, gen), unit_rows(N, 128, gen)
         prev_mem = ref_mem.clone()

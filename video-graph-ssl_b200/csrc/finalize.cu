@@ -59,6 +59,7 @@ __device__ __forceinline__ void enqueue_rows(const FinalizeParams& F, int blk, i
         int ok = 1;
         if ((int)threadIdx.x < F.xchg.W * XCHG_SLICES)
             ok = xchg_wait_slice(F.xchg, xstep, threadIdx.x / XCHG_SLICES, threadIdx.x % XCHG_SLICES) ? 1 : 0;
+        if (F.timebuf && threadIdx.x == 0) atomicMax(F.timebuf + 32 * 1000 + 6, globaltimer_ns());   // bring-up only: flags seen
         // a peer that did not deliver within the timeout (xstate[2] is raised, sticky): this CTA writes nothing -- the mailbox
         // holds stale rows -- and the last CTA below leaves the ring pointer where it was.  The step's loss and gradient do not
         // depend on the gathered keys; the caller polls the flag (PeerKeyExchange.check(), GraphedReplicaStep.step()).
@@ -101,6 +102,7 @@ __device__ __forceinline__ void enqueue_rows(const FinalizeParams& F, int blk, i
             if (peer) F.xchg.xstate[0] = xstep + 1;       // every enqueue CTA has read the step before taking its ticket
         }
     }
+    if (F.timebuf && threadIdx.x == 0) atomicMax(F.timebuf + 32 * 1000 + 5, globaltimer_ns());       // bring-up only
 }
 
 // kVec (d == 128, <= 8 * FIN_VCH splits: the tcgen05 family at its usual sizes): every warp reads whole 512-byte partial rows

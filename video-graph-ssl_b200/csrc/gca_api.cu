@@ -71,7 +71,8 @@ InfoNceWs infonce_ws_carve(void* base, int B, int d, int nsplit)
 
 static int pick_algo(int algo, int dtype_queue, int d)
 {
-    if (algo == GCA_ALGO_AUTO) return (dtype_queue == GCA_BF16 && d == 128) ? GCA_ALGO_TCGEN05 : GCA_ALGO_FFMA;
+    // d == 128 runs on the tensor cores in either queue precision; other widths keep the CUDA-core fp32 kernel
+    if (algo == GCA_ALGO_AUTO) return d != 128 ? GCA_ALGO_FFMA : (dtype_queue == GCA_BF16 ? GCA_ALGO_TCGEN05 : GCA_ALGO_TC32);
     return algo;
 }
 
@@ -82,11 +83,15 @@ static int check_infonce_args(const char* fn, const void* q, const void* k, cons
     GCA_CHECK_ARG(dtype_queue == GCA_F32 || dtype_queue == GCA_BF16, "%s: bad dtype_queue %d", fn, dtype_queue);
     GCA_CHECK_ARG(B >= 1 && K >= 1, "%s: need B >= 1 and K >= 1 (B=%d K=%lld)", fn, B, K);
     GCA_CHECK_ARG(inv_T > 0.f, "%s: inv_T must be > 0", fn);
-    GCA_CHECK_ARG(algo == GCA_ALGO_AUTO || algo == GCA_ALGO_FFMA || algo == GCA_ALGO_TCGEN05, "%s: bad algo %d", fn, algo);
+    GCA_CHECK_ARG(algo == GCA_ALGO_AUTO || algo == GCA_ALGO_FFMA || algo == GCA_ALGO_TCGEN05 || algo == GCA_ALGO_TC32,
+                  "%s: bad algo %d", fn, algo);
     const int a = pick_algo(algo, dtype_queue, d);
     if (a == GCA_ALGO_TCGEN05) {
         if (dtype_queue != GCA_BF16 || d != 128)
             return set_err(GCA_ERR_UNSUPPORTED, "%s: GCA_ALGO_TCGEN05 needs a bf16 queue and d == 128", fn);
+    } else if (a == GCA_ALGO_TC32) {
+        if (dtype_queue != GCA_F32 || d != 128)
+            return set_err(GCA_ERR_UNSUPPORTED, "%s: GCA_ALGO_TC32 needs an fp32 queue and d == 128", fn);
     } else {
         if (d % 32 != 0 || d < 32 || d > 1024)
             return set_err(GCA_ERR_UNSUPPORTED, "%s: GCA_ALGO_FFMA needs d %% 32 == 0 and 32 <= d <= 1024 (d=%d)", fn, d);
@@ -96,6 +101,7 @@ static int check_infonce_args(const char* fn, const void* q, const void* k, cons
 
 static int nsplit_for(int algo, int B, long long K, int d)
 {
+    if (algo == GCA_ALGO_TC32) return infonce_tc32_nsplit(B, K);
     return algo == GCA_ALGO_TCGEN05 ? infonce_tc_nsplit(B, K) : infonce_ffma_nsplit(B, K, d);
 }
 
@@ -110,8 +116,10 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
     if (sm_count_cached() < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
     const int nsplit = nsplit_for(a, B, K, d);
     InfoNceWs ws = infonce_ws_carve(workspace, B, d, nsplit);
-    if (!workspace || workspace_bytes < ws.bytes)
-        return set_err(GCA_ERR_WORKSPACE, "InfoNCE workspace too small: %zu bytes given, %zu needed", workspace_bytes, ws.bytes);
+    const size_t common = align_up(infonce_ws_carve(nullptr, B, d, infonce_max_splits(B)).bytes, 1024);
+    const size_t need = (a == GCA_ALGO_TC32) ? common + infonce_tc32_extra_ws(B, K) : ws.bytes;
+    if (!workspace || workspace_bytes < need)
+        return set_err(GCA_ERR_WORKSPACE, "InfoNCE workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
     InfoNceStreamParams P{};
     P.q = q; P.k = k; P.queue = queue; P.B = B; P.K = K; P.d = d; P.inv_T = inv_T; P.lse_fixed = lse_fixed;
     P.counter = ws.counter; P.part_max = ws.part_max; P.part_sum = ws.part_sum; P.part_cnt = ws.part_cnt;
@@ -134,6 +142,7 @@ static int run_stream(const float* q, const float* k, const void* queue, int dty
     }
     *ws_out = ws;
     count_launch(1);
+    if (a == GCA_ALGO_TC32) return infonce_tc32_launch(P, (char*)workspace + common, st);
     if (a == GCA_ALGO_TCGEN05) return infonce_tc_launch(P, lse_fixed != nullptr, st);
     return infonce_ffma_launch(P, dtype_queue, lse_fixed != nullptr, st);
 }
@@ -152,10 +161,13 @@ extern "C" int gca_sm_count(void)
 extern "C" size_t gca_infonce_workspace_bytes(int B, long long K, int d, int dtype_queue, int algo)
 {
     using namespace gca;
-    (void)K; (void)dtype_queue; (void)algo;
+    (void)dtype_queue;
     if (B < 1 || d < 1) return 0;
     // sized for the largest split count any family may choose on this device (so one allocation serves all calls)
-    return infonce_ws_carve(nullptr, B, d, infonce_max_splits(B)).bytes;
+    const size_t common = infonce_ws_carve(nullptr, B, d, infonce_max_splits(B)).bytes;
+    if (pick_algo(algo, dtype_queue, d) == GCA_ALGO_TC32 && K >= 1)
+        return align_up(common, 1024) + infonce_tc32_extra_ws(B, K);                                // + queue / q planes
+    return common;
 }
 
 static int infonce_fwd_impl(const char* fn, const float* q, const float* k, const void* queue, int dtype_queue, int B,
@@ -174,6 +186,8 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
         GCA_CHECK_ARG(enq_N >= 0 && enq_N <= K, "%s: N=%d rows do not fit a ring of %lld slots", fn, enq_N, K);
         GCA_CHECK_ARG(enq_state || (enq_index >= 0 && enq_index < K), "%s: pointer %lld outside [0, %lld)", fn, enq_index, K);
     }
+    if (algo == GCA_ALGO_AUTO && logits_out && pick_algo(algo, dtype_queue, d) == GCA_ALGO_TC32)
+        algo = GCA_ALGO_FFMA;                            // materialised logits: the CUDA-core kernel writes them
     cudaStream_t st = (cudaStream_t)stream;
     InfoNceWs ws;
     FinalizeParams F{};
@@ -191,13 +205,14 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
         const float* kh = k_hat_out ? k_hat_out : ws.k_hat;
         F.k = kh; F.zq = q; F.inv_nq = ws.inv_nq;
         if (F.enq_queue && F.enq_keys == nullptr) F.enq_keys = kh;
-    } else if (pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05) {
+    } else if (pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05 || pick_algo(algo, dtype_queue, d) == GCA_ALGO_TC32) {
         F.k = ws.k_hat;                                  // staged by the prep kernel: k is read once per step
     }
     F.counter = ws.counter; F.part_max = ws.part_max; F.part_sum = ws.part_sum; F.part_cnt = ws.part_cnt;
     F.part_acc = dq_unit ? ws.part_acc : nullptr;
     F.nsplit = ws.nsplit; F.Bpad = ws.Bpad;
-    F.range_checked = (pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05 && logits_out == nullptr) ? 1 : 0;
+    F.range_checked = ((pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05 || pick_algo(algo, dtype_queue, d) == GCA_ALGO_TC32) &&
+                       logits_out == nullptr) ? 1 : 0;
     if (keys_ready_event) GCA_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)keys_ready_event, 0));
     rc = infonce_finalize_launch(F, FIN_FULL, st);
     if (rc == GCA_OK && px && pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05) rc = keys_push_join(st);   // the side-stream key push
@@ -279,6 +294,7 @@ extern "C" int gca_infonce_bwd(const float* q, const float* k, const void* queue
     int rc = check_infonce_args("gca_infonce_bwd", q, k, queue, dtype_queue, B, K, d, inv_T, algo);
     if (rc != GCA_OK) return rc;
     GCA_CHECK_ARG(lse && dq, "gca_infonce_bwd: lse and dq are required");
+    if (algo == GCA_ALGO_AUTO && pick_algo(algo, dtype_queue, d) == GCA_ALGO_TC32) algo = GCA_ALGO_FFMA;   // (no two-pass variant)
     cudaStream_t st = (cudaStream_t)stream;
     InfoNceWs ws;
     // the stream kernel recomputes the positive logits into ws.pos_tmp

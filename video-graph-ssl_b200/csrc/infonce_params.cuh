@@ -47,6 +47,11 @@ int infonce_ffma_launch(const InfoNceStreamParams& P, int dtype_queue, bool fixe
 int infonce_tc_nsplit(int B, long long K);
 int infonce_tc_launch(const InfoNceStreamParams& P, bool fixed_max, cudaStream_t st);
 
+// tcgen05 fp32-grade family (infonce_tc32.cu): `extra` = infonce_tc32_extra_ws() bytes behind the common workspace
+int infonce_tc32_nsplit(int B, long long K);
+size_t infonce_tc32_extra_ws(int B, long long K);
+int infonce_tc32_launch(const InfoNceStreamParams& P, void* extra, cudaStream_t st);
+
 // finalize.cu
 enum FinalizeMode { FIN_FULL = 0, FIN_SHARD = 1, FIN_BWD = 2 };
 struct FinalizeParams {

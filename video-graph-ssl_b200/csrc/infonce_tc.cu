@@ -555,6 +555,22 @@ int get_queue_tmap(const void* queue, long long K, CUtensorMap* out)
     return GCA_OK;
 }
 
+// row-major bf16 [rows, 128] tensor, box = box_rows rows x 64 features, 128-byte swizzle (not cached: callers keep the map)
+int make_bf16_tmap(const void* base, long long rows, int box_rows, CUtensorMap* out)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_err(GCA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)TC_D, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)TC_D * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(GCA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return GCA_OK;
+}
+
 int infonce_tc_nsplit(int B, long long K)
 {
     const int nblk = infonce_bpad(B) / TC_BM;

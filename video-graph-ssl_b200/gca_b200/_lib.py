@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("GCA_B200_LIB") or os.path.join(_HERE, "libgca_b200.so
 
 GCA_OK = 0
 GCA_F32, GCA_BF16 = 0, 1
-ALGO = {"auto": 0, "ffma": 1, "tcgen05": 2}
+ALGO = {"auto": 0, "ffma": 1, "tcgen05": 2, "tc32": 3}
 
 
 class GcaLibraryError(RuntimeError):
