@@ -448,6 +448,7 @@ def run_single(args):
         except (ValueError, OSError):
             pass
     secondary = None if args.no_secondary else secondary_measurements(dev, flush, pk)
+    pretrain = None if args.no_secondary else pretrain_clips(0, 1, dev)
 
     cpu_rate, cpu_ms, cpu_n, cores = cpu_head_rate(60, 2, budget_s=15.0) if not args.no_cpu else (None, None, 0, 0)
     line = {
@@ -476,6 +477,7 @@ def run_single(args):
         "gpu_launches": launches,
         "roofline": roof,
         "secondary": secondary,
+        "pretrain_clips_per_s": pretrain,
         "cpu_baseline": None if args.no_cpu else {
             "value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": cpu_ms,
             "sample": "%d full-size steps (B=%d, K=%d, d=%d, fp32) of the oracle port of the reference step, %s" % (cpu_n, B, K, D, cpu_model())},
@@ -665,6 +667,7 @@ def run_multi(args, rank, world, local_rank):
         sharded = time_sharded_k1m(rank, world, dev, flush)
         if B % world == 0:
             sharded_strong = time_sharded_k1m(rank, world, dev, flush, steps=100, rows_per_gpu=B // world)
+    pretrain = None if args.no_sharded else pretrain_clips(rank, world, dev)
     if rank == 0:
         line = {
             "metric": METRIC, "value": world * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -693,6 +696,7 @@ def run_multi(args, rank, world, local_rank):
             "gpu_launches": launches,
             "sharded_k1m": sharded,
             "sharded_k1m_strong": sharded_strong,
+            "pretrain_clips_per_s": pretrain,
         }
         print(json.dumps(line), flush=True)
     # Leave without tearing the communicator down: destroy_process_group() after NCCL work was captured into CUDA graphs
@@ -702,6 +706,28 @@ def run_multi(args, rank, world, local_rank):
     sys.stdout.flush()
     sys.stderr.flush()
     os._exit(0)
+
+
+def pretrain_clips(rank, world, dev):
+    """BASELINE's second headline figure, pre-train clips/s (config 2: visual_moco.yaml shape, 64 videos/GPU x 2 clips of
+    3x16x112x112, queue 65536, bf16 autocast) with the B200 head + one-launch EMA inside the trainer's step
+    (tools/pretrain_step.py: ShuffleBN all-to-all + DDP at N > 1).  The encoder is a STAND-IN of the R3D-18 shape on cuDNN
+    (the reference's own backbone is not on the GPU box and is outside the hot path): >97 % of this step is library code."""
+    import types
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import pretrain_step as ps
+    args = types.SimpleNamespace(batch=64, K=K, steps=8, warmup=4, quiet=True)
+    torch.backends.cudnn.benchmark = True
+    try:
+        r = ps.run("b200", args, rank, world, dev)
+        torch.cuda.empty_cache()
+        return {"clips_per_s": r["clips_per_s"], "ms_per_step": r["ms_per_step"], "videos_per_gpu": 64, "n_gpus": world,
+                "head_fwd_ms_median": r["head_fwd_ms_median"], "ema_ms": r["ema_ms"],
+                "encoder": "stand-in of the R3D-18 shape (7x7x7 stem, 4 x 2 basic blocks, 512-d, MLP head) on cuDNN, bf16 autocast, "
+                           "random init; synthetic Kinetics-shaped clips"}
+    except Exception as e:                                   # a secondary figure must never take the headline down
+        return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
 _KEEP = []

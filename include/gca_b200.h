@@ -49,8 +49,21 @@ extern "C" {
 /* ranks are exact below this value when the caller asks for top-k hit counts only (rank_gt == NULL) */
 #define GCA_TOPK_RANK_CAP 8
 
-/* graph head flags (0 = the reference's arithmetic) */
+/* graph head flags (0 = the reference's arithmetic).  The variants below have NO counterpart in the reference (SURVEY.md
+ * D5-D7: its only sparsifier is the hop mask, its only augmentation the relaxed Bernoulli, its only normalisation the row
+ * softmax); they are default-OFF options whose parity is UNPINNED -- the checker is our own restatement (oracle/graph.py,
+ * graph_variants).  They apply to the hop-weighted adjacency `adj`, in this order:
+ *   THRESHOLD : adj_ij < tau -> 0                                   (removed like a hop-masked edge)
+ *   TOPK      : keep the topk largest entries of every row (ties towards the lower column), the rest -> 0
+ *   EDGE_DROP : hard seeded edge drop instead of the relaxed Bernoulli: s_ij = adj_ij * [u_ij >= p_drop]
+ *   SYMNORM   : s <- D^-1/2 s D^-1/2, D = diag(row sums of s)       (symmetric normalisation before the aggregation)
+ * Cosine adjacency and the feature mask are compositions around the kernel (gca_b200.ops.TemporalGraphAug). */
 #define GCA_GRAPH_REFERENCE 0u
+#define GCA_GRAPH_THRESHOLD 1u
+#define GCA_GRAPH_TOPK      2u
+#define GCA_GRAPH_EDGE_DROP 4u
+#define GCA_GRAPH_SYMNORM   8u
+typedef struct GcaGraphOpts { unsigned flags; float tau; int topk; float p_drop; } GcaGraphOpts;
 
 int         gca_version(void);
 const char* gca_last_error(void);
@@ -263,6 +276,16 @@ int gca_graph_bwd(const float* gq, const float* gk, int Cq, int S, const float* 
                   float alpha, int max_hop, float temperature, unsigned flags,
                   float* d_gq, float* d_gk, float* d_support,
                   void* workspace, size_t workspace_bytes, void* stream);
+/* The same two calls with the default-OFF variants (opts == NULL or opts->flags == 0: identical to the calls above).
+ * The backward additionally takes the uniforms `u` of the forward (keep mask of EDGE_DROP, pre-normalisation s of SYMNORM). */
+int gca_graph_fwd_ex(const float* gq, const float* gk, int Cq, int S, const float* support, int C, int HW,
+                     int T, int B, const float* u, float alpha, int max_hop, float temperature, const GcaGraphOpts* opts,
+                     float* sim, float* adj, float* s, float* y, void* workspace, size_t workspace_bytes, void* stream);
+int gca_graph_bwd_ex(const float* gq, const float* gk, int Cq, int S, const float* support, int C, int HW,
+                     int T, int B, const float* sim, const float* adj, const float* s, const float* dy, const float* u,
+                     float alpha, int max_hop, float temperature, const GcaGraphOpts* opts,
+                     float* d_gq, float* d_gk, float* d_support,
+                     void* workspace, size_t workspace_bytes, void* stream);
 /* scratch for gca_graph_fwd / gca_graph_bwd (d_logit + per-chunk pair-dot partials; only touched for large feature maps) */
 size_t gca_graph_workspace_bytes(int B, int T);
 

@@ -110,3 +110,40 @@ def graph_forward_backward(x, wq, wk, wg, u, dy, **kw):
     y, _, _, _ = graph_forward(x, ws[0], ws[1], ws[2], u, **kw)
     grads = torch.autograd.grad(y, [x] + ws, dy)
     return (y.detach(),) + tuple(grads)
+
+
+def graph_core_variants(gq, gk, support, u, alpha=0.5, max_hop=3, temperature=1.0, threshold=None, topk=None, edge_drop=None,
+                        symnorm=False):
+    """`graph_core` with the default-OFF variants of include/gca_b200.h (GCA_GRAPH_*).  PARITY UNPINNED: the reference has
+    no thresholded / top-k edges, no hard edge drop and no D^-1/2 A D^-1/2 on its forward path (its
+    compute_ppr, temporal_graph.py:212-219, is dead and broken), so this is OUR statement of north_star's wording, written in
+    differentiable torch ops (autograd provides the backward the kernel is checked against).  Order: hop-weighted adjacency ->
+    threshold -> row top-k (ties towards the lower column) -> relaxed-Bernoulli re-sample | hard edge drop [u >= p] ->
+    symmetric normalisation -> aggregation + skip.  Removed edges become 0 exactly like hop-masked edges."""
+    B, Cq, T, S = gq.shape
+    eps = EPS32                     # the clamps are those of the fp32 path (clamp_probs), whatever precision this runs in
+    Gq = gq.transpose(2, 1).contiguous().view(B, T, -1)
+    Gk = gk.transpose(2, 1).contiguous().view(B, T, -1)
+    sim = F.softmax(torch.matmul(Gq, Gk.permute(0, 2, 1)), dim=-1)
+    adj = sim * edge_weight_matrix(T, max_hop, alpha, sim.dtype)[None]
+    keep = torch.ones_like(adj, dtype=torch.bool)
+    if threshold is not None:
+        keep &= ~(adj < threshold)
+    adj_m = torch.where(keep, adj, torch.zeros_like(adj))
+    if topk is not None:
+        a = adj_m.detach()
+        col = torch.arange(T)
+        better = (a[..., None, :] > a[..., :, None]) | ((a[..., None, :] == a[..., :, None]) & (col[None, :] < col[:, None]))
+        rank = better.sum(-1)                                   # [B, T, T]: entries of the row that come first
+        adj_m = torch.where(rank < topk, adj_m, torch.zeros_like(adj_m))
+    if edge_drop is not None:
+        s = torch.where(u >= edge_drop, adj_m, torch.zeros_like(adj_m))
+    else:
+        p = adj_m.clamp(min=eps, max=1 - eps)
+        uc = u.clamp(min=eps, max=1 - eps)
+        s = torch.sigmoid((uc.log() - (-uc).log1p() + p.log() - (-p).log1p()) / temperature)
+    if symnorm:
+        r = s.sum(-1).clamp(min=eps).rsqrt()
+        s = s * r[:, :, None] * r[:, None, :]
+    y = torch.einsum('bij,bcjs->bcis', s, support) + support
+    return y, sim, adj_m, s

@@ -695,6 +695,65 @@ def test_graph_core_random_shapes(GF, shape, sub):
 
 
 # ============================================================================================ K6 SimSiam D
+VARIANTS = [dict(threshold=0.05), dict(topk=3), dict(edge_drop=0.3), dict(symnorm=True),
+            dict(threshold=0.02, topk=4, symnorm=True), dict(topk=2, edge_drop=0.25, symnorm=True)]
+
+
+@pytest.mark.parametrize("shape", [(3, 16, 8, 4, 4), (2, 192, 8, 14, 14), (4, 64, 8, 1, 1), (2, 8, 16, 6, 6)])
+@pytest.mark.parametrize("variants", VARIANTS, ids=lambda v: "+".join(sorted(v)))
+def test_graph_variants_against_own_restatement(GF, shape, variants):
+    """The default-OFF variants of the graph head (GCA_GRAPH_THRESHOLD / TOPK / EDGE_DROP / SYMNORM; no reference counterpart,
+    PARITY UNPINNED): forward and backward of gca_graph_fwd_ex / gca_graph_bwd_ex against oracle.graph.graph_core_variants
+    (torch autograd), all three kernel paths (per-video, split, large maps).  The kept-edge masks are integer work: exact."""
+    B, C, T, H, W = shape
+    torch.manual_seed(sum(shape))
+    Cq = max(C // 2, 1)
+    gq = (torch.randn(B, Cq, T, H * W) * 0.3).requires_grad_(True)
+    gk = (torch.randn(B, Cq, T, H * W) * 0.3).requires_grad_(True)
+    sup = torch.randn(B, C, T, H * W).requires_grad_(True)
+    u = torch.rand(B, T, T)
+    dy = torch.randn(B, C, T, H * W)
+    y_ref, sim_ref, adj_ref, s_ref = og.graph_core_variants(gq.double(), gk.double(), sup.double(), u.double(), **variants)
+    g_ref = torch.autograd.grad(y_ref, [gq, gk, sup], dy.double())
+    a, b, c = cu(gq.detach()).requires_grad_(True), cu(gk.detach()).requires_grad_(True), cu(sup.detach()).requires_grad_(True)
+    y, sim, adj, s = GF.graph_core(a, b, c, cu(u), variants=variants)
+    y.backward(cu(dy))
+    # masks: an entry is removed in the kernel exactly where the restatement removes it (away from fp32 ties at the cut)
+    kept_ref, kept = adj_ref > 0, adj.cpu() > 0
+    near_cut = torch.zeros_like(kept_ref)
+    if "threshold" in variants:
+        near_cut |= (sim_ref * og.edge_weight_matrix(T, 3, 0.5, torch.float64)[None] - variants["threshold"]).abs() < 1e-6
+    if not near_cut.any() and "topk" not in variants:
+        assert torch.equal(kept, kept_ref)
+    if "topk" in variants and "threshold" not in variants:
+        assert int((kept != kept_ref).sum()) <= 2 * B                      # (fp32 near-ties at the k-th entry may swap)
+    if torch.equal(kept, kept_ref):
+        assert rel_max(s, s_ref) <= 2e-5 and rel_max(y, y_ref) <= 2e-5
+        for got, ref in zip((a.grad, b.grad, c.grad), g_ref):
+            assert rel_max(got, ref) <= 2e-4
+
+
+def test_graph_module_variants_compose(lib):
+    """Cosine adjacency and the feature mask are compositions around the kernel (module options, default OFF): shapes, the
+    seeded masks and autograd through them; the default module draws exactly one torch.rand like the reference."""
+    import gca_b200
+    torch.manual_seed(0)
+    m = gca_b200.TemporalGraphAug(32, sub_sample=False, adjacency="cosine", edge_topk=3, sym_norm=True, feature_mask=0.25).cuda()
+    x = torch.randn(4, 32, 8, 2, 2, device="cuda", requires_grad=True)
+    torch.manual_seed(7)
+    y, info = m(x, return_graph=True)
+    torch.manual_seed(7)
+    u = torch.rand(4, 8, 8, device="cuda")
+    keep = torch.rand(4, 32, device="cuda") >= 0.25
+    assert torch.equal(u, info["u"])
+    assert torch.equal((y.detach().abs().sum(dim=(2, 3, 4)) > 0), keep)          # masked channels are exactly zero
+    assert int((info["adj"] > 0).sum(-1).max()) <= 3                            # top-k rows
+    y.sum().backward()
+    assert torch.isfinite(x.grad).all() and float(x.grad.abs().sum()) > 0
+    # cosine: the logits are bounded by 1 in magnitude -> softmax rows within e^2 of uniform
+    assert float(info["sim"].max() / info["sim"].min()) <= np.e ** 2 + 1e-3
+
+
 def test_negcos_golden(lib, golden):
     import gca_b200
     g = golden("negcos")

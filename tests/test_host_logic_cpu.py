@@ -93,8 +93,16 @@ def test_graph_module_matches_reference_layout_and_init(golden):
     m2 = gca_b200.TemporalGraphAug(16)                         # sub_sample=True default -> Sequential(conv, pool)
     assert sorted(m2.state_dict()) == ["g_k.0.weight", "g_q.0.weight", "gcns.0.conv.weight"]
     assert m2.inter_channels == 8 and m2.gcns[0].conv.out_channels == 16 and m2.alpha == 0.5 and m2.max_hop == 3
-    with pytest.raises(NotImplementedError):
-        gca_b200.TemporalGraphAug(16, mask_frame=True)
+    # mask_frame=True: upstream constructs, but no forward can complete (probed on the reference: its mask loop indexes the
+    # batch axis, temporal_graph.py:169-174) -- IndexError when B < nei_size (default T), else NaN rows -> ValueError from
+    # RelaxedBernoulli's argument check.  The drop-in shows the same error behaviour.
+    m3 = gca_b200.TemporalGraphAug(16, sub_sample=False, mask_frame=True)
+    with pytest.raises(IndexError):
+        m3(torch.randn(3, 16, 8, 2, 2))
+    with pytest.raises(ValueError):
+        m3(torch.randn(8, 16, 8, 2, 2))
+    with pytest.raises(ValueError):
+        gca_b200.TemporalGraphAug(16, sub_sample=False, mask_frame=True, nei_size=4)(torch.randn(4, 16, 8, 2, 2))
     with pytest.raises(NotImplementedError):
         gca_b200.TemporalGraphAug(16, num_gcn_layers=2)
 

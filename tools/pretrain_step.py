@@ -186,17 +186,19 @@ def run(variant, args, rank, world, dev):
         ema_step()
     b.record()
     torch.cuda.synchronize()
-    if rank == 0:
-        print(json.dumps({"workload": "pretrain step, R3D-18-shaped encoder, %d videos/GPU x 2 clips of 3x16x112x112, "
-                                      "queue %d x 128, bf16 autocast" % (args.batch, args.K),
-                          "variant": {"b200": "gca_b200 fused head (bf16 queue) + one-launch EMA",
-                                      "eager": "reference op sequence in eager PyTorch + per-tensor EMA loop"}[variant],
-                          "n_gpus": world, "ms_per_step": round(ms, 3),
-                          "clips_per_s": round(2 * args.batch * world / (ms * 1e-3), 1),
-                          "videos_per_s": round(args.batch * world / (ms * 1e-3), 1),
-                          "head_fwd_ms_median": round(head, 4), "ema_ms": round(a.elapsed_time(b) / 10, 4),
-                          "last_loss": round(lv, 5), "steps": args.steps, "warmup": args.warmup}), flush=True)
+    res = {"workload": "pretrain step, R3D-18-shaped encoder, %d videos/GPU x 2 clips of 3x16x112x112, "
+                       "queue %d x 128, bf16 autocast" % (args.batch, args.K),
+           "variant": {"b200": "gca_b200 fused head (bf16 queue) + one-launch EMA",
+                       "eager": "reference op sequence in eager PyTorch + per-tensor EMA loop"}[variant],
+           "n_gpus": world, "ms_per_step": round(ms, 3),
+           "clips_per_s": round(2 * args.batch * world / (ms * 1e-3), 1),
+           "videos_per_s": round(args.batch * world / (ms * 1e-3), 1),
+           "head_fwd_ms_median": round(head, 4), "ema_ms": round(a.elapsed_time(b) / 10, 4),
+           "last_loss": round(lv, 5), "steps": args.steps, "warmup": args.warmup}
+    if rank == 0 and not getattr(args, "quiet", False):
+        print(json.dumps(res), flush=True)
     del net, model, model_ema, opt, contrast
+    return res
 
 
 def main():

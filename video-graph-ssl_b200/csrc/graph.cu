@@ -24,7 +24,7 @@ graph_fwd_kernel(const GraphArgs a)
     const int b = blockIdx.x, T = a.T;
     const size_t tt = (size_t)b * T * T;
     pair_dots(a.gq + (size_t)b * a.Cq * T * a.S, a.gk + (size_t)b * a.Cq * T * a.S, a.Cq, T, a.S, tiles, red, m0);
-    adj_forward(m0, m1, m2, a.u + tt, a.th, T, a.max_hop, a.inv_temp, a.sim + tt, a.adj + tt, a.s + tt);
+    adj_forward(m0, m1, m2, a.u + tt, a.th, T, a.max_hop, a.inv_temp, a.sim + tt, a.adj + tt, a.s + tt, a.opt);
     if constexpr (kAgg) {
         const size_t off = (size_t)b * a.C * T * a.HW;
         aggregate_items<TMAX, VH>(a.support + off, a.y + off, m0, false, true, a.C, T, a.HW, threadIdx.x, G_THREADS);
@@ -271,6 +271,20 @@ static bool use_fused(const GraphArgs& a)
     return per_video <= 256u * 1024u;
 }
 
+static int check_graph_opts(const char* fn, const GcaGraphOpts* o, int T, const float* u, GraphOpts* out)
+{
+    *out = GraphOpts{0u, 0.f, 0, 0.f};
+    if (!o || o->flags == 0u) return GCA_OK;
+    const unsigned all = GCA_GRAPH_THRESHOLD | GCA_GRAPH_TOPK | GCA_GRAPH_EDGE_DROP | GCA_GRAPH_SYMNORM;
+    if (o->flags & ~all) return set_err(GCA_ERR_UNSUPPORTED, "%s: flags 0x%x not supported", fn, o->flags);
+    GCA_CHECK_ARG(!(o->flags & GCA_GRAPH_TOPK) || (o->topk >= 1 && o->topk <= T), "%s: topk=%d outside [1, T=%d]", fn, o->topk, T);
+    GCA_CHECK_ARG(!(o->flags & GCA_GRAPH_EDGE_DROP) || (o->p_drop >= 0.f && o->p_drop <= 1.f), "%s: p_drop outside [0, 1]", fn);
+    GCA_CHECK_ARG(!(o->flags & GCA_GRAPH_THRESHOLD) || o->tau >= 0.f, "%s: tau < 0", fn);
+    GCA_CHECK_ARG(!(o->flags & (GCA_GRAPH_EDGE_DROP | GCA_GRAPH_SYMNORM)) || u, "%s: these variants need the uniforms u", fn);
+    *out = GraphOpts{o->flags, o->tau, o->topk, o->p_drop};
+    return GCA_OK;
+}
+
 static int check_graph_args(const char* fn, int Cq, int S, int C, int HW, int T, int B, int max_hop, float temperature,
                             unsigned flags)
 {
@@ -295,16 +309,31 @@ extern "C" int gca_graph_fwd(const float* gq, const float* gk, int Cq, int S, co
                              float* sim, float* adj, float* s, float* y, void* workspace, size_t workspace_bytes,
                              void* stream)
 {
+    if (flags != GCA_GRAPH_REFERENCE)
+        return gca::set_err(GCA_ERR_UNSUPPORTED, "gca_graph_fwd: flags 0x%x need gca_graph_fwd_ex (parameters in GcaGraphOpts)", flags);
+    return gca_graph_fwd_ex(gq, gk, Cq, S, support, C, HW, T, B, u, alpha, max_hop, temperature, nullptr, sim, adj, s, y,
+                            workspace, workspace_bytes, stream);
+}
+
+extern "C" int gca_graph_fwd_ex(const float* gq, const float* gk, int Cq, int S, const float* support, int C, int HW,
+                                int T, int B, const float* u, float alpha, int max_hop, float temperature,
+                                const GcaGraphOpts* opts, float* sim, float* adj, float* s, float* y, void* workspace,
+                                size_t workspace_bytes, void* stream)
+{
     using namespace gca;
     GCA_CHECK_ARG(gq && gk && support && u && sim && adj && s && y, "gca_graph_fwd: null pointer");
-    int rc = check_graph_args("gca_graph_fwd", Cq, S, C, HW, T, B, max_hop, temperature, flags);
+    int rc = check_graph_args("gca_graph_fwd", Cq, S, C, HW, T, B, max_hop, temperature, 0u);
+    if (rc != GCA_OK) return rc;
+    GraphOpts gopt;
+    rc = check_graph_opts("gca_graph_fwd_ex", opts, T, u, &gopt);
     if (rc != GCA_OK) return rc;
     GraphArgs a{};
+    a.opt = gopt;
     a.gq = gq; a.gk = gk; a.Cq = Cq; a.S = S; a.support = support; a.C = C; a.HW = HW; a.T = T; a.B = B; a.u = u;
     a.max_hop = max_hop; a.inv_temp = 1.f / temperature; a.sim = sim; a.adj = adj; a.s = s; a.y = y;
     fill_theta(a.th, alpha, max_hop);
     cudaStream_t st = (cudaStream_t)stream;
-    if (graph_smem_fits(a, false)) return graph_smem_launch(a, false, st);
+    if (gopt.flags == 0u && graph_smem_fits(a, false)) return graph_smem_launch(a, false, st);
     if (use_fused(a)) return graph_fwd_adj_launch(a, true, st);
     if (!workspace || workspace_bytes < gca_graph_workspace_bytes(B, T))
         return set_err(GCA_ERR_WORKSPACE, "gca_graph_fwd: workspace of %zu bytes needed", gca_graph_workspace_bytes(B, T));
@@ -322,18 +351,34 @@ extern "C" int gca_graph_bwd(const float* gq, const float* gk, int Cq, int S, co
                              float* d_gq, float* d_gk, float* d_support, void* workspace, size_t workspace_bytes,
                              void* stream)
 {
+    if (flags != GCA_GRAPH_REFERENCE)
+        return gca::set_err(GCA_ERR_UNSUPPORTED, "gca_graph_bwd: flags 0x%x need gca_graph_bwd_ex (parameters in GcaGraphOpts)", flags);
+    return gca_graph_bwd_ex(gq, gk, Cq, S, support, C, HW, T, B, sim, adj, s, dy, nullptr, alpha, max_hop, temperature, nullptr,
+                            d_gq, d_gk, d_support, workspace, workspace_bytes, stream);
+}
+
+extern "C" int gca_graph_bwd_ex(const float* gq, const float* gk, int Cq, int S, const float* support, int C, int HW,
+                                int T, int B, const float* sim, const float* adj, const float* s, const float* dy,
+                                const float* u, float alpha, int max_hop, float temperature, const GcaGraphOpts* opts,
+                                float* d_gq, float* d_gk, float* d_support, void* workspace, size_t workspace_bytes,
+                                void* stream)
+{
     using namespace gca;
     GCA_CHECK_ARG(gq && gk && support && sim && adj && s && dy && d_gq && d_gk && d_support, "gca_graph_bwd: null pointer");
-    int rc = check_graph_args("gca_graph_bwd", Cq, S, C, HW, T, B, max_hop, temperature, flags);
+    int rc = check_graph_args("gca_graph_bwd", Cq, S, C, HW, T, B, max_hop, temperature, 0u);
+    if (rc != GCA_OK) return rc;
+    GraphOpts gopt;
+    rc = check_graph_opts("gca_graph_bwd_ex", opts, T, u, &gopt);
     if (rc != GCA_OK) return rc;
     GraphArgs a{};
+    a.opt = gopt; a.u = gopt.flags ? u : nullptr;
     a.gq = gq; a.gk = gk; a.Cq = Cq; a.S = S; a.support = support; a.C = C; a.HW = HW; a.T = T; a.B = B;
     a.max_hop = max_hop; a.inv_temp = 1.f / temperature;
     a.sim = const_cast<float*>(sim); a.adj = const_cast<float*>(adj); a.s = const_cast<float*>(s);
     a.dy = dy; a.d_gq = d_gq; a.d_gk = d_gk; a.d_support = d_support;
     fill_theta(a.th, alpha, max_hop);
     cudaStream_t st = (cudaStream_t)stream;
-    if (graph_smem_fits(a, true)) return graph_smem_launch(a, true, st);
+    if (gopt.flags == 0u && graph_smem_fits(a, true)) return graph_smem_launch(a, true, st);
     if (use_fused(a)) return graph_bwd_adj_launch(a, true, st);
     if (!workspace || workspace_bytes < gca_graph_workspace_bytes(B, T))
         return set_err(GCA_ERR_WORKSPACE, "gca_graph_bwd: workspace of %zu bytes needed", gca_graph_workspace_bytes(B, T));

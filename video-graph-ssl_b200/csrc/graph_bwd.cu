@@ -18,7 +18,7 @@ graph_bwd_kernel(const GraphArgs a)
     const size_t tt = (size_t)b * T * T;
     const size_t offH = (size_t)b * a.C * T * a.HW, offS = (size_t)b * a.Cq * T * a.S;
     pair_dots(a.dy + offH, a.support + offH, a.C, T, a.HW, tiles, red, m0);      // ds[i][j] = <dy_i, support_j>
-    adj_backward(m0, a.sim + tt, a.adj + tt, a.s + tt, a.th, T, a.max_hop, a.inv_temp);
+    adj_backward(m0, a.sim + tt, a.adj + tt, a.s + tt, a.th, T, a.max_hop, a.inv_temp, a.opt, a.u ? a.u + tt : nullptr);
     if constexpr (kAgg) {
         for (int p = threadIdx.x; p < T * T; p += G_THREADS) m1[p] = __ldg(a.s + tt + p);
         __syncthreads();

@@ -10,6 +10,8 @@ constexpr int G_CHUNK_FLOATS = 4096;            // per operand tile in pair_dots
 constexpr float G_EPS = 1.1920928955078125e-07f;  // torch.finfo(float32).eps (clamp_probs)
 
 struct GraphTheta { float w[G_TMAXMAX + 1]; };  // theta(hop) for hop <= max_hop, computed on the host in double
+// default-OFF variants of the T x T chain (include/gca_b200.h, GCA_GRAPH_*): flags == 0 is the reference's arithmetic
+struct GraphOpts { unsigned flags; float tau; int topk; float p_drop; };
 
 // ------------------------------------------------------------------------------------------------------------
 // pair_dots: A, Bm point at one video's [Cn][T][S] block.  Result in out_tt[T*T] (shared).  `tiles` holds
@@ -89,46 +91,119 @@ __device__ __forceinline__ float edge_w(const GraphTheta& th, int i, int j, int 
     return hop <= max_hop ? th.w[hop] : 0.f;
 }
 
+// re-sampled edge weight from the (masked) adjacency entry: the reference's relaxed Bernoulli, or the hard seeded edge drop
+__device__ __forceinline__ float resample_edge(float adj, float u, float inv_temp, const GraphOpts& opt)
+{
+    if (opt.flags & GCA_GRAPH_EDGE_DROP) return (u >= opt.p_drop) ? adj : 0.f;     // keep mask = [u >= p_drop]
+    const float p  = fminf(fmaxf(adj, G_EPS), 1.f - G_EPS);     // clamp_probs
+    const float uc = fminf(fmaxf(u, G_EPS), 1.f - G_EPS);
+    const float z = (logf(uc) - log1pf(-uc) + logf(p) - log1pf(-p)) * inv_temp;   // LogitRelaxedBernoulli.rsample
+    return 1.f / (1.f + expf(-z));                              // SigmoidTransform
+}
+
 // forward T x T element work: logits (smem) -> sim, adj, s (smem + global)
 __device__ static void adj_forward(float* lg /*in: logits, out: s*/, float* sim_s, float* adj_s, const float* u,
                             const GraphTheta& th, int T, int max_hop, float inv_temp,
-                            float* sim_g, float* adj_g, float* s_g)
+                            float* sim_g, float* adj_g, float* s_g, const GraphOpts opt = GraphOpts{0u, 0.f, 0, 0.f})
 {
+    __shared__ float deg_s[G_TMAXMAX];                                  // row sums of s (GCA_GRAPH_SYMNORM)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = warp; i < T; i += G_THREADS / 32) {
         const float x = lane < T ? lg[i * T + lane] : -INFINITY;
         const float m = warp_max(x);
         const float e = lane < T ? expf(x - m) : 0.f;
         const float sum = warp_sum(e);
+        const float sim = e / sum;                                      // F.softmax(dim=-1), :176
+        float adj = lane < T ? sim * edge_w(th, i, lane, max_hop) : -INFINITY;      // :204-210
+        if (opt.flags & GCA_GRAPH_THRESHOLD) { if (lane < T && adj < opt.tau) adj = 0.f; }
+        if (opt.flags & GCA_GRAPH_TOPK) {
+            // rank of this entry in its row: larger value first, ties towards the lower column (deterministic, integer work)
+            int rank = 0;
+            for (int mcol = 0; mcol < T; ++mcol) {
+                const float o = __shfl_sync(0xffffffffu, adj, mcol);
+                rank += (o > adj || (o == adj && mcol < lane)) ? 1 : 0;
+            }
+            if (lane < T && rank >= opt.topk) adj = 0.f;
+        }
+        float sv = 0.f;
+        if (lane < T) sv = resample_edge(adj, u[i * T + lane], inv_temp, opt);
+        if (opt.flags & GCA_GRAPH_SYMNORM) {
+            const float d = warp_sum(sv);
+            if (lane == 0) deg_s[i] = d;
+        }
         if (lane < T) {
             const int o = i * T + lane;
-            const float sim = e / sum;                                  // F.softmax(dim=-1), :176
-            const float adj = sim * edge_w(th, i, lane, max_hop);       // :204-210
-            const float p  = fminf(fmaxf(adj, G_EPS), 1.f - G_EPS);     // clamp_probs
-            const float uc = fminf(fmaxf(u[o], G_EPS), 1.f - G_EPS);          // (u may live in shared memory)
-            const float z = (logf(uc) - log1pf(-uc) + logf(p) - log1pf(-p)) * inv_temp;   // LogitRelaxedBernoulli.rsample
-            const float s = 1.f / (1.f + expf(-z));                     // SigmoidTransform
-            sim_s[o] = sim; adj_s[o] = adj; lg[o] = s;
-            sim_g[o] = sim; adj_g[o] = adj; s_g[o] = s;
+            sim_s[o] = sim; adj_s[o] = adj; lg[o] = sv;
+            sim_g[o] = sim; adj_g[o] = adj; s_g[o] = sv;
         }
     }
     __syncthreads();
+    if (opt.flags & GCA_GRAPH_SYMNORM) {
+        // s <- D^-1/2 s D^-1/2,  D = diag(row sums of s)  (degrees below G_EPS count as G_EPS)
+        for (int p = threadIdx.x; p < T * T; p += G_THREADS) {
+            const int i = p / T, j = p - i * T;
+            const float v = lg[p] * rsqrtf(fmaxf(deg_s[i], G_EPS)) * rsqrtf(fmaxf(deg_s[j], G_EPS));
+            lg[p] = v; s_g[p] = v;
+        }
+        __syncthreads();
+    }
 }
 
-// backward T x T element work: ds (smem, in place -> d_logit)
+// backward T x T element work: ds (smem, in place -> d_logit).  `u` is only read by the variants that need the pre-
+// normalisation s again (GCA_GRAPH_SYMNORM) or the keep mask (GCA_GRAPH_EDGE_DROP).
 __device__ static void adj_backward(float* ds, const float* __restrict__ sim_g, const float* __restrict__ adj_g,
-                             const float* __restrict__ s_g, const GraphTheta& th, int T, int max_hop, float inv_temp)
+                             const float* __restrict__ s_g, const GraphTheta& th, int T, int max_hop, float inv_temp,
+                             const GraphOpts opt = GraphOpts{0u, 0.f, 0, 0.f}, const float* __restrict__ u = nullptr)
 {
+    __shared__ float sraw_s[G_TMAXMAX * G_TMAXMAX];                     // GCA_GRAPH_SYMNORM: s before the normalisation
+    __shared__ float deg_s[G_TMAXMAX], cvec_s[G_TMAXMAX];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool symnorm = (opt.flags & GCA_GRAPH_SYMNORM) != 0;
+    if (symnorm) {
+        // s' = s_ij r_i r_j, r = d^-1/2, d_i = sum_j s_ij:  dL/ds_ij = g_ij r_i r_j - 1/2 d_i^-3/2 c_i,
+        // c_i = dL/dr_i = sum_j g_ij s_ij r_j + sum_k g_ki s_ki r_k      (g = dL/ds')
+        for (int i = warp; i < T; i += G_THREADS / 32) {
+            float sv = 0.f;
+            if (lane < T) sv = resample_edge(__ldg(adj_g + i * T + lane), __ldg(u + i * T + lane), inv_temp, opt);
+            const float d = warp_sum(sv);
+            if (lane < T) sraw_s[i * T + lane] = sv;
+            if (lane == 0) deg_s[i] = fmaxf(d, G_EPS);
+        }
+        __syncthreads();
+        for (int i = warp; i < T; i += G_THREADS / 32) {
+            float c = 0.f;
+            if (lane < T) {
+                const float rj = rsqrtf(deg_s[lane]);
+                c = ds[i * T + lane] * sraw_s[i * T + lane] * rj + ds[lane * T + i] * sraw_s[lane * T + i] * rj;
+            }
+            c = warp_sum(c);
+            if (lane == 0) cvec_s[i] = c;
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < T * T; p += G_THREADS) {
+            const int i = p / T, j = p - i * T;
+            const float di = deg_s[i];
+            const float below = (di <= G_EPS) ? 0.f : 0.5f * cvec_s[i] / (di * sqrtf(di));      // clamped degree: no gradient
+            ds[p] = ds[p] * rsqrtf(di) * rsqrtf(deg_s[j]) - below;
+        }
+        __syncthreads();
+    }
     for (int i = warp; i < T; i += G_THREADS / 32) {
         float sim = 0.f, dsim = 0.f;
         if (lane < T) {
             const int o = i * T + lane;
             sim = __ldg(sim_g + o);
-            const float adj = __ldg(adj_g + o), s = __ldg(s_g + o);
-            const float p = fminf(fmaxf(adj, G_EPS), 1.f - G_EPS);
-            const bool inside = (adj >= G_EPS) && (adj <= 1.f - G_EPS);   // clamp passes gradient on [min, max]
-            const float dadj = inside ? ds[o] * s * (1.f - s) * inv_temp / (p * (1.f - p)) : 0.f;
+            const float adj = __ldg(adj_g + o);
+            float dadj;
+            if (opt.flags & GCA_GRAPH_EDGE_DROP) {
+                dadj = (__ldg(u + o) >= opt.p_drop) ? ds[o] : 0.f;
+                if (adj == 0.f) dadj = 0.f;                             // removed by the hop mask / threshold / top-k
+            } else {
+                const float s = symnorm ? sraw_s[o] : __ldg(s_g + o);
+                const float p = fminf(fmaxf(adj, G_EPS), 1.f - G_EPS);
+                const bool inside = (adj >= G_EPS) && (adj <= 1.f - G_EPS);   // clamp passes gradient on [min, max]
+                dadj = inside ? ds[o] * s * (1.f - s) * inv_temp / (p * (1.f - p)) : 0.f;
+            }
             dsim = dadj * edge_w(th, i, lane, max_hop);
         }
         const float dot = warp_sum(dsim * sim);
@@ -201,6 +276,7 @@ struct GraphArgs {
     float* d_gq; float* d_gk; float* d_support;
     float* dl;                                 // [B, T, T] scratch (bwd, split path)
     GraphTheta th;
+    GraphOpts opt;                             // default-OFF variants (flags == 0: the reference's arithmetic)
 };
 
 constexpr int G_SMEM_FLOATS = 2 * G_CHUNK_FLOATS + 4 * G_THREADS + 3 * G_TMAXMAX * G_TMAXMAX;

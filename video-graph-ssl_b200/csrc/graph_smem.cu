@@ -110,11 +110,11 @@ graph_smem_kernel(const GraphArgs a)
     if (!kBwd) {
         pair_dots_smem(q_s, k_s, a.Cq, T, a.S, red, m0);
         // adj_forward reads the uniforms through a pointer: give it the staged copy
-        adj_forward(m0, m1, m2, u_s, a.th, T, a.max_hop, a.inv_temp, a.sim + tt, a.adj + tt, a.s + tt);
+        adj_forward(m0, m1, m2, u_s, a.th, T, a.max_hop, a.inv_temp, a.sim + tt, a.adj + tt, a.s + tt, a.opt);
         aggregate_items<TMAX, VH, true>(sup_s, a.y + (size_t)b * ns, m0, false, true, a.C, T, a.HW, threadIdx.x, G_THREADS);
     } else {
         pair_dots_smem(dy_s, sup_s, a.C, T, a.HW, red, m0);               // ds[i][j] = <dy_i, support_j>
-        adj_backward(m0, a.sim + tt, a.adj + tt, a.s + tt, a.th, T, a.max_hop, a.inv_temp);
+        adj_backward(m0, a.sim + tt, a.adj + tt, a.s + tt, a.th, T, a.max_hop, a.inv_temp, a.opt, a.u ? a.u + tt : nullptr);
         for (int p = threadIdx.x; p < tt_n; p += G_THREADS) m1[p] = __ldg(a.s + tt + p);
         __syncthreads();
         aggregate_items<TMAX, VH, true>(dy_s, a.d_support + (size_t)b * ns, m1, true, true, a.C, T, a.HW, threadIdx.x, G_THREADS);

@@ -171,10 +171,10 @@ adj_from_partials_kernel(const GraphArgs a, const float* __restrict__ partials, 
     }
     __syncthreads();
     if (kBwd) {
-        adj_backward(m0, a.sim + tt, a.adj + tt, a.s + tt, a.th, T, a.max_hop, a.inv_temp);
+        adj_backward(m0, a.sim + tt, a.adj + tt, a.s + tt, a.th, T, a.max_hop, a.inv_temp, a.opt, a.u ? a.u + tt : nullptr);
         for (int p = threadIdx.x; p < T * T; p += G_THREADS) a.dl[tt + p] = m0[p];
     } else {
-        adj_forward(m0, m1, m2, a.u + tt, a.th, T, a.max_hop, a.inv_temp, a.sim + tt, a.adj + tt, a.s + tt);
+        adj_forward(m0, m1, m2, a.u + tt, a.th, T, a.max_hop, a.inv_temp, a.sim + tt, a.adj + tt, a.s + tt, a.opt);
     }
 }
 

@@ -17,6 +17,14 @@ GCA_F32, GCA_BF16 = 0, 1
 ALGO = {"auto": 0, "ffma": 1, "tcgen05": 2, "tc32": 3}
 
 
+GRAPH_THRESHOLD, GRAPH_TOPK, GRAPH_EDGE_DROP, GRAPH_SYMNORM = 1, 2, 4, 8
+
+
+class GraphOpts(ctypes.Structure):
+    """GcaGraphOpts of include/gca_b200.h (default-OFF variants of the graph head)."""
+    _fields_ = [("flags", c_uint), ("tau", c_float), ("topk", c_int), ("p_drop", c_float)]
+
+
 class GcaLibraryError(RuntimeError):
     pass
 
@@ -61,6 +69,12 @@ SIGNATURES = {
     "gca_graph_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_float, c_uint,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gca_graph_fwd_ex": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                 c_float, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                 c_void_p]),
+    "gca_graph_bwd_ex": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_float, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gca_graph_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gca_negcos_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                    c_void_p]),

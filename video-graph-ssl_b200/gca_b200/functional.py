@@ -200,7 +200,7 @@ class _GraphCore(torch.autograd.Function):
     """y = GCN-aggregate(resample(hop-weight(softmax(gq . gk)))) for one layer (temporal_graph.py:161-239)."""
 
     @staticmethod
-    def forward(ctx, gq, gk, support, u, alpha, max_hop, temperature):
+    def forward(ctx, gq, gk, support, u, alpha, max_hop, temperature, variants=None):
         _need_cuda(gq, gk, support, u)
         gq, gk, support, u = _f32c(gq), _f32c(gk), _f32c(support), _f32c(u)
         B, Cq, T = gq.shape[:3]
@@ -213,17 +213,21 @@ class _GraphCore(torch.autograd.Function):
         s = torch.empty_like(sim)
         y = torch.empty_like(support)
         ws = workspace(dev, int(_lib.load().gca_graph_workspace_bytes(B, T)), "graph")
-        _lib.call("gca_graph_fwd", ptr(gq), ptr(gk), Cq, S, ptr(support), C, HW, T, B, ptr(u), float(alpha), int(max_hop),
-                  float(temperature), 0, ptr(sim), ptr(adj), ptr(s), ptr(y), ptr(ws), ws.numel(), _stream(gq))
-        ctx.save_for_backward(gq, gk, support, sim, adj, s)
+        opts = _graph_opts(variants)
+        _lib.call("gca_graph_fwd_ex", ptr(gq), ptr(gk), Cq, S, ptr(support), C, HW, T, B, ptr(u), float(alpha), int(max_hop),
+                  float(temperature), ctypes.byref(opts) if opts is not None else None, ptr(sim), ptr(adj), ptr(s), ptr(y),
+                  ptr(ws), ws.numel(), _stream(gq))
+        ctx.save_for_backward(gq, gk, support, sim, adj, s, u)
         ctx.cfg = (float(alpha), int(max_hop), float(temperature))
+        ctx.variants = variants
         ctx.mark_non_differentiable(sim, adj, s)
         return y, sim, adj, s
 
     @staticmethod
     def backward(ctx, dy, *_):
-        gq, gk, support, sim, adj, s = ctx.saved_tensors
+        gq, gk, support, sim, adj, s, u = ctx.saved_tensors
         alpha, max_hop, temperature = ctx.cfg
+        opts = _graph_opts(ctx.variants)
         dy = _f32c(dy)
         B, Cq, T = gq.shape[:3]
         S = gq[0, 0, 0].numel()
@@ -231,14 +235,36 @@ class _GraphCore(torch.autograd.Function):
         HW = support[0, 0, 0].numel()
         d_gq, d_gk, d_sup = torch.empty_like(gq), torch.empty_like(gk), torch.empty_like(support)
         ws = workspace(gq.device, int(_lib.load().gca_graph_workspace_bytes(B, T)), "graph")
-        _lib.call("gca_graph_bwd", ptr(gq), ptr(gk), Cq, S, ptr(support), C, HW, T, B, ptr(sim), ptr(adj), ptr(s), ptr(dy),
-                  alpha, max_hop, temperature, 0, ptr(d_gq), ptr(d_gk), ptr(d_sup), ptr(ws), ws.numel(), _stream(gq))
-        return d_gq, d_gk, d_sup, None, None, None, None
+        _lib.call("gca_graph_bwd_ex", ptr(gq), ptr(gk), Cq, S, ptr(support), C, HW, T, B, ptr(sim), ptr(adj), ptr(s), ptr(dy),
+                  ptr(u), alpha, max_hop, temperature, ctypes.byref(opts) if opts is not None else None, ptr(d_gq), ptr(d_gk),
+                  ptr(d_sup), ptr(ws), ws.numel(), _stream(gq))
+        return d_gq, d_gk, d_sup, None, None, None, None, None
 
 
-def graph_core(gq, gk, support, u, alpha=0.5, max_hop=3, temperature=1.0):
-    """gq, gk [B,Cq,T,...], support [B,C,T,...], u [B,T,T] -> (y like support, sim, adj, s)."""
-    return _GraphCore.apply(gq, gk, support, u, alpha, max_hop, temperature)
+def _graph_opts(variants):
+    """dict(threshold=tau, topk=k, edge_drop=p, symnorm=bool) -> GcaGraphOpts (None: the reference's arithmetic)."""
+    if not variants:
+        return None
+    unknown = set(variants) - {"threshold", "topk", "edge_drop", "symnorm"}
+    if unknown:
+        raise ValueError("unknown graph variants %r" % sorted(unknown))
+    o = _lib.GraphOpts(0, 0.0, 0, 0.0)
+    if variants.get("threshold") is not None:
+        o.flags |= _lib.GRAPH_THRESHOLD; o.tau = float(variants["threshold"])
+    if variants.get("topk") is not None:
+        o.flags |= _lib.GRAPH_TOPK; o.topk = int(variants["topk"])
+    if variants.get("edge_drop") is not None:
+        o.flags |= _lib.GRAPH_EDGE_DROP; o.p_drop = float(variants["edge_drop"])
+    if variants.get("symnorm"):
+        o.flags |= _lib.GRAPH_SYMNORM
+    return o if o.flags else None
+
+
+def graph_core(gq, gk, support, u, alpha=0.5, max_hop=3, temperature=1.0, variants=None):
+    """gq, gk [B,Cq,T,...], support [B,C,T,...], u [B,T,T] -> (y like support, sim, adj, s).
+    `variants`: default-OFF options with no reference counterpart (include/gca_b200.h GCA_GRAPH_*; parity unpinned):
+    dict(threshold=tau, topk=k, edge_drop=p_drop, symnorm=True)."""
+    return _GraphCore.apply(gq, gk, support, u, alpha, max_hop, temperature, variants)
 
 
 # --------------------------------------------------------------------------------------------- SimSiam D

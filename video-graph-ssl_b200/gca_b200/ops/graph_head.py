@@ -33,10 +33,20 @@ class GCN(nn.Module):
 class TemporalGraphAug(nn.Module):
     def __init__(self, in_channels, inter_channels=None, sub_sample=True, bias=False, bn_layer=False,
                  zero_init=False, max_pool=True, mask_frame=False, nei_size=None, alpah=0.5,
-                 num_gcn_layers=1, temperature=1., max_hop=3):
+                 num_gcn_layers=1, temperature=1., max_hop=3, *, adjacency="dot", edge_threshold=None, edge_topk=None,
+                 edge_drop=None, sym_norm=False, feature_mask=None):
+        """The positional / upstream keywords are the reference's (temporal_graph.py:67-71).  The keyword-only ones are
+        default-OFF variants with NO reference counterpart (north_star's wording; parity unpinned, checked
+        against oracle.graph.graph_core_variants): adjacency="cosine" (unit-norm per-frame projections before the dot
+        product), edge_threshold=tau / edge_topk=k (sparsify the hop-weighted adjacency), edge_drop=p (hard seeded edge drop
+        [u >= p] instead of the relaxed Bernoulli), sym_norm (D^-1/2 A D^-1/2), feature_mask=p (seeded per-(video, channel)
+        mask of the output features)."""
         super(TemporalGraphAug, self).__init__()
-        if mask_frame:
-            raise NotImplementedError("mask_frame=True (temporal_graph.py:169-174) is not on the fused path")
+        if adjacency not in ("dot", "cosine"):
+            raise ValueError("adjacency must be 'dot' or 'cosine'")
+        self.adjacency, self.feature_mask = adjacency, feature_mask
+        self.variants = {k: v for k, v in (("threshold", edge_threshold), ("topk", edge_topk), ("edge_drop", edge_drop),
+                                           ("symnorm", True if sym_norm else None)) if v is not None}
         if num_gcn_layers != 1:
             # upstream builds layers >= 2 from the raw `inter_channels` argument (None by default) and cannot
             # construct them (:94-99); one layer is the shipped configuration
@@ -83,13 +93,30 @@ class TemporalGraphAug(nn.Module):
     def forward(self, x, return_graph=False):
         """x [B, C, T, H, W] -> y [B, C', T, H, W] (C' = C by default)."""
         B, _, T, H, W = x.shape
+        if self.mask_frame:
+            # Upstream cannot complete a forward with mask_frame=True (probed on the reference itself): its mask loop indexes
+            # the BATCH axis with range(nei_size) (temporal_graph.py:169-174) -> IndexError when B < nei_size (default T);
+            # otherwise batch element 0 is fully masked, its softmax rows are NaN and RelaxedBernoulli's argument check
+            # raises ValueError (:187-190).  Same error behaviour here, before any kernel runs.
+            nei = T if not self.nei_size else self.nei_size
+            if B < nei:
+                raise IndexError("index %d is out of bounds for dimension 0 with size %d" % (B, B))
+            raise ValueError("Expected parameter probs of distribution LogitRelaxedBernoulli to satisfy the constraint "
+                             "Interval(lower_bound=0.0, upper_bound=1.0): mask_frame=True masks whole rows (NaN after softmax)")
         g_q = self.g_q(x)
         g_k = self.g_k(x)
         support = self.gcns[0].conv(x)                               # :58
         # the one RNG draw of the upstream forward: rsample's torch.rand(adj.shape) from the global generator (:188-191)
         u = torch.rand(B, T, T, dtype=torch.float32, device=x.device)
-        y, sim, adj, s = GF.graph_core(g_q, g_k, support, u, self.alpha, self.max_hop, self.temperature)
+        if self.adjacency == "cosine":                               # variant: per-frame unit-norm projections (autograd)
+            g_q = g_q / g_q.flatten(3).pow(2).sum(dim=(1, 3), keepdim=True).sqrt().clamp_min(1e-8).unsqueeze(-1)
+            g_k = g_k / g_k.flatten(3).pow(2).sum(dim=(1, 3), keepdim=True).sqrt().clamp_min(1e-8).unsqueeze(-1)
+        y, sim, adj, s = GF.graph_core(g_q, g_k, support, u, self.alpha, self.max_hop, self.temperature,
+                                       self.variants or None)
         y = y.view(B, -1, T, H, W).to(x.dtype)
+        if self.feature_mask is not None:                            # variant: drawn AFTER u (the default RNG stream is untouched)
+            keep = torch.rand(B, y.shape[1], device=x.device) >= self.feature_mask
+            y = y * keep[:, :, None, None, None].to(y.dtype)
         if return_graph:
             return y, {"sim": sim, "adj": adj, "s": s, "u": u}
         return y
