@@ -74,43 +74,19 @@ keys_push_kernel(const float4* __restrict__ keys_local, const PeerXchg X)
     xchg_push_slice(X, keys_local, step, blockIdx.x, blockIdx.y);
 }
 
-struct SideLane { cudaStream_t stream; cudaEvent_t fork, join; bool ok; };
-static SideLane* side_lane()
-{
-    static SideLane lanes[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    SideLane& L = lanes[dev];
-    if (!L.ok) {                                         // (first use is the un-captured warm-up call of a step)
-        if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        L.ok = true;
-    }
-    return &L;
-}
-
 int keys_push_fork(const float* keys_local, const PeerXchg& X, cudaStream_t st)
 {
-    SideLane* L = side_lane();
-    if (!L) return set_err(GCA_ERR_CUDA, "could not create the side stream of the key push");
-    GCA_CUDA(cudaEventRecord(L->fork, st));
-    GCA_CUDA(cudaStreamWaitEvent(L->stream, L->fork, 0));
+    cudaStream_t side;
+    const int rc = side_stream_fork(st, &side);
+    if (rc != GCA_OK) return rc;
     dim3 grid(X.W, XCHG_SLICES);
-    keys_push_kernel<<<grid, 256, 0, L->stream>>>((const float4*)keys_local, X);
+    keys_push_kernel<<<grid, 256, 0, side>>>((const float4*)keys_local, X);
     GCA_LAUNCH_CHECK("keys_push_kernel");
     count_launch(1);
-    GCA_CUDA(cudaEventRecord(L->join, L->stream));
     return GCA_OK;
 }
 
-int keys_push_join(cudaStream_t st)
-{
-    SideLane* L = side_lane();
-    if (!L) return set_err(GCA_ERR_CUDA, "could not create the side stream of the key push");
-    GCA_CUDA(cudaStreamWaitEvent(st, L->join, 0));
-    return GCA_OK;
-}
+int keys_push_join(cudaStream_t st) { return side_stream_join(st); }
 
 }  // namespace gca
 

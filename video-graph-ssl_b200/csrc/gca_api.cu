@@ -38,6 +38,44 @@ int sm_count_cached()
     return cached_sms;
 }
 
+// One side stream per device for work that may run beside the caller's stream (a parallel branch when the caller is
+// capturing a CUDA graph): fork = the side stream waits for everything issued so far on `st`; join = `st` waits for
+// everything issued on the side stream since the fork.  Not re-entrant: one fork / join pair at a time per device.
+struct SideLane { cudaStream_t stream; cudaEvent_t fork, join; bool ok; };
+static SideLane* side_lane()
+{
+    static SideLane lanes[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideLane& L = lanes[dev];
+    if (!L.ok) {                                         // (first use is an un-captured warm-up call)
+        if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        L.ok = true;
+    }
+    return &L;
+}
+
+int side_stream_fork(cudaStream_t st, cudaStream_t* side)
+{
+    SideLane* L = side_lane();
+    if (!L) return set_err(GCA_ERR_CUDA, "could not create the side stream");
+    GCA_CUDA(cudaEventRecord(L->fork, st));
+    GCA_CUDA(cudaStreamWaitEvent(L->stream, L->fork, 0));
+    *side = L->stream;
+    return GCA_OK;
+}
+
+int side_stream_join(cudaStream_t st)
+{
+    SideLane* L = side_lane();
+    if (!L) return set_err(GCA_ERR_CUDA, "could not create the side stream");
+    GCA_CUDA(cudaEventRecord(L->join, L->stream));
+    GCA_CUDA(cudaStreamWaitEvent(st, L->join, 0));
+    return GCA_OK;
+}
+
 int infonce_max_splits(int B)
 {
     // every kernel family uses at most (#SMs / row blocks) splits with >= 32-row blocks; 1024 bounds finalize's smem

@@ -83,6 +83,8 @@ struct PeerMerge {
 static inline int infonce_bpad(int B) { return (B + 127) / 128 * 128; }
 // upper bound on the number of K-splits any kernel family uses (2 CTAs worth per SM, at least 1)
 int infonce_max_splits(int B);
+int side_stream_fork(cudaStream_t st, cudaStream_t* side);                                     // gca_api.cu
+int side_stream_join(cudaStream_t st);
 int keys_push_fork(const float* keys_local, const PeerXchg& X, cudaStream_t st);              // exchange.cu: side-stream push ...
 int keys_push_join(cudaStream_t st);                                                          // ... joined after the step's last launch
 int keys_exchange_launch(const float* keys_local, int B, int d, int W, int rank, void* const* mailboxes, float* all_k,

@@ -7,6 +7,7 @@
 // split into an adjacency kernel (one CTA per video) and a grid-parallel aggregation kernel with 128-bit loads.
 // All sums have a fixed order (deterministic).
 #include "graph_dev.cuh"
+#include <stdlib.h>
 
 namespace gca {
 
@@ -41,7 +42,7 @@ graph_agg_vec4_kernel(const AggJobs jobs)
 {
     __shared__ float M[TMAX * TMAX];
     const AggJob jb = jobs.j[blockIdx.z];
-    const int T = jobs.T, b = blockIdx.y, S = jb.S;
+    const int T = jobs.T, b = jb.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, S = jb.S;
     const size_t off = (size_t)b * jb.Cn * T * S;
     const int stride = gridDim.x * G_THREADS;
     const int SV = S / 4, n_items = jb.Cn * SV;
@@ -99,7 +100,7 @@ graph_agg_scalar_kernel(const AggJobs jobs)
 {
     __shared__ float M[TMAX * TMAX];
     const AggJob jb = jobs.j[blockIdx.z];
-    const int T = jobs.T, b = blockIdx.y, S = jb.S;
+    const int T = jobs.T, b = jb.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, S = jb.S;
     const size_t off = (size_t)b * jb.Cn * T * S;
     const int n_items = jb.Cn * S;
     const float* in = jb.in + off;
@@ -156,7 +157,7 @@ graph_agg_kernel(const AggJobs jobs)
 {
     __shared__ float M[G_TMAXMAX * G_TMAXMAX];
     const AggJob jb = jobs.j[blockIdx.z];
-    const int T = jobs.T, b = blockIdx.y;
+    const int T = jobs.T, b = jb.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
     for (int p = threadIdx.x; p < T * T; p += G_THREADS) M[p] = __ldg(jb.M + (size_t)b * T * T + p);
     __syncthreads();
     const size_t off = (size_t)b * jb.Cn * T * jb.S;
@@ -258,6 +259,18 @@ int graph_agg_launch(const AggJobs& jobs, int njobs, int B, cudaStream_t st)
                        ((reinterpret_cast<uintptr_t>(jb.in) | reinterpret_cast<uintptr_t>(jb.out)) & 15) == 0;
         if (v) fast.j[nf++] = jb; else slow.j[ns++] = jb;
     }
+    if (nf && ns) {
+        // the two groups are independent (different outputs): the scalar group runs on a forked side stream (a parallel
+        // branch under graph capture) so that its lower-bandwidth loads hide under the 128-bit group
+        cudaStream_t side;
+        int rc = side_stream_fork(st, &side);
+        if (rc != GCA_OK) return rc;
+        rc = agg_launch_group(slow, ns, B, false, side);
+        if (rc != GCA_OK) return rc;
+        rc = agg_launch_group(fast, nf, B, true, st);
+        if (rc != GCA_OK) return rc;
+        return side_stream_join(st);
+    }
     if (nf) { const int rc = agg_launch_group(fast, nf, B, true, st); if (rc != GCA_OK) return rc; }
     if (ns) { const int rc = agg_launch_group(slow, ns, B, false, st); if (rc != GCA_OK) return rc; }
     return GCA_OK;
@@ -341,7 +354,7 @@ extern "C" int gca_graph_fwd_ex(const float* gq, const float* gk, int Cq, int S,
     if (rc != GCA_OK) return rc;
     AggJobs jobs{};
     jobs.T = T;
-    jobs.j[0] = AggJob{support, y, s, 0, 1, C, HW};
+    jobs.j[0] = AggJob{support, y, s, 0, 1, C, HW, 0};
     return graph_agg_launch(jobs, 1, B, st);
 }
 
@@ -383,12 +396,33 @@ extern "C" int gca_graph_bwd_ex(const float* gq, const float* gk, int Cq, int S,
     if (!workspace || workspace_bytes < gca_graph_workspace_bytes(B, T))
         return set_err(GCA_ERR_WORKSPACE, "gca_graph_bwd: workspace of %zu bytes needed", gca_graph_workspace_bytes(B, T));
     a.dl = (float*)workspace;
+    // d_support = s^T dy + dy uses the FORWARD's s: it does not depend on the backward chain, so it runs on a forked side
+    // stream (a parallel branch under graph capture) BESIDE the pair-dot kernel.  Both stream dy video by video in ascending
+    // order; whichever is behind finds the lines in L2, so dy comes from HBM once per backward instead of twice (an in-kernel
+    // fusion of the two was measured slower: the extra stores and FMAs cost the pair-dot kernel its loads in flight).
+    static int early_on = -1;                         // GCA_GRAPH_NOEARLY=1: the aggregation waits for the chain (A/B timing)
+    if (early_on < 0) { const char* e = getenv("GCA_GRAPH_NOEARLY"); early_on = (e && e[0] == '1') ? 0 : 1; }
+    const bool early = early_on && T <= 8 && HW % 4 == 0 &&
+                       ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(d_support)) & 15) == 0;
+    AggJobs first{};
+    first.T = T;
+    first.j[0] = AggJob{dy, d_support, s, 1, 1, C, HW, 0};
+    if (early) {
+        cudaStream_t side;
+        rc = side_stream_fork(st, &side);
+        if (rc != GCA_OK) return rc;
+        rc = graph_agg_launch(first, 1, B, side);
+        if (rc != GCA_OK) return rc;
+    }
     rc = graph_split_adj_launch(a, true, (float*)workspace + (size_t)B * T * T, st);
     if (rc != GCA_OK) return rc;
     AggJobs jobs{};
     jobs.T = T;
-    jobs.j[0] = AggJob{dy, d_support, s, 1, 1, C, HW};
-    jobs.j[1] = AggJob{gk, d_gq, a.dl, 0, 0, Cq, S};
-    jobs.j[2] = AggJob{gq, d_gk, a.dl, 1, 0, Cq, S};
-    return graph_agg_launch(jobs, 3, B, st);
+    int nj = 0;
+    if (!early) jobs.j[nj++] = AggJob{dy, d_support, s, 1, 1, C, HW, 1};      // (descending: the tail of dy is still in L2)
+    jobs.j[nj++] = AggJob{gk, d_gq, a.dl, 0, 0, Cq, S, 0};
+    jobs.j[nj++] = AggJob{gq, d_gk, a.dl, 1, 0, Cq, S, 0};
+    rc = graph_agg_launch(jobs, nj, B, st);
+    if (rc != GCA_OK) return rc;
+    return early ? side_stream_join(st) : GCA_OK;
 }

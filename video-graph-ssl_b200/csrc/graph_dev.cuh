@@ -261,7 +261,8 @@ __device__ __forceinline__ void aggregate_items(const float* __restrict__ in, fl
     }
 }
 
-struct AggJob { const float* in; float* out; const float* M; int transpose; int skip; int Cn; int S; };
+struct AggJob { const float* in; float* out; const float* M; int transpose; int skip; int Cn; int S;
+                int reverse; };   // reverse: videos in descending order (re-read what the previous kernel touched last while it is in L2)
 struct AggJobs { AggJob j[3]; int T; };
 
 struct GraphArgs {
