@@ -838,6 +838,43 @@ def test_retrieval_massive_ties_take_the_fallback(GF):
     assert bool((val[:, :-1] >= val[:, 1:]).all())
 
 
+@pytest.mark.parametrize("Nq,Ng,d,k", [(300, 5000, 128, 50), (131, 4099, 64, 10), (64, 9000, 512, 64)])
+def test_retrieval_large_gallery_matches_oracle(GF, Nq, Ng, d, k):
+    """Galleries of several thousand rows (many column tiles per row, per-tile maxima as the threshold input): indices equal
+    the fp32 oracle's stable argsort (near-ties below fp32 resolution excepted), the exact tie keeps the lower index first."""
+    rng = np.random.default_rng(Nq + Ng + d)
+    qry = rng.standard_normal((Nq, d)).astype(np.float32)
+    gal = rng.standard_normal((Ng, d)).astype(np.float32)
+    gal[Ng // 2] = gal[3]
+    idx, val = GF.cosine_topk(cu(T_(qry)), cu(T_(gal)), k)
+    oidx, oval = oracle.cosine_topk(qry, gal, k)
+    got, gv = idx.cpu().numpy(), val.cpu().numpy()
+    np.testing.assert_allclose(gv, oval, rtol=0, atol=3e-6)
+    mism = got != oidx
+    if mism.any():
+        r, c = np.nonzero(mism)
+        assert np.all(np.abs(oval[r, c] - gv[r, c]) <= 3e-6) and mism.mean() < 0.002
+    assert bool((val[:, :-1] >= val[:, 1:]).all())
+    three = np.nonzero((got == 3).any(1) & (got == Ng // 2).any(1))[0]
+    for row in three:
+        assert list(got[row]).index(3) < list(got[row]).index(Ng // 2)
+
+
+def test_retrieval_large_gallery_massive_ties(GF):
+    """2000 identical gallery rows in a 6000-row gallery: the candidate list of a query equal to them overflows and the row
+    takes the arg-max rounds (lowest indices first); the other rows come from their candidate lists."""
+    rng = np.random.default_rng(11)
+    gal = rng.standard_normal((6000, 64)).astype(np.float32)
+    gal[1000:3000] = gal[1000]
+    qry = np.concatenate([gal[1000:1001], rng.standard_normal((40, 64)).astype(np.float32)])
+    idx, val = GF.cosine_topk(cu(T_(qry)), cu(T_(gal)), 20)
+    got = idx.cpu().numpy()
+    assert got[0].tolist() == list(range(1000, 1020))
+    oidx, oval = oracle.cosine_topk(qry, gal, 20)
+    np.testing.assert_allclose(val.cpu().numpy(), oval, rtol=0, atol=3e-6)
+    assert (got[1:] != oidx[1:]).mean() < 0.01
+
+
 # ============================================================================================ full-size properties
 def test_headline_shape_full_size(GF):
     """BASELINE metric shape (B=256, K=65536, d=128): both modes against the fp64 oracle, pointer wrap over a lap."""

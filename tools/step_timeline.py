@@ -33,6 +33,11 @@ for cold in (True, False):
           "last-block exit %.2f (span %.2f)" % ("cold" if cold else "warm", a.elapsed_time(b) * 1e3, (s_in - p_in) / 1e3, (s_out - p_in) / 1e3,
           (s_out - s_in) / 1e3, (f_in - p_in) / 1e3, (f_out - p_in) / 1e3, (f_out - f_in) / 1e3))
 
+    for sl, nm in ((0, "stream CTA entry"), (9, "producer: first TMA issued"), (10, "mma: q block seen"), (11, "mma: first tile landed"),
+                   (4, "first S tile seen"), (5, "main loop done"), (6, "last O GEMM done"), (7, "partials written"), (8, "exit")):
+        rel = (cta[:, sl] - p_in) / 1e3
+        print("   stream %-28s mean %6.2f  min %6.2f  max %6.2f us since prep entry" % (nm, rel.mean(), rel.min(), rel.max()))
+    print("   prep last row CTA done %.2f us" % ((float(t[32 * 1000 + 4]) - p_in) / 1e3))
     if float(cta[:, 14].max()) > 0:      # fused finalize stamps (per CTA): 12 partial written, 13 past the grid barrier, 14 done
         for sl, nm in ((5, "main loop done"), (6, "last MMA done"), (12, "partial written"), (13, "past grid barrier"), (14, "fused finalize done"), (8, "exit")):
             rel = (cta[:, sl] - p_in) / 1e3
