@@ -456,22 +456,27 @@ def run_single(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": "moco_head_B256_K65536_d128", "B": B, "K": K, "d": D, "T": T, "queue_dtype": "bf16",
-                   "algo": "tcgen05 single-pass (loss + dq in one queue sweep)", "cuda_graph": True, "input_pool": POOL,
+                   "algo": "tcgen05 single-pass (loss + dq in one queue sweep)",
+                   "cuda_graph": steps_g[0].plan is None, "launch_plan": steps_g[0].plan is not None, "input_pool": POOL,
                    "queue_pool": QPOOL, "outputs": "loss, dq[256,128], top-1/top-5 hit counts (rank_gt = NULL), enqueue + pointer",
                    "l2": "no flush needed: consecutive steps use %d distinct queue replicas + workspaces (%.0f MB > 126 MB L2)"
                          % (QPOOL, QPOOL * (K * D * 2 + 74 * B * D * 4) / 1e6),
-                   "timing": "EXACTLY `steps` graph-replayed steps back to back between ONE CUDA event pair on the launch "
-                             "stream, synchronised on both sides; value = steps / elapsed"},
+                   "timing": "EXACTLY `steps` steps (GraphedMoCoStep.step(): %s) back to back between ONE CUDA event pair on "
+                             "the launch stream, synchronised on both sides; value = steps / elapsed"
+                             % ("the step's three launches re-issued from a recorded launch plan (gca_plan_run), programmatic "
+                                "dependent launch between them and across steps" if steps_g[0].plan is not None else
+                                "one CUDA-graph launch per step")},
         "ms_per_step_isolated": ms_isolated, "isolated_note": "one step between its own event pair after a 256 MiB L2 flush "
-                                "(round 1's method; includes the launch latency of a lone graph)",
+                                "(round 1's method; includes the launch latency of a lone step)",
         "wall_s_total": wall, "loss_last": loss_last,
         "clocks": clocks,
         "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                 "path": ("GraphedMoCoStep.step_host_io(): the step's first kernel reads q|k from the pinned host buffer over PCIe "
                          "(zero-copy, each once), its enqueue CTAs read all_k from it, " if zc_in else
                          "GraphedMoCoStep.step_host_io(): pinned host q|k|all_k -> H2D copy -> step (C ABI), ") +
-                        "its last kernel stores loss|top-k hits|dq straight into the pinned host result buffer -- one graph "
-                        "launch, stream synchronised and the loss read on the host every step",
+                        "its last kernel stores loss|top-k hits|dq straight into the pinned host result buffer -- %s, "
+                        "stream synchronised and the loss read on the host every step"
+                        % "one CUDA-graph launch (a synchronous step wants a single submission)",
                 "zero_copy_in": zc_in,
                 "loss_last": e2e_loss},
         "gpu_launches": launches,
@@ -681,7 +686,8 @@ def run_multi(args, rank, world, local_rank):
                                          "NVLink peer-memory stores fused into the step's own launches" if xmode == "fused" else
                                          "gca_keys_exchange: one NVLink peer-memory kernel per step", B * world),
                        "key_exchange": "nccl" if exchange is None else ("fused_p2p" if xmode == "fused" else "p2p_kernel"),
-                       "cuda_graph": graphed, "queue_pool": QPOOL,
+                       "cuda_graph": graphed and steps_g[0].plan is None, "launch_plan": graphed and steps_g[0].plan is not None,
+                       "queue_pool": QPOOL,
                        "outputs": "loss, dq[256,128], top-1/top-5 hit counts (rank_gt = NULL), enqueue + pointer",
                        "l2": "no flush needed: consecutive steps use %d distinct queue replicas + workspaces per rank (> 126 MB L2)" % QPOOL,
                        "timing": "EXACTLY `steps` steps back to back between ONE CUDA event pair per rank, barrier + synchronise on "

@@ -211,6 +211,26 @@ int gca_moco_step_peer(const float* q, const float* k, void* queue, int dtype_qu
                        long long* state, float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt,
                        int* top_hits, float* dq_unit, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Launch plans.  A head step is 3-4 kernel launches whose parameters do not change from step to step when the caller
+ * uses static buffers and the device-resident ring pointer (`state` != NULL) -- what the reference's training loop does
+ * every iteration (tools/train_video_contrast_dis.py:405-428).  Between gca_plan_begin() and gca_plan_end() the step
+ * entry points of the tcgen05 family (gca_moco_step, gca_moco_step_proj, gca_moco_step_peer on a bf16 queue with
+ * d == 128) called by THIS thread are recorded instead of launched; gca_plan_run() re-issues the recorded launches
+ * on `stream` with three host-side launch calls, keeping the programmatic dependencies between them and across
+ * consecutive steps (the first launch of step s+1 is resident while the last launch of step s drains -- a CUDA-graph
+ * launch per step cannot do that).  Every pointer given while recording must stay valid for the life of the plan;
+ * `state` must be non-NULL (a host `index` would be frozen into the plan).  gca_plan_end() fails with
+ * GCA_ERR_UNSUPPORTED if a call made while recording was not recordable (launches of that call which bypass the
+ * recorder were issued on the spot, the others dropped: its results are undefined).
+ * Plans are bound to the device that was current in gca_plan_begin(); gca_plan_run is not thread-safe per plan. */
+typedef struct gca_plan gca_plan;
+int gca_plan_begin(void);
+int gca_plan_end(gca_plan** plan);
+int gca_plan_run(gca_plan* plan, void* stream);
+int gca_plan_launches(const gca_plan* plan);    /* kernel launches per gca_plan_run */
+void gca_plan_destroy(gca_plan* plan);
+
 /* The K-sharded head step with every exchange over NVLink peer memory (the partition of SURVEY.md section 8e; replaces the
  * replicated queue + key gather of tools/train_video_contrast_dis.py:182-187, 222, 233-242 and the three NCCL collectives
  * of the gca_infonce_shard_* sequence above).  One call per step and rank launches

@@ -76,6 +76,18 @@ def test_argument_validation_without_gpu(lib):
     assert lib.gca_sim_topk(one, one, 4, 8, 16, 4, 1, one, null, one, 8, null) == -4  # workspace too small
 
 
+def test_launch_plan_entry_points_without_gpu(lib):
+    """gca_plan_*: misuse returns error codes; without a CUDA device recording cannot start (no CPU path)."""
+    h = ctypes.c_void_p()
+    assert lib.gca_plan_end(ctypes.byref(h)) == -1                                  # not recording
+    assert lib.gca_plan_run(None, None) == -1
+    assert lib.gca_plan_launches(None) == 0
+    lib.gca_plan_destroy(None)
+    if not torch.cuda.is_available():
+        assert lib.gca_plan_begin() == -3                                           # GCA_ERR_CUDA
+        assert b"no CUDA device" in lib.gca_last_error()
+
+
 def test_workspace_sizes(lib):
     assert lib.gca_infonce_workspace_bytes(256, 65536, 128, 1, 0) >= 74 * 256 * 128 * 4
     assert lib.gca_infonce_workspace_bytes(0, 65536, 128, 1, 0) == 0

@@ -938,6 +938,57 @@ def test_graphed_step_matches_oracle_over_a_lap(lib, queue_dtype, B, N, K):
     assert torch.equal(moco.memory.cpu(), ref_mem)                          # slot contents: exact
 
 
+@pytest.mark.parametrize("B,N,K", [(64, 64, 1024), (256, 256, 65536)])
+def test_launch_plan_equals_graph_replay(lib, B, N, K):
+    """gca_plan_*: the step re-issued from a recorded launch plan (three launches, programmatic dependent launch between
+    them and across consecutive steps) gives bit-identical loss, gradient, hit counts, queue and ring pointer to the
+    CUDA-graph replay of the same step, back to back over a wrap of the ring; launch bookkeeping agrees."""
+    import gca_b200
+    from gca_b200.graphed import GraphedMoCoStep
+    gen = torch.Generator().manual_seed(7 * B + K)
+    mocos = [gca_b200.RGBMoCo(128, K=K, T=0.07, queue_dtype="bf16").cuda() for _ in range(2)]
+    mocos[1].load_state_dict(mocos[0].state_dict())
+    for m in mocos:
+        m.index = K - 2 * N - 3
+    steps = [GraphedMoCoStep(m, B, N).capture() for m in mocos]
+    assert steps[0].plan is not None and steps[0].plan.launches == steps[0].launches_per_step == 3
+    steps[1].prefer_graph = True
+    n0 = lib.gca_launch_count()
+    nsteps = 6
+    for it in range(nsteps):                                              # no synchronisation between the steps of a variant
+        q, k, all_k = cu(unit_rows(B, 128, gen)), cu(unit_rows(B, 128, gen)), cu(unit_rows(N, 128, gen))
+        for s in steps:
+            s.step(q, k, all_k)
+        if it in (1, nsteps - 1):
+            torch.cuda.synchronize()
+            assert torch.equal(steps[0].outputs, steps[1].outputs)        # loss | hits | dq
+            assert torch.equal(steps[0].rank, steps[1].rank) and torch.equal(steps[0].lse, steps[1].lse)
+    torch.cuda.synchronize()
+    assert int(lib.gca_launch_count() - n0) == 3 * nsteps                 # the plan counts its launches, graph replays do not
+    assert torch.equal(steps[0].state, steps[1].state) and mocos[0].index == mocos[1].index
+    assert torch.equal(mocos[0].memory, mocos[1].memory)
+
+
+def test_launch_plan_rejects_unrecordable_calls(lib, GF):
+    """Only the tcgen05-family step entry points are recordable: a plan around an fp32-queue step is refused (the call
+    itself has then run normally), and begin / end / run misuse returns error codes."""
+    import ctypes
+    import gca_b200
+    from gca_b200 import _lib
+    from gca_b200.graphed import GraphedMoCoStep
+    assert lib.gca_plan_end(ctypes.byref(ctypes.c_void_p())) == -1        # not recording
+    moco = gca_b200.RGBMoCo(64, K=256, T=0.07, queue_dtype="fp32").cuda()
+    step = GraphedMoCoStep(moco, 32, 32).capture()
+    assert step.plan is None                                              # d = 64: graph replays only
+    with pytest.raises(_lib.GcaError, match="recordable"):
+        _lib.LaunchPlan.record(lambda: step._enqueue_work(None), moco.memory.device)
+    torch.cuda.synchronize()
+    assert lib.gca_plan_begin() == 0 and lib.gca_plan_begin() == -1       # already recording
+    h = ctypes.c_void_p()
+    assert lib.gca_plan_end(ctypes.byref(h)) == -2 and not h.value        # nothing recorded
+    assert lib.gca_plan_run(None, None) == -1
+
+
 @pytest.mark.parametrize("B,K,with_all_k", [(64, 2048, False), (200, 4096, True), (256, 65536, False)])
 def test_projection_tail_fusion_matches_normalize_then_head(lib, B, K, with_all_k):
     """gca_moco_step_proj / RGBMoCo.forward_from_projections: Normalize(2) of both projections inside the kernels ==

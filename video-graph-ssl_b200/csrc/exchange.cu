@@ -16,6 +16,7 @@
 // Flags are monotone step numbers, so nothing is ever reset; the step counter lives in device memory (xstate[0]) so
 // a captured CUDA graph can be replayed.
 #include "gca_common.cuh"
+#include "launch_plan.cuh"
 
 namespace gca {
 
@@ -79,8 +80,9 @@ int keys_push_fork(const float* keys_local, const PeerXchg& X, cudaStream_t st)
     cudaStream_t side;
     const int rc = side_stream_fork(st, &side);
     if (rc != GCA_OK) return rc;
-    dim3 grid(X.W, XCHG_SLICES);
-    keys_push_kernel<<<grid, 256, 0, side>>>((const float4*)keys_local, X);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(X.W, XCHG_SLICES); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = side;
+    GCA_CUDA(launch_ex(&cfg, keys_push_kernel, (const float4*)keys_local, X));
     GCA_LAUNCH_CHECK("keys_push_kernel");
     count_launch(1);
     return GCA_OK;

@@ -4,6 +4,7 @@
 #include "gca_common.cuh"
 #include "infonce_params.cuh"
 #include "tc_ptx.cuh"
+#include "launch_plan.cuh"
 #include <stdlib.h>
 
 namespace gca {
@@ -122,6 +123,9 @@ infonce_finalize_kernel(const FinalizeParams F)
     // launched with a programmatic dependency on the stream kernel: everything below reads its partials (or, for the
     // enqueue CTAs, overwrites queue rows it may still be reading)
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // the next launch in the stream (the prep kernel of the next step waits for this whole grid before it touches anything)
+    // may become resident now
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (F.timebuf && tid == 0) {                              // bring-up only
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -480,8 +484,8 @@ int infonce_finalize_launch(const FinalizeParams& F_, int mode, cudaStream_t st)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
 #define GCA_FIN_LAUNCH(MODE) do { \
-        if (vec) GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_finalize_kernel<MODE, true>, F)); \
-        else     GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_finalize_kernel<MODE, false>, F)); } while (0)
+        if (vec) GCA_CUDA(launch_ex(&cfg, infonce_finalize_kernel<MODE, true>, F)); \
+        else     GCA_CUDA(launch_ex(&cfg, infonce_finalize_kernel<MODE, false>, F)); } while (0)
     if (mode == FIN_FULL)       GCA_FIN_LAUNCH(FIN_FULL);
     else if (mode == FIN_SHARD) GCA_FIN_LAUNCH(FIN_SHARD);
     else                        GCA_FIN_LAUNCH(FIN_BWD);

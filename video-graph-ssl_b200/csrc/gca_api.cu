@@ -1,6 +1,7 @@
 // C-ABI entry points of the InfoNCE head + library-wide helpers.  See include/gca_b200.h for the contract.
 #include "gca_common.cuh"
 #include "infonce_params.cuh"
+#include "launch_plan.cuh"
 #include <string.h>
 #include <atomic>
 
@@ -22,7 +23,13 @@ int set_err(int code, const char* fmt, ...)
 }
 
 static std::atomic<long long> g_launches{0};
-void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static thread_local LaunchPlan* t_plan = nullptr;        // non-null between gca_plan_begin and gca_plan_end on this thread
+LaunchPlan* plan_recording() { return t_plan; }
+void count_launch(int n)
+{
+    if (t_plan) t_plan->counted += n;                    // recorded, not launched: gca_plan_run counts them when they run
+    else g_launches.fetch_add(n, std::memory_order_relaxed);
+}
 
 int sm_count_cached()
 {
@@ -57,10 +64,22 @@ static SideLane* side_lane()
     return &L;
 }
 
+bool plan_is_side_stream(cudaStream_t st)
+{
+    SideLane* L = side_lane();
+    return L != nullptr && st == L->stream;
+}
+
 int side_stream_fork(cudaStream_t st, cudaStream_t* side)
 {
     SideLane* L = side_lane();
     if (!L) return set_err(GCA_ERR_CUDA, "could not create the side stream");
+    if (t_plan) {                                        // recording: the fork becomes a plan operation
+        PlanOp op; op.kind = PLAN_FORK;
+        t_plan->ops.push_back(std::move(op));
+        *side = L->stream;
+        return GCA_OK;
+    }
     GCA_CUDA(cudaEventRecord(L->fork, st));
     GCA_CUDA(cudaStreamWaitEvent(L->stream, L->fork, 0));
     *side = L->stream;
@@ -71,6 +90,11 @@ int side_stream_join(cudaStream_t st)
 {
     SideLane* L = side_lane();
     if (!L) return set_err(GCA_ERR_CUDA, "could not create the side stream");
+    if (t_plan) {
+        PlanOp op; op.kind = PLAN_JOIN;
+        t_plan->ops.push_back(std::move(op));
+        return GCA_OK;
+    }
     GCA_CUDA(cudaEventRecord(L->join, L->stream));
     GCA_CUDA(cudaStreamWaitEvent(st, L->join, 0));
     return GCA_OK;
@@ -196,6 +220,72 @@ extern "C" int gca_sm_count(void)
     return n > 0 ? n : gca::set_err(GCA_ERR_CUDA, "no CUDA device available");
 }
 
+// ---- launch plans (launch_plan.cuh) ----------------------------------------------------------------------------------
+struct gca_plan { gca::LaunchPlan plan; };
+
+extern "C" int gca_plan_begin(void)
+{
+    using namespace gca;
+    if (t_plan) return set_err(GCA_ERR_BAD_ARG, "gca_plan_begin: this thread is already recording a plan");
+    if (sm_count_cached() < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    gca_plan* p = new gca_plan();
+    cudaGetDevice(&p->plan.device);
+    t_plan = &p->plan;
+    return GCA_OK;
+}
+
+extern "C" int gca_plan_end(gca_plan** out)
+{
+    using namespace gca;
+    if (!t_plan) return set_err(GCA_ERR_BAD_ARG, "gca_plan_end: this thread is not recording");
+    gca_plan* p = reinterpret_cast<gca_plan*>(t_plan);   // (the plan is the first member)
+    t_plan = nullptr;
+    if (out) *out = nullptr;
+    if (!out) { delete p; return set_err(GCA_ERR_BAD_ARG, "gca_plan_end: null output pointer"); }
+    if (p->plan.recorded == 0 || p->plan.recorded != p->plan.counted) {
+        const int rec = p->plan.recorded, cnt = p->plan.counted;
+        delete p;
+        return set_err(GCA_ERR_UNSUPPORTED, "gca_plan_end: %d launches recorded, %d issued -- only the tcgen05-family step entry "
+                       "points (gca_moco_step, gca_moco_step_proj, gca_moco_step_peer on a bf16 queue with d == 128) are recordable", rec, cnt);
+    }
+    *out = p;
+    return GCA_OK;
+}
+
+extern "C" int gca_plan_run(gca_plan* p, void* stream)
+{
+    using namespace gca;
+    GCA_CHECK_ARG(p != nullptr, "gca_plan_run: null plan");
+    if (t_plan) return set_err(GCA_ERR_BAD_ARG, "gca_plan_run: called while recording");
+    cudaStream_t st = (cudaStream_t)stream, side = nullptr;
+    for (PlanOp& op : p->plan.ops) {
+        switch (op.kind) {
+        case PLAN_LAUNCH: {
+            cudaLaunchConfig_t cfg = op.cfg;
+            cfg.attrs = op.attrs; cfg.numAttrs = (unsigned)op.nattrs;
+            cfg.stream = op.lane ? side : st;
+            if (op.lane && side == nullptr) return set_err(GCA_ERR_BAD_ARG, "gca_plan_run: side-stream launch without a fork");
+            GCA_CUDA(cudaLaunchKernelExC(&cfg, op.func, op.args.data()));
+            break;
+        }
+        case PLAN_FORK: { const int rc = side_stream_fork(st, &side); if (rc != GCA_OK) return rc; break; }
+        case PLAN_JOIN: { const int rc = side_stream_join(st); if (rc != GCA_OK) return rc; break; }
+        case PLAN_WAIT_EVENT: GCA_CUDA(cudaStreamWaitEvent(st, op.event, 0)); break;
+        default: return set_err(GCA_ERR_BAD_ARG, "gca_plan_run: corrupt plan");
+        }
+    }
+    count_launch(p->plan.recorded);
+    return GCA_OK;
+}
+
+extern "C" int gca_plan_launches(const gca_plan* p) { return p ? p->plan.recorded : 0; }
+
+extern "C" void gca_plan_destroy(gca_plan* p)
+{
+    if (p && gca::t_plan == &p->plan) gca::t_plan = nullptr;
+    delete p;
+}
+
 extern "C" size_t gca_infonce_workspace_bytes(int B, long long K, int d, int dtype_queue, int algo)
 {
     using namespace gca;
@@ -251,7 +341,14 @@ static int infonce_fwd_impl(const char* fn, const float* q, const float* k, cons
     F.nsplit = ws.nsplit; F.Bpad = ws.Bpad;
     F.range_checked = ((pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05 || pick_algo(algo, dtype_queue, d) == GCA_ALGO_TC32) &&
                        logits_out == nullptr) ? 1 : 0;
-    if (keys_ready_event) GCA_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)keys_ready_event, 0));
+    if (keys_ready_event) {
+        if (plan_recording()) {
+            PlanOp op; op.kind = PLAN_WAIT_EVENT; op.event = (cudaEvent_t)keys_ready_event;
+            plan_recording()->ops.push_back(std::move(op));
+        } else {
+            GCA_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)keys_ready_event, 0));
+        }
+    }
     rc = infonce_finalize_launch(F, FIN_FULL, st);
     if (rc == GCA_OK && px && pick_algo(algo, dtype_queue, d) == GCA_ALGO_TCGEN05) rc = keys_push_join(st);   // the side-stream key push
     return rc;

@@ -12,6 +12,7 @@
 #include "gca_common.cuh"
 #include "infonce_params.cuh"
 #include "tc_ptx.cuh"
+#include "launch_plan.cuh"
 #include <stdlib.h>
 
 namespace gca {
@@ -433,6 +434,10 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
                     const char* __restrict__ pf_base, unsigned long long pf_bytes, float q_scale, const int npush,
                     const int gather_Bl)
 {
+    // launched with a programmatic dependency on whatever kernel precedes it in the stream (normally the finalize launch of the
+    // previous step, whose enqueue CTAs write the queue): resident and past its launch latency when that kernel drains.
+    // Nothing of this step may start before it has completed -- the sweep's first queue tiles are loaded before ITS wait.
+    ptx::pdl_wait();
     ptx::pdl_launch_dependents();            // the streaming kernel may start its setup and its first queue-tile loads
     // warm the L2 with the head of the queue (the first tile waves of the stream kernel): this launch starts ~1 us before
     // the stream kernel's TMA producer can, and a cold queue tile costs a full HBM round trip at the head of every CTA's
@@ -637,8 +642,10 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
         cudaLaunchAttribute pattr[1];
         pattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         pattr[0].val.programmaticStreamSerializationAllowed = 1;
-        pcfg.attrs = pattr; pcfg.numAttrs = 0;
-        GCA_CUDA(cudaLaunchKernelEx(&pcfg, infonce_prep_kernel, P.q, P.k, P.B, P.Bpad, P.inv_T, (__nv_bfloat16*)P.q_bf16_ws,
+        static int prep_pdl = -1;                              // GCA_PREP_PDL=0: plain stream order in front of the prep launch (A/B timing)
+        if (prep_pdl < 0) { const char* e = getenv("GCA_PREP_PDL"); prep_pdl = (e && e[0] == '0') ? 0 : 1; }
+        pcfg.attrs = pattr; pcfg.numAttrs = (pdl_enabled() && prep_pdl) ? 1 : 0;
+        GCA_CUDA(launch_ex(&pcfg, infonce_prep_kernel, P.q, P.k, P.B, P.Bpad, P.inv_T, (__nv_bfloat16*)P.q_bf16_ws,
                                     P.pos_ws, P.pos_out, debug_timebuf(), P.xchg, nprep, P.counter + 6,
                                     P.k_hat, P.inv_nq, P.normalize,
                                     pf_on ? (const char*)P.queue : (const char*)nullptr, pf_bytes,
@@ -663,7 +670,7 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
 #define GCA_TC_LAUNCH(ACC, FIX) do { \
         auto kern = infonce_tc_kernel<ACC, FIX>; \
         GCA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES)); \
-        GCA_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, qmap, P, dbg)); } while (0)
+        GCA_CUDA(launch_ex(&cfg, kern, tmap, qmap, P, dbg)); } while (0)
     if (want_acc) { if (fixed_max) GCA_TC_LAUNCH(true, true); else GCA_TC_LAUNCH(true, false); }
     else          { if (fixed_max) GCA_TC_LAUNCH(false, true); else GCA_TC_LAUNCH(false, false); }
 #undef GCA_TC_LAUNCH

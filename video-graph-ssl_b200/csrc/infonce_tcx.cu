@@ -24,6 +24,7 @@
 #include "gca_common.cuh"
 #include "infonce_params.cuh"
 #include "tc_ptx.cuh"
+#include "launch_plan.cuh"
 #include <stdlib.h>
 
 
@@ -479,10 +480,10 @@ int infonce_tcx_launch(const InfoNceStreamParams& P, cudaStream_t st)
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
     if (dbg.timebuf) {
         GCA_CUDA(cudaFuncSetAttribute(infonce_tcx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X_SMEM_BYTES));
-        GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_tcx_kernel<true>, tmap, qmap, P, dbg, m_ref0, rank_cap));
+        GCA_CUDA(launch_ex(&cfg, infonce_tcx_kernel<true>, tmap, qmap, P, dbg, m_ref0, rank_cap));
     } else {
         GCA_CUDA(cudaFuncSetAttribute(infonce_tcx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X_SMEM_BYTES));
-        GCA_CUDA(cudaLaunchKernelEx(&cfg, infonce_tcx_kernel<false>, tmap, qmap, P, dbg, m_ref0, rank_cap));
+        GCA_CUDA(launch_ex(&cfg, infonce_tcx_kernel<false>, tmap, qmap, P, dbg, m_ref0, rank_cap));
     }
     GCA_LAUNCH_CHECK("infonce_tcx_kernel");
     return GCA_OK;

@@ -100,6 +100,11 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "gca_bn1d_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gca_plan_begin": (c_int, []),
+    "gca_plan_end": (c_int, [c_void_p]),
+    "gca_plan_run": (c_int, [c_void_p, c_void_p]),
+    "gca_plan_launches": (c_int, [c_void_p]),
+    "gca_plan_destroy": (None, [c_void_p]),
     "gca_sim_topk_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gca_sim_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_size_t, c_void_p]),
@@ -162,3 +167,46 @@ def call(name, *args):
             return
     rc = fn(*args)
     check(name, rc)
+
+
+class LaunchPlan(object):
+    """gca_plan_* of include/gca_b200.h: the launches of one step recorded once, re-issued by `run(stream)` with one library
+    call (three host-side launch calls for a head step; programmatic dependent launch between them and across steps)."""
+
+    def __init__(self, handle, device):
+        self.handle, self.device = handle, device
+        lib = load()
+        self._run = lib.gca_plan_run
+        self.launches = int(lib.gca_plan_launches(handle))
+
+    @classmethod
+    def record(cls, issue, device):
+        """`issue()` makes the library calls to record (tcgen05-family step entry points only) with `device` current."""
+        import torch
+        lib = load()
+        with torch.cuda.device(device):
+            check("gca_plan_begin", lib.gca_plan_begin())
+            handle = c_void_p()
+            try:
+                issue()
+            except BaseException:
+                lib.gca_plan_end(ctypes.byref(handle))
+                if handle.value:
+                    lib.gca_plan_destroy(handle)
+                raise
+            check("gca_plan_end", lib.gca_plan_end(ctypes.byref(handle)))
+        return cls(handle, device)
+
+    def run(self, stream):
+        """Re-issue the recorded launches on `stream` (raw cudaStream_t as int / c_void_p) of the plan's device."""
+        rc = self._run(self.handle, stream)
+        if rc != GCA_OK:
+            check("gca_plan_run", rc)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h is not None and _lib is not None:
+            try:
+                _lib.gca_plan_destroy(h)
+            except Exception:
+                pass
