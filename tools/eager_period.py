@@ -39,5 +39,6 @@ out = {}
 for rep in range(2):
     out["graph_%d" % rep] = run(lambda i: steps[i % POOL].graph.replay(), 3000)
     out["eager_%d" % rep] = run(lambda i: steps[i % POOL]._enqueue_work(st), 3000)
+    out["plan_%d" % rep] = run(lambda i: steps[i % POOL].step(), 3000)
 out["loss"] = [float(steps[0].loss), float(steps[1].loss)]
 print(json.dumps(out))
