@@ -545,6 +545,7 @@ def run_multi(args, rank, world, local_rank):
     for i in range(pool):
         s = GraphedReplicaStep(mocos[i], B, state=states[i], exchange=exchange, fuse_exchange=(xmode == "fused"), want_rank=False)
         s.inputs[:2 * B].copy_(batches[i % len(batches)])
+        s.prefer_graph = os.environ.get("GCA_BENCH_PREFER_GRAPH") == "1"     # A/B: one CUDA-graph launch per step
         steps_g.append(s)
     graphed = True
     torch.cuda.synchronize()
@@ -686,7 +687,8 @@ def run_multi(args, rank, world, local_rank):
                                          "NVLink peer-memory stores fused into the step's own launches" if xmode == "fused" else
                                          "gca_keys_exchange: one NVLink peer-memory kernel per step", B * world),
                        "key_exchange": "nccl" if exchange is None else ("fused_p2p" if xmode == "fused" else "p2p_kernel"),
-                       "cuda_graph": graphed and steps_g[0].plan is None, "launch_plan": graphed and steps_g[0].plan is not None,
+                       "cuda_graph": graphed and (steps_g[0].plan is None or steps_g[0].prefer_graph),
+                       "launch_plan": graphed and steps_g[0].plan is not None and not steps_g[0].prefer_graph,
                        "queue_pool": QPOOL,
                        "outputs": "loss, dq[256,128], top-1/top-5 hit counts (rank_gt = NULL), enqueue + pointer",
                        "l2": "no flush needed: consecutive steps use %d distinct queue replicas + workspaces per rank (> 126 MB L2)" % QPOOL,

@@ -100,6 +100,21 @@ def main():
         assert torch.equal(sa.dq, sb.dq) and torch.equal(sa.rank, sb.rank) and torch.equal(sa.hits, sb.hits), step
         assert torch.equal(mocos[0].memory, mocos[1].memory), ("fused queue", step)
         assert int(sa.state[0]) == int(sb.state[0]) == mocos[0].index == mocos[1].index, step
+    # back to back, no synchronisation between the steps (the launch-plan path chains consecutive steps by programmatic
+    # dependent launch; the key push rides in the first launch with a late trigger), one rank delayed now and then: the
+    # queue, the ring pointer and the last step's results must still equal the NCCL step's
+    assert sb.plan is not None and sb.plan.launches == 3, "the fused replica step should run from a launch plan"
+    qs = [torch.nn.functional.normalize(torch.randn(B, d, device=dev, generator=gen)) for _ in range(8)]
+    ks = [torch.nn.functional.normalize(torch.randn(B, d, device=dev, generator=gen)) for _ in range(8)]
+    for s_, tag in ((sa, "nccl"), (sb, "plan")):
+        for step in range(40):
+            if tag == "plan" and step % 7 == rank % 7:
+                torch.cuda._sleep(int(3e5))
+            s_.step(qs[step % 8], ks[step % 8])
+        torch.cuda.synchronize()
+    assert torch.equal(sa.loss, sb.loss) and torch.equal(sa.dq, sb.dq) and torch.equal(sa.hits, sb.hits), "back-to-back results"
+    assert torch.equal(mocos[0].memory, mocos[1].memory), "back-to-back queue"
+    assert int(sa.state[0]) == int(sb.state[0]) == mocos[0].index == mocos[1].index
     ex.check()
     dist.barrier()
     torch.cuda.synchronize()

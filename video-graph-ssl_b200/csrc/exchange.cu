@@ -75,11 +75,14 @@ keys_push_kernel(const float4* __restrict__ keys_local, const PeerXchg X)
     xchg_push_slice(X, keys_local, step, blockIdx.x, blockIdx.y);
 }
 
+static thread_local bool t_push_forked = false;        // the key push of the step being issued went out on the side stream
+
 int keys_push_fork(const float* keys_local, const PeerXchg& X, cudaStream_t st)
 {
     cudaStream_t side;
     const int rc = side_stream_fork(st, &side);
     if (rc != GCA_OK) return rc;
+    t_push_forked = true;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(X.W, XCHG_SLICES); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = side;
     GCA_CUDA(launch_ex(&cfg, keys_push_kernel, (const float4*)keys_local, X));
@@ -88,7 +91,13 @@ int keys_push_fork(const float* keys_local, const PeerXchg& X, cudaStream_t st)
     return GCA_OK;
 }
 
-int keys_push_join(cudaStream_t st) { return side_stream_join(st); }
+// joins the side stream if (and only if) this step's key push went out on it
+int keys_push_join(cudaStream_t st)
+{
+    if (!t_push_forked) return GCA_OK;
+    t_push_forked = false;
+    return side_stream_join(st);
+}
 
 }  // namespace gca
 

@@ -38,6 +38,8 @@ struct InfoNceStreamParams {
     int    gather_Bl;        // > 0 (K-sharded step over peer memory): q = this rank's [q_loc; k_loc] block of 2 * gather_Bl rows;
                              // the prep launch pushes it to every peer and reads all B = W * gather_Bl rows from the mailbox
     float  q_scale;          // factor folded into the bf16 queries by the prep kernel (1, or log2(e)/T for infonce_tcx)
+    int    no_prep_wait;     // infonce_tcx: the prep launch triggers this kernel only after its rows are written (late trigger):
+                             // do not wait for its completion (push CTAs of a peer exchange ride in it)
 };
 
 // ffma family (infonce_ffma.cu)

@@ -432,13 +432,18 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
                     unsigned long long* timebuf, const PeerXchg X, int nprep, unsigned int* range_flag,
                     float* __restrict__ k_hat, float* __restrict__ inv_nq, int normalize,
                     const char* __restrict__ pf_base, unsigned long long pf_bytes, float q_scale, const int npush,
-                    const int gather_Bl)
+                    const int gather_Bl, const int late_trigger)
 {
     // launched with a programmatic dependency on whatever kernel precedes it in the stream (normally the finalize launch of the
     // previous step, whose enqueue CTAs write the queue): resident and past its launch latency when that kernel drains.
     // Nothing of this step may start before it has completed -- the sweep's first queue tiles are loaded before ITS wait.
     ptx::pdl_wait();
-    ptx::pdl_launch_dependents();            // the streaming kernel may start its setup and its first queue-tile loads
+    // late_trigger (replica step with the key push riding in this launch): the row CTAs release the streaming kernel only
+    // AFTER their rows are written and fenced -- its launch is then the "rows are ready" signal and it never waits for the
+    // completion of this launch, i.e. for the NVLink round trip of the push CTAs' system-scope releases.  Otherwise the
+    // streaming kernel may start its setup and its first queue-tile loads right away (it waits for this launch later).
+    const bool row_cta = (int)blockIdx.x >= npush;
+    if (!(late_trigger && row_cta)) ptx::pdl_launch_dependents();
     // warm the L2 with the head of the queue (the first tile waves of the stream kernel): this launch starts ~1 us before
     // the stream kernel's TMA producer can, and a cold queue tile costs a full HBM round trip at the head of every CTA's
     // pipeline.  32 KB bulk prefetches, dealt round-robin over the CTAs of this launch (a few per SM).
@@ -514,6 +519,10 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
         if (fabsf(dsum) > 1.0625f * inv_T) range_flag[0] = 1u;        // see the partial write of the stream kernel
     }
     if (timebuf && threadIdx.x == 0) atomicMax(timebuf + 32 * 1000 + 4, globaltimer_ns());       // bring-up only
+    if (late_trigger) {
+        __threadfence();                     // this thread's rows are visible device-wide before its CTA counts as triggered
+        ptx::pdl_launch_dependents();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -624,8 +633,20 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
         // the key push of the replica step goes out as its own small launch on a side stream (joined by the caller after the
         // step's last launch, gca_api.cu)
         const bool gather = P.xchg.mailboxes != nullptr && P.gather_Bl > 0;
-        const bool push_first = P.xchg.mailboxes != nullptr && !gather;
-        const int npush = gather ? P.xchg.W * XCHG_SLICES : 0;
+        // replica step on the single-pass kernel with programmatic launches, issued directly or from a launch plan: the key push
+        // rides in this launch and the row CTAs trigger late (see the kernel) -- one linear chain of launches, which also
+        // chains consecutive steps (24.6 us per step at 2 GPUs against 29.9 us).  Otherwise the push goes out on a side
+        // stream (the other stream kernels wait for the whole prep grid).
+        static int push_side = -1;                          // GCA_PUSH_SIDE=1: side-stream push everywhere (A/B timing)
+        if (push_side < 0) { const char* e = getenv("GCA_PUSH_SIDE"); push_side = (e && e[0] == '1') ? 1 : 0; }
+        // (a captured step is one graph launch: there the side branch is faster -- 29.9 us against 31.6 us at 2 GPUs)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (plan_recording() == nullptr && cudaStreamIsCapturing(st, &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
+        const bool late = P.xchg.mailboxes != nullptr && !gather && use_tcx && pdl_enabled() && !push_side &&
+                          cap == cudaStreamCaptureStatusNone;
+        const bool push_first = P.xchg.mailboxes != nullptr && !gather && !late;
+        const int npush = (gather || late) ? P.xchg.W * XCHG_SLICES : 0;
+        P.no_prep_wait = late ? 1 : 0;
         if (push_first) {
             rc = keys_push_fork(P.k, P.xchg, st);
             if (rc != GCA_OK) return rc;
@@ -649,7 +670,7 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
                                     P.pos_ws, P.pos_out, debug_timebuf(), P.xchg, nprep, P.counter + 6,
                                     P.k_hat, P.inv_nq, P.normalize,
                                     pf_on ? (const char*)P.queue : (const char*)nullptr, pf_bytes,
-                                    P.q_scale, npush, P.gather_Bl));
+                                    P.q_scale, npush, P.gather_Bl, late ? 1 : 0));
         GCA_LAUNCH_CHECK("infonce_prep_kernel");
         count_launch(1);
     }

@@ -220,8 +220,8 @@ infonce_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         if (warp < X_SM_WARPS) {
             // =========================================================================================== softmax warps
             if (npass == 0) {
-                pdl_wait();                                           // prep kernel results are visible from here
-                pos_nat0 = P.pos_ws[row];                             // natural-log units (q.k / T); 0 for padding rows
+                if (!P.no_prep_wait) pdl_wait();                      // prep kernel results are visible from here (late trigger:
+                pos_nat0 = __ldcg(P.pos_ws + row);                    // they were before this kernel could launch).  q.k / T
                 pos_l2 = pos_nat0 * 1.4426950408889634f;
                 if (split == 0 && blockIdx.y == 0 && threadIdx.x == 0) { for (int w = 0; w < 6; ++w) P.counter[w] = 0u; }   // re-arm the finalize control block
                 X_STAMP(3);
@@ -324,7 +324,7 @@ infonce_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     if (kDbg) x_stamp(dbg, 9);
                     const int pre = n < X_TMA_LEAD ? n : X_TMA_LEAD;
                     for (; v0 < pre; ++v0) load_tile(v0);
-                    pdl_wait();                                           // q_bf16 comes from the prep kernel
+                    if (!P.no_prep_wait) pdl_wait();                      // q_bf16 comes from the prep kernel
                     mbar_arrive_expect_tx(&bar->q_ready, (uint32_t)X_QTILE_BYTES);
                     tma_load_2d(qtile, &qmap, &bar->q_ready, 0, row0);
                     tma_load_2d(qtile + X_HALF_BYTES, &qmap, &bar->q_ready, 64, row0);
