@@ -276,6 +276,10 @@ def run_single(args):
     lib = _lib.load()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
+    # the launching thread and the pinned host buffers of the e2e leg go to the GPU's own NUMA node (gca_b200/affinity.py);
+    # undone before the CPU baseline leg, which uses every host core
+    from gca_b200 import affinity
+    aff = affinity.bind_cpu_to_device(0) if os.environ.get("GCA_BENCH_NO_BIND") != "1" else {"bound": False, "source": "off"}
     torch.manual_seed(1)
     batches = synthetic_batches(2, POOL, B, B, device=dev)
     # QPOOL replicas of the queue, one captured step each (the step's inputs cycle through POOL batches): consecutive timed
@@ -340,12 +344,16 @@ def run_single(args):
     e2e_t = []
     e2e_steps = min(args.steps, 2000)
     e2e_loss = 0.0
+    e2e_sync = os.environ.get("GCA_BENCH_E2E_SYNC") == "1"     # A/B: cudaDeviceSynchronize instead of the completion word
     for i in range(args.warmup + e2e_steps):
         flush.fill_(i & 1)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        steps_g[i % POOL].step_host_io()
-        torch.cuda.synchronize()
+        if e2e_sync:
+            steps_g[i % POOL].step_host_io()
+            torch.cuda.synchronize()
+        else:
+            steps_g[i % POOL].step_host_io(wait=True)      # returns when the results are in the host buffer (completion word)
         e2e_loss = float(host_outs[i % POOL][0])           # the step's result, read on the host
         if i >= args.warmup:
             e2e_t.append(time.perf_counter() - t1)
@@ -450,6 +458,7 @@ def run_single(args):
     secondary = None if args.no_secondary else secondary_measurements(dev, flush, pk)
     pretrain = None if args.no_secondary else pretrain_clips(0, 1, dev)
 
+    affinity.restore(aff)
     cpu_rate, cpu_ms, cpu_n, cores = cpu_head_rate(60, 2, budget_s=15.0) if not args.no_cpu else (None, None, 0, 0)
     line = {
         "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -470,13 +479,16 @@ def run_single(args):
                                 "(round 1's method; includes the launch latency of a lone step)",
         "wall_s_total": wall, "loss_last": loss_last,
         "clocks": clocks,
+        "cpu_affinity": {k: aff.get(k) for k in ("bound", "source", "cpus")},
         "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                 "path": ("GraphedMoCoStep.step_host_io(): the step's first kernel reads q|k from the pinned host buffer over PCIe "
                          "(zero-copy, each once), its enqueue CTAs read all_k from it, " if zc_in else
                          "GraphedMoCoStep.step_host_io(): pinned host q|k|all_k -> H2D copy -> step (C ABI), ") +
-                        "its last kernel stores loss|top-k hits|dq straight into the pinned host result buffer -- %s, "
-                        "stream synchronised and the loss read on the host every step"
-                        % "one CUDA-graph launch (a synchronous step wants a single submission)",
+                        "its last kernel stores loss|top-k hits|dq straight into the pinned host result buffer -- one CUDA-graph "
+                        "launch (a synchronous step wants a single submission), " +
+                        ("the device is synchronised and the loss read on the host every step" if e2e_sync else
+                         "the host waits for the step's completion word in the pinned result buffer (gca_workspace_set_done_flag) "
+                         "and reads the loss every step"),
                 "zero_copy_in": zc_in,
                 "loss_last": e2e_loss},
         "gpu_launches": launches,
@@ -504,6 +516,8 @@ def run_multi(args, rank, world, local_rank):
     lib = _lib.load()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    from gca_b200 import affinity
+    aff = affinity.bind_cpu_to_device(local_rank) if os.environ.get("GCA_BENCH_NO_BIND") != "1" else {"bound": False, "source": "off"}
     dist.init_process_group("nccl", device_id=dev)
     # QPOOL queue replicas per rank (consecutive timed steps stream disjoint working sets from HBM, see run_single); every
     # rank draws its own and rank 0's wins, as upstream (train_video_contrast_dis.py:233-242)
@@ -696,6 +710,7 @@ def run_multi(args, rank, world, local_rank):
                                  "both sides, max over ranks; value = n_gpus * steps / elapsed (each global step processes "
                                  "n_gpus x 256 rows)"},
             "ms_per_step_isolated": float(iso_t), "wall_s_total": wall, "loss_last": loss_last, "replicas_consistent": consistent, "clocks": clocks,
+            "cpu_affinity": {k: aff.get(k) for k in ("bound", "source", "cpus")},
             "e2e": {"value": world * 1e3 / float(e2e), "unit": UNIT, "h2d_bytes_per_step": 2 * B * D * 4,
                     "d2h_bytes_per_step": g0.outputs.numel() * 4, "ms_per_step": float(e2e),
                     "path": "GraphedReplicaStep.step_host_io(): one graph launch per step, q|k read from / results stored to pinned "

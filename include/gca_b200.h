@@ -211,6 +211,14 @@ int gca_moco_step_peer(const float* q, const float* k, void* queue, int dtype_qu
                        long long* state, float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt,
                        int* top_hits, float* dq_unit, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Host-visible completion word for callers whose step results land in pinned host memory (zero-copy outputs): once armed
+ * for a workspace, the last launch of every gca_infonce_fwd / gca_moco_step* call on that workspace stores the number of
+ * steps completed on it (1, 2, ...) into *host_word -- a 32-bit word in pinned, device-addressable host memory -- after all
+ * of the step's stores are visible system-wide and its host-resident inputs have been read.  A host thread that polls the
+ * word replaces the stream synchronisation after the step (~1 us instead of the driver's wake-up path).  host_word == NULL
+ * disarms.  Synchronises `stream` (a set-up call, not a per-step one). */
+int gca_workspace_set_done_flag(void* workspace, unsigned int* host_word, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Launch plans.  A head step is 3-4 kernel launches whose parameters do not change from step to step when the caller
  * uses static buffers and the device-resident ring pointer (`state` != NULL) -- what the reference's training loop does

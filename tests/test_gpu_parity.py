@@ -1097,11 +1097,17 @@ def test_graphed_step_host_io_equals_device_step(lib, zero_copy_out, zero_copy_i
         pk = torch.cat([unit_rows(B, 128, gen), unit_rows(B, 128, gen), unit_rows(B, 128, gen)])
         host_in.copy_(pk)
         a.step(cu(pk[:B]), cu(pk[B:2 * B]), cu(pk[2 * B:]))
-        b.step_host_io()
+        # wait=True: with zero-copy outputs the host polls the step's completion word (the pad word [3] of the result block)
+        # instead of synchronising the stream -- the results must be complete the moment it returns
+        b.step_host_io(wait=True)
+        got = host_out.clone()
+        if zero_copy_out:
+            assert int(host_out[3:4].view(torch.int32)) == it + 1                            # steps completed on this workspace
+            host_in[:2 * B].zero_()                                                          # inputs are consumed: free to overwrite
         torch.cuda.synchronize()
         ref = a.outputs.cpu()
-        assert torch.equal(host_out[:3], ref[:3]) and torch.equal(host_out[4:], ref[4:])      # [3] is padding
-        assert float(host_out[0]) == float(a.loss)
+        assert torch.equal(got[:3], ref[:3]) and torch.equal(got[4:], ref[4:])
+        assert float(got[0]) == float(a.loss)
         assert torch.equal(mocos[0].memory, mocos[1].memory) and mocos[0].index == mocos[1].index == (it + 1) * B
 
 

@@ -12,6 +12,12 @@ from gca_b200.graphed import GraphedMoCoStep
 B, K = 256, 65536
 moco = gca_b200.RGBMoCo(128, K=K, queue_dtype="bf16").cuda()
 step = GraphedMoCoStep(moco, B, B).capture()
+HOSTIO = os.environ.get("HOSTIO") == "1"              # the e2e variant: q | k | all_k read from / results stored to pinned host memory
+if HOSTIO:
+    host_in = torch.nn.functional.normalize(torch.randn(3 * B, 128)).pin_memory()
+    host_out = torch.empty_like(step.outputs, device="cpu").pin_memory()
+    step.capture_host_io(host_in, host_out, zero_copy_out=True, zero_copy_in=True)
+    step.graph = step.graph_io
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 BIG = 1 << 62
 for cold in (True, False):

@@ -32,6 +32,30 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigne
     return last;
 }
 
+// Optional completion word in (pinned) host memory, armed per workspace by gca_workspace_set_done_flag: every CTA of a
+// FIN_FULL launch -- row CTAs and enqueue CTAs -- orders its stores before a device-scope count; the CTA that takes the last
+// count fences at system scope and publishes the step number.  A host thread polling that word sees a step complete (results stored, host inputs
+// consumed) about a microsecond after the kernel's last store, without the driver's stream-synchronisation round trip.
+__device__ __forceinline__ void publish_done(unsigned int* counter)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long p = *reinterpret_cast<volatile unsigned long long*>(counter + 12);
+        if (p != 0ull) {
+            __threadfence();                                   // this CTA's stores (device and host) are ordered before its count
+            if (atomicAdd(counter + 14, 1u) == gridDim.x - 1u) {
+                counter[14] = 0u;
+                const unsigned int seq = counter[15] + 1u;
+                counter[15] = seq;
+                // ONE system-scope fence, by the CTA that has observed every other CTA's count: cumulativity orders all their
+                // stores before the completion word for an observer on the host (320 system fences cost ~4 us per step)
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int*>(p) = seq;
+            }
+        }
+    }
+}
+
 // mean of rows[0..n) in a fixed order, by one block
 __device__ __forceinline__ float block_mean_fixed(const float* rows, int n, float* red)
 {
@@ -135,6 +159,7 @@ infonce_finalize_kernel(const FinalizeParams F)
     if (kMode == FIN_FULL && (int)blockIdx.x >= F.B) {        // fused enqueue CTAs
         if (F.enq_dtype == GCA_F32) enqueue_rows<float>(F, blockIdx.x - F.B, gridDim.x - F.B);
         else                        enqueue_rows<__nv_bfloat16>(F, blockIdx.x - F.B, gridDim.x - F.B);
+        publish_done(F.counter);
         return;
     }
     const int b = blockIdx.x;
@@ -436,6 +461,7 @@ infonce_finalize_kernel(const FinalizeParams F)
             }
         }
     }
+    if (kMode == FIN_FULL) publish_done(F.counter);
 }
 
 int infonce_finalize_launch(const FinalizeParams& F_, int mode, cudaStream_t st)

@@ -286,6 +286,21 @@ extern "C" void gca_plan_destroy(gca_plan* p)
     delete p;
 }
 
+extern "C" int gca_workspace_set_done_flag(void* workspace, unsigned int* host_word, void* stream)
+{
+    using namespace gca;
+    GCA_CHECK_ARG(workspace != nullptr, "gca_workspace_set_done_flag: null workspace");
+    // control words 12..13 of the workspace (gca_common.cuh): the pointer the finalize launch publishes the step number to
+    static thread_local unsigned long long staged[16];
+    static thread_local int slot = 0;
+    unsigned long long* src = &staged[slot++ & 15];          // (the async copy reads it later: one slot per recent call)
+    *src = (unsigned long long)(uintptr_t)host_word;
+    GCA_CUDA(cudaMemcpyAsync((char*)workspace + 12 * sizeof(unsigned int), src, sizeof(unsigned long long), cudaMemcpyHostToDevice,
+                             (cudaStream_t)stream));
+    GCA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return GCA_OK;
+}
+
 extern "C" size_t gca_infonce_workspace_bytes(int B, long long K, int d, int dtype_queue, int algo)
 {
     using namespace gca;

@@ -26,7 +26,10 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 // ---------------------------------------------------------------------------------------------
 // Workspace layout shared by the InfoNCE stream kernels and the finalize kernels.
-//   [0, 256)                 : control block (block-completion counter, self-resetting)
+//   [0, 256)                 : control block, 64 words: [0] ticket, [2..3] packed loss / hit word, [4] top-1, [5] top-5 hits,
+//                              [6] out-of-range-logit flag (all self-resetting); [12..13] device-addressable pointer to a
+//                              32-bit host completion word (gca_workspace_set_done_flag; 0 = off), [14] CTAs of the finalize
+//                              launch that are done, [15] number of completed steps (what is written to the completion word)
 //   part_max [nsplit, Bpad]  : natural-log max logit of the split        (-inf when the split is empty)
 //   part_sum [nsplit, Bpad]  : sum exp(logit - part_max)
 //   part_cnt [nsplit, Bpad]  : #negatives > positive in the split

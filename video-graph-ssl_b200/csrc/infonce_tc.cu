@@ -466,7 +466,7 @@ infonce_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, in
         xchg_push_slice(X, reinterpret_cast<const float4*>(gather_Bl > 0 ? q : k), step, e / XCHG_SLICES, e % XCHG_SLICES);
         return;
     }
-    const int lane = threadIdx.x & 31, row = rb * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, row = rb * (int)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (timebuf && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -628,7 +628,9 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
     // loss + gradient in one sweep (the product path): second-generation stream kernel (infonce_tcx.cu)
     const bool use_tcx = P.part_acc != nullptr && !fixed_max && P.logits_out == nullptr && infonce_tcx_enabled();
     if (!P.skip_prep) {
-        const int nprep = (P.Bpad + 7) / 8;
+        int prep_rows = 8;                                   // rows (warps) per CTA of the prep launch
+        { const char* e = getenv("GCA_PREP_ROWS"); if (e && P.xchg.mailboxes == nullptr) { const int r = atoi(e); if (r == 1 || r == 2 || r == 4) prep_rows = r; } }
+        const int nprep = (P.Bpad + prep_rows - 1) / prep_rows;
         // peer exchange: the q|k gather of the K-sharded step rides in this launch (its rows are needed by this very launch);
         // the key push of the replica step goes out as its own small launch on a side stream (joined by the caller after the
         // step's last launch, gca_api.cu)
@@ -657,9 +659,9 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
         unsigned long long pf_bytes = (unsigned long long)P.K * TC_D * 2;
         const unsigned long long pf_waves = 2ull * (unsigned long long)P.nsplit * TC_STAGE_BYTES;   // tiles 0 and 1 of every split
         if (pf_bytes > pf_waves) pf_bytes = pf_waves;
-        if ((unsigned long long)nprep * 256ull * 32768ull < pf_bytes) pf_bytes = (unsigned long long)nprep * 256ull * 32768ull;
+        if ((unsigned long long)nprep * (32ull * prep_rows) * 32768ull < pf_bytes) pf_bytes = (unsigned long long)nprep * (32ull * prep_rows) * 32768ull;
         cudaLaunchConfig_t pcfg{};
-        pcfg.gridDim = dim3(nprep + npush); pcfg.blockDim = dim3(256); pcfg.dynamicSmemBytes = 0; pcfg.stream = st;
+        pcfg.gridDim = dim3(nprep + npush); pcfg.blockDim = dim3(32 * prep_rows); pcfg.dynamicSmemBytes = 0; pcfg.stream = st;
         cudaLaunchAttribute pattr[1];
         pattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         pattr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -100,6 +100,7 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "gca_bn1d_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gca_workspace_set_done_flag": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gca_plan_begin": (c_int, []),
     "gca_plan_end": (c_int, [c_void_p]),
     "gca_plan_run": (c_int, [c_void_p, c_void_p]),
