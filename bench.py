@@ -262,6 +262,27 @@ def secondary_measurements(dev, flush, pk):
                                "tflops_bf16_equiv": 6 * 2.0 * 3783 * 13320 * 512 / (ms * 1e-3) / 1e12}
     except Exception as e:
         out["retrieval_c5"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    try:
+        # instance-bank mode (MEM_TYPE 'bank', lib/memory/mem_bank.py): bsz 256, 16384 sampled negatives, 240k-clip bank
+        Bb, Kb, nb = 256, 16384, 240000
+        bank = F.normalize(torch.randn(nb, D, device=dev))
+        xb = F.normalize(torch.randn(Bb, D, device=dev)).requires_grad_(True)
+        yb = torch.randperm(nb, device=dev)[:Bb]
+        ib = torch.randint(0, nb, (Bb, Kb + 1), device=dev)
+        ib[:, 0] = yb
+        wb = torch.randn(Bb, Kb + 1, device=dev)
+
+        def bank_step():
+            lg = GF.bank_logits(xb, bank, ib, T)
+            torch.autograd.grad(lg, (xb,), wb)
+            GF.bank_update_(bank, xb, yb, 0.5)
+        ms = _time_graph(bank_step, flush, iters=8, warm=2)
+        gathered = 2.0 * Bb * (Kb + 1) * D * 4
+        out["instance_bank"] = {"what": "bank logits + dx + momentum update (gca_bank_*), bsz 256, K 16384, d 128, n_data 240000",
+                                "ms": ms, "steps_per_s": 1e3 / ms, "alg_bytes": gathered,
+                                "hbm_frac": gathered / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
+    except Exception as e:
+        out["instance_bank"] = {"error": "%s: %s" % (type(e).__name__, e)}
     return out
 
 

@@ -211,6 +211,27 @@ int gca_moco_step_peer(const float* q, const float* k, void* queue, int dtype_qu
                        long long* state, float* loss_mean, float* loss_rows, float* lse, float* pos_logit, int* rank_gt,
                        int* top_hits, float* dq_unit, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * NPID instance bank (RGBMem / CMCMem, lib/memory/mem_bank.py:15-90; the MEM_TYPE 'bank' branch of lib/memory/build.py:6-9).
+ *   bank   [n_data, d] fp32 row-major (L2-normalised rows), x [B, d] fp32, idx [B, K1] int64 (K1 = K + 1 sampled bank rows
+ *   per feature row, column 0 the positive: mem_bank.py:64-66), d a multiple of 4 up to 1024.
+ * gca_bank_logits : logits[b, j] = <bank[idx[b, j]], x[b]> * inv_T      (index_select + bmm + div, mem_bank.py:67-73, 29-39)
+ *                   without materialising the [B, K1, d] gather.  An index outside [0, n_data) yields NaN.
+ * gca_bank_dx     : dx[b] = inv_T * sum_j g_logits[b, j] * bank[idx[b, j]]  -- autograd of the above w.r.t. x (the bank is a
+ *                   buffer).  Fixed-order sums (deterministic).
+ * gca_bank_update : bank[y[n]] <- normalize(momentum * bank[y[n]] + one_minus_momentum * x[n]), n < N  (mem_bank.py:15-27):
+ *                   every row is computed from the bank as it was BEFORE the call; of a duplicated index the last
+ *                   occurrence wins (index_copy_ on the CPU).  Pass one_minus_momentum = (float)(1.0 - momentum) computed in
+ *                   double, as the reference's Python expression does. */
+int gca_bank_logits(const float* x, const float* bank, const long long* idx, int B, int K1, int d, long long n_data,
+                    float inv_T, float* logits, void* stream);
+size_t gca_bank_dx_workspace_bytes(int B, int d);
+int gca_bank_dx(const float* g_logits, const float* bank, const long long* idx, int B, int K1, int d, long long n_data,
+                float inv_T, float* dx, void* workspace, size_t workspace_bytes, void* stream);
+size_t gca_bank_update_workspace_bytes(int N, int d);
+int gca_bank_update(float* bank, const float* x, const long long* y, int N, int d, long long n_data, float momentum,
+                    float one_minus_momentum, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Host-visible completion word for callers whose step results land in pinned host memory (zero-copy outputs): once armed
  * for a workspace, the last launch of every gca_infonce_fwd / gca_moco_step* call on that workspace stores the number of
  * steps completed on it (1, 2, ...) into *host_word -- a 32-bit word in pinned, device-addressable host memory -- after all

@@ -875,6 +875,83 @@ def test_retrieval_large_gallery_massive_ties(GF):
     assert (got[1:] != oidx[1:]).mean() < 0.01
 
 
+# ============================================================================================ K13 instance bank
+def test_instance_bank_matches_reference_fixture(GF, golden):
+    """gca_b200.RGBMem / CMCMem against tests/golden/bank.npz (the reference's own modules): logits, d loss / d x under
+    NCESoftmaxLoss (also of the jigsaw head), the bank after the momentum update incl. a duplicated index."""
+    import gca_b200
+    g = golden("bank")
+    n_data, K, T, m = int(g["n_data"]), int(g["K"]), float(g["T"]), float(g["m"])
+    bank = gca_b200.RGBMem(128, n_data, K=K, T=T, m=m).cuda()
+    bank.load_state_dict({"memory": T_(g["rgb_memory_before"])})
+    crit = gca_b200.NCESoftmaxLoss()
+    for st in range(2):
+        x = cu(T_(g["rgb%d_x" % st])).requires_grad_(True)
+        y, idx = cu(T_(g["rgb%d_y" % st])), cu(T_(g["rgb%d_idx" % st]))
+        if st == 1:
+            xj = cu(T_(g["rgb1_x_jig"])).requires_grad_(True)
+            logits, logits_jig, labels = bank(x, y, xj, cu(T_(g["rgb1_all_x"])), cu(T_(g["rgb1_all_y"])), idx=idx)
+            (crit(logits) + crit(logits_jig)).backward()
+            assert rel_max(logits_jig, T_(g["rgb1_logits_jig"])) <= 2e-6 and rel_max(xj.grad, T_(g["rgb1_dx_jig"])) <= 1e-5
+        else:
+            logits, labels = bank(x, y, idx=idx)
+            crit(logits).backward()
+        assert labels.dtype == torch.long and int(labels.abs().sum()) == 0
+        assert rel_max(logits, T_(g["rgb%d_logits" % st])) <= 2e-6
+        assert rel_max(x.grad, T_(g["rgb%d_dx" % st])) <= 1e-5
+        after = T_(g["rgb%d_memory_after" % st])
+        assert float((bank.memory.cpu() - after).abs().max()) <= 2e-7
+    two = gca_b200.CMCMem(128, n_data, K=K, T=T, m=m).cuda()
+    two.load_state_dict({"memory_1": T_(g["cmc_memory_1_before"]), "memory_2": T_(g["cmc_memory_2_before"])})
+    x1, x2 = cu(T_(g["cmc_x1"])).requires_grad_(True), cu(T_(g["cmc_x2"])).requires_grad_(True)
+    l1, l2, labels = two(x1, x2, cu(T_(g["cmc_y"])), idx=cu(T_(g["cmc_idx"])))
+    (crit(l1) + crit(l2)).backward()
+    assert rel_max(l1, T_(g["cmc_logits1"])) <= 2e-6 and rel_max(l2, T_(g["cmc_logits2"])) <= 2e-6
+    assert rel_max(x1.grad, T_(g["cmc_dx1"])) <= 1e-5 and rel_max(x2.grad, T_(g["cmc_dx2"])) <= 1e-5
+    assert float((two.memory_1.cpu() - T_(g["cmc_memory_1_after"])).abs().max()) <= 2e-7
+    assert float((two.memory_2.cpu() - T_(g["cmc_memory_2_after"])).abs().max()) <= 2e-7
+
+
+@pytest.mark.parametrize("B,K,d,n_data", [(7, 33, 64, 500), (64, 4096, 128, 20000), (16, 1000, 320, 3000), (256, 16384, 128, 100000)])
+def test_instance_bank_kernels_match_oracle(GF, B, K, d, n_data):
+    """gca_bank_logits / gca_bank_dx / gca_bank_update at ragged and at full size (256 x 16385 sampled rows) against
+    oracle/bank.py: logits and gradients to fp32 rounding, the drawn indices stay inside the bank, the update with
+    duplicated indices keeps the LAST occurrence and leaves every other row untouched (bit-exact)."""
+    from oracle import bank as ob
+    import gca_b200
+    gen = torch.Generator().manual_seed(B + K + d)
+    mem = unit_rows(n_data, d, gen)
+    x = unit_rows(B, d, gen)
+    idx = torch.randint(0, n_data, (B, K + 1), generator=gen)
+    xg = cu(x).requires_grad_(True)
+    logits = GF.bank_logits(xg, cu(mem), cu(idx), 0.07)
+    w = torch.randn(B, K + 1, generator=gen)
+    (logits * cu(w)).sum().backward()
+    ref = ob.bank_logits(x.double(), mem.double(), idx, 0.07)
+    assert rel_max(logits, ref) <= 2e-6
+    assert rel_max(xg.grad, ob.bank_grad_x(w.double(), mem.double(), idx, 0.07)) <= 2e-5
+    # update: N rows, some indices twice
+    N = min(2 * B, 300)
+    y = torch.randint(0, n_data, (N,), generator=gen)
+    y[N // 2] = y[1]
+    y[N - 1] = y[0]
+    feats = unit_rows(N, d, gen)
+    dmem = cu(mem).clone()
+    GF.bank_update_(dmem, cu(feats), cu(y), 0.5)
+    expect = ob.bank_update(mem.clone(), feats, y, 0.5)
+    got = dmem.cpu()
+    touched = torch.zeros(n_data, dtype=torch.bool)
+    touched[y] = True
+    assert torch.equal(got[~touched], mem[~touched])                      # untouched rows: bit-exact
+    assert float((got[touched] - expect[touched]).abs().max()) <= 2e-7
+    # the module draws in-range indices with the positive in column 0
+    bank = gca_b200.RGBMem(d, n_data, K=K).cuda()
+    yy = cu(torch.randint(0, n_data, (B,), generator=gen))
+    with torch.no_grad():
+        lg, labels = bank(cu(x), yy)
+    assert lg.shape == (B, K + 1) and bool(torch.isfinite(lg).all())
+
+
 # ============================================================================================ full-size properties
 def test_headline_shape_full_size(GF):
     """BASELINE metric shape (B=256, K=65536, d=128): both modes against the fp64 oracle, pointer wrap over a lap."""

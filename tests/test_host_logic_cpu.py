@@ -30,6 +30,33 @@ def test_factories_follow_reference_contract():
         gca_b200.create_criterion(cfg(crit="nope"), 1)
     b = gca_b200.create_contrast(cfg(QUEUE_DTYPE="bf16"), 1)
     assert b.memory.dtype == torch.bfloat16
+    # the instance-bank branch (lib/memory/build.py:6-9, 24-25)
+    bank = gca_b200.create_contrast(cfg("bank", K=32), n_data=50)
+    assert isinstance(bank, gca_b200.RGBMem) and (bank.K, bank.T, bank.m) == (32, 0.07, 0.5)
+    assert list(bank.state_dict().keys()) == ["memory"] and bank.memory.shape == (50, 128)
+    c2 = cfg("bank", K=32)
+    c2.CROSS.MODALITY = "cross"
+    two = gca_b200.create_contrast(c2, n_data=50)
+    assert isinstance(two, gca_b200.CMCMem) and list(two.state_dict().keys()) == ["memory_1", "memory_2"]
+    assert isinstance(gca_b200.create_criterion(cfg(crit="NCE"), 77), gca_b200.NCECriterion)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        bank(torch.randn(4, 128), torch.arange(4))
+
+
+def test_alias_sampler_and_nce_criterion_match_reference_fixture(golden):
+    """AliasMethod tables / draw arithmetic and NCECriterion of the drop-in against tests/golden/bank.npz (integer tables and
+    samples exact)."""
+    import numpy as np
+    from gca_b200.memory import AliasMethod
+    g = golden("bank")
+    am = AliasMethod(torch.from_numpy(g["alias_p"]))
+    assert torch.equal(am.prob, torch.from_numpy(g["alias_prob"])) and torch.equal(am.alias, torch.from_numpy(g["alias_alias"]))
+    torch.manual_seed(4)                                                   # the seed the fixture's reference draw used
+    assert torch.equal(am.draw(1000), torch.from_numpy(g["alias_draw"]))
+    uni = AliasMethod(torch.ones(9))
+    assert torch.equal(uni.prob, torch.ones(9))
+    loss = gca_b200.NCECriterion(int(g["n_data"]))(torch.from_numpy(g["nce_x"]))
+    np.testing.assert_allclose(float(loss), float(g["nce_loss"]), rtol=1e-6)
 
 
 def test_queue_init_consumes_rng_like_reference():

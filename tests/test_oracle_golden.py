@@ -229,3 +229,29 @@ def test_simsiam_mlp_restatement_matches_reference(golden, name):
         np.testing.assert_allclose(0.9 * p[blk + ".1.running_mean"] + 0.1 * c["mean"], g[name + ".after." + blk + ".1.running_mean"], atol=1e-5)
         np.testing.assert_allclose(0.9 * p[blk + ".1.running_var"] + 0.1 * c["var_unb"], g[name + ".after." + blk + ".1.running_var"], atol=1e-5)
         assert int(g[name + ".after." + blk + ".1.num_batches_tracked"]) == 1
+
+
+def test_instance_bank_restatement_matches_reference(golden):
+    """oracle/bank.py against tests/golden/bank.npz (RGBMem / CMCMem / AliasMethod / NCECriterion of the reference run by
+    oracle/gen_golden_bank.py): alias tables and the draw arithmetic exact, logits exact, gradients 1e-6, bank update exact
+    (incl. the duplicated index: the last occurrence wins)."""
+    from oracle import bank as ob
+    g = golden("bank")
+    prob, alias = ob.alias_tables(T_(g["alias_p"]))
+    assert torch.equal(prob, T_(g["alias_prob"])) and torch.equal(alias, T_(g["alias_alias"]))
+    assert torch.equal(ob.alias_pick(prob, alias, T_(g["alias_kk"]), T_(g["alias_b"])), T_(g["alias_draw"]))
+    T, m = float(g["T"]), float(g["m"])
+    mem = T_(g["rgb_memory_before"]).clone()
+    for st in range(2):
+        x, y, idx = T_(g["rgb%d_x" % st]), T_(g["rgb%d_y" % st]), T_(g["rgb%d_idx" % st])
+        assert torch.equal(idx[:, 0], y)
+        assert torch.equal(ob.bank_logits(x, mem, idx, T), T_(g["rgb%d_logits" % st]))
+        dx = ob.bank_grad_x(T_(g["rgb%d_glogits" % st]), mem, idx, T)
+        np.testing.assert_allclose(dx.numpy(), g["rgb%d_dx" % st], rtol=1e-5, atol=1e-7)
+        if st == 1:
+            assert torch.equal(ob.bank_logits(T_(g["rgb1_x_jig"]), mem, idx, T), T_(g["rgb1_logits_jig"]))
+            ob.bank_update(mem, T_(g["rgb1_all_x"]), T_(g["rgb1_all_y"]), m)
+        else:
+            ob.bank_update(mem, x, y, m)
+        assert torch.equal(mem, T_(g["rgb%d_memory_after" % st]))
+    np.testing.assert_allclose(float(ob.nce_criterion(T_(g["nce_x"]), int(g["n_data"]))), float(g["nce_loss"]), rtol=1e-6)

@@ -20,7 +20,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
          "--expt-relaxed-constexpr"]
 # accuracy-sensitive translation units keep IEEE expf/logf/div (the graph head must match torch to ~1e-6)
-PRECISE = {"graph.cu", "negcos.cu", "finalize.cu", "sim_tc.cu"}
+PRECISE = {"graph.cu", "negcos.cu", "finalize.cu", "sim_tc.cu", "bank.cu"}
 
 
 def nvcc():

@@ -5,8 +5,9 @@ Mirrors `lib.memory` (create_contrast / create_criterion / RGBMoCo / NCESoftmaxL
 interfaces runs in libgca_b200.so (hand-written CUDA, C ABI in include/gca_b200.h).  No CPU fallback.
 """
 from . import _lib, functional                                   # noqa: F401
-from .memory import (RGBMoCo, CMCMoCo, NCESoftmaxLoss, D, FusedLogits, create_contrast, create_criterion)  # noqa: F401
+from .memory import (RGBMoCo, CMCMoCo, RGBMem, CMCMem, NCESoftmaxLoss, NCECriterion, D, FusedLogits,  # noqa: F401
+                     create_contrast, create_criterion)
 from .ops import TemporalGraphAug, build_aug_block, get_agg, ProjectionMLP, PredictionMLP       # noqa: F401
 
-__all__ = ["RGBMoCo", "CMCMoCo", "NCESoftmaxLoss", "D", "FusedLogits", "create_contrast", "create_criterion",
+__all__ = ["RGBMoCo", "CMCMoCo", "RGBMem", "CMCMem", "NCESoftmaxLoss", "NCECriterion", "D", "FusedLogits", "create_contrast", "create_criterion",
            "TemporalGraphAug", "build_aug_block", "get_agg", "ProjectionMLP", "PredictionMLP", "functional"]

@@ -100,6 +100,13 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "gca_bn1d_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gca_bank_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_float, c_void_p, c_void_p]),
+    "gca_bank_dx_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gca_bank_dx": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_float, c_void_p, c_void_p, c_size_t,
+                            c_void_p]),
+    "gca_bank_update_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gca_bank_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_float, c_float, c_void_p, c_size_t,
+                                c_void_p]),
     "gca_workspace_set_done_flag": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gca_plan_begin": (c_int, []),
     "gca_plan_end": (c_int, [c_void_p]),

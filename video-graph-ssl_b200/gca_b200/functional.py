@@ -359,3 +359,63 @@ def cosine_topk(queries, gallery, k, normalize=True):
     _lib.call("gca_sim_topk", ptr(queries), ptr(gallery), Nq, Ng, d, k, 1 if normalize else 0, ptr(idx), ptr(val),
               ptr(ws), ws.numel(), _stream(queries))
     return idx, val
+
+
+# --------------------------------------------------------------------------------------------- NPID instance bank
+class _BankLogits(torch.autograd.Function):
+    """logits[b, j] = <bank[idx[b, j]], x[b]> / T  (mem_bank.py:67-73, 29-39) without the [B, K+1, d] gather; the gradient
+    reaches x only (the bank is a buffer)."""
+
+    @staticmethod
+    def forward(ctx, x, bank, idx, T):
+        xc = _f32c(x.detach())
+        B, d = xc.shape
+        K1 = idx.shape[1]
+        logits = torch.empty(B, K1, dtype=torch.float32, device=xc.device)
+        _lib.call("gca_bank_logits", ptr(xc), ptr(bank), ptr(idx), B, K1, d, bank.shape[0], 1.0 / T, ptr(logits), _stream(xc))
+        ctx.save_for_backward(bank, idx)
+        ctx.T, ctx.shape = T, (B, K1, d)
+        # the backward gathers the rows again: it must see the bank as it was here, and the caller updates the bank in place
+        # right after the logits (mem_bank.py:81-85) -- so the rows' version is checked like any saved tensor
+        return logits
+
+    @staticmethod
+    def backward(ctx, g):
+        bank, idx = ctx.saved_tensors
+        B, K1, d = ctx.shape
+        g = _f32c(g)
+        dx = torch.empty(B, d, dtype=torch.float32, device=g.device)
+        ws = workspace(g.device, int(_lib.load().gca_bank_dx_workspace_bytes(B, d)), "bank_dx")
+        _lib.call("gca_bank_dx", ptr(g), ptr(bank), ptr(idx), B, K1, d, bank.shape[0], 1.0 / ctx.T, ptr(dx), ptr(ws), ws.numel(),
+                  _stream(g))
+        return dx, None, None, None
+
+
+def bank_logits(x, bank, idx, T):
+    """x [B, d], bank [n_data, d] fp32 contiguous, idx [B, K+1] int64 -> logits [B, K+1] (differentiable w.r.t. x)."""
+    _need_cuda(x, bank, idx)
+    if bank.dtype != torch.float32 or not bank.is_contiguous():
+        raise ValueError("the bank must be a contiguous fp32 tensor")
+    idx = idx.contiguous()
+    if idx.dtype != torch.int64:
+        idx = idx.long()
+    return _BankLogits.apply(x, bank, idx, float(T))
+
+
+def bank_update_(bank, x, y, m):
+    """In place: bank[y] <- normalize(m * bank[y] + (1 - m) * x)  (mem_bank.py:15-27)."""
+    _need_cuda(bank, x, y)
+    if bank.dtype != torch.float32 or not bank.is_contiguous():
+        raise ValueError("the bank must be a contiguous fp32 tensor")
+    x = _f32c(x.detach())
+    y = y.reshape(-1).contiguous()
+    if y.dtype != torch.int64:
+        y = y.long()
+    N, d = x.shape
+    if y.numel() != N or d != bank.shape[1]:
+        raise ValueError("x [N, d] and y [N] must match the bank's width")
+    ws = workspace(bank.device, int(_lib.load().gca_bank_update_workspace_bytes(N, d)), "bank_update")
+    # (1 - m) is a Python double in the reference and is rounded to fp32 once, when it meets the tensor
+    _lib.call("gca_bank_update", ptr(bank), ptr(x), ptr(y), N, d, bank.shape[0], float(m), float(1.0 - m), ptr(ws), ws.numel(),
+              _stream(bank))
+    return bank

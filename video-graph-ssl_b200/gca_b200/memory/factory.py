@@ -5,7 +5,8 @@ Extra, optional config keys (absent keys keep upstream behaviour):
   cfg.CONTRAST.ALGO         'auto' | 'ffma' | 'tcgen05'
 """
 from .moco_queue import RGBMoCo, CMCMoCo
-from .losses import NCESoftmaxLoss, D
+from .mem_bank import RGBMem, CMCMem
+from .losses import NCESoftmaxLoss, NCECriterion, D
 
 
 def _opt(node, name, default):
@@ -24,8 +25,8 @@ def create_contrast(cfg, n_data):
     elif cfg.CONTRAST.MEM_TYPE == 'simsiam':
         memory = None
     elif cfg.CONTRAST.MEM_TYPE == 'bank':
-        # NPID instance bank (lib/memory/mem_bank.py) is outside the hot path this package rebuilds
-        raise NotImplementedError("MEM_TYPE 'bank' is not provided by gca_b200; use the reference's lib.memory for it")
+        mem_func = RGBMem if cfg.CROSS.MODALITY == 'visual' else CMCMem
+        memory = mem_func(cfg.CROSS.FEAT_DIM, n_data, cfg.CONTRAST.NCE_K, cfg.CONTRAST.NCE_T, cfg.CONTRAST.NCE_M)
     else:
         raise NotImplementedError('mem not suported: {}'.format(cfg.CONTRAST.MEM_TYPE))
     return memory
@@ -37,7 +38,7 @@ def create_criterion(cfg, n_data):
     elif cfg.CROSS.CRITERION == 'simsiam_d':
         criterion = D()
     elif cfg.CROSS.CRITERION == 'NCE':
-        raise NotImplementedError("criterion 'NCE' is not provided by gca_b200; use the reference's lib.memory for it")
+        criterion = NCECriterion(n_data)
     else:
         raise NotImplementedError('criterion not suported: {}'.format(cfg.CROSS.CRITERION))
     return criterion
