@@ -53,7 +53,11 @@ def bank_update(memory, x, y, m):
     w = memory.index_select(0, y.view(-1))
     w = w * m + x * (1 - m)
     w = w / w.norm(2, dim=1, keepdim=True).clamp_min(1e-12)
-    memory.index_copy_(0, y.view(-1), w)
+    # index_copy_ with a duplicated index is sequential on one CPU thread (how the fixture was generated: the last occurrence
+    # wins) but unordered once ATen parallelises it; restate the sequential order explicitly
+    yy = y.view(-1).tolist()
+    for n, r in enumerate(yy):
+        memory[r] = w[n]
     return memory
 
 

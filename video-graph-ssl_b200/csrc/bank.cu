@@ -24,43 +24,49 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc)
     return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
 
-// grid (ceil((K+1) / rows per CTA), B); a warp takes rows w, w + 8, ... of its CTA's slice, four at a time
+// grid (ceil((K+1) / rows per CTA), B); the warps of a CTA take its slice eight rows at a time
+template <int NCH>                                  // float4 chunks per lane and row: d <= 128 * NCH
 __global__ void __launch_bounds__(BK_THREADS)
 bank_logits_kernel(const float* __restrict__ x, const float* __restrict__ bank, const long long* __restrict__ idx, int K1, int d,
                    long long n_data, float inv_T, int rows_per_cta, float* __restrict__ logits)
 {
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d4 = d >> 2;
-    float4 xr[BK_MAX_CH];
+    float4 xr[NCH];
 #pragma unroll
-    for (int c = 0; c < BK_MAX_CH; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int i = lane + 32 * c;
         xr[c] = (i < d4) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)b * d) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const int j0 = blockIdx.x * rows_per_cta, j1 = min(K1, j0 + rows_per_cta);
     const long long* irow = idx + (size_t)b * K1;
     float* lrow = logits + (size_t)b * K1;
-    constexpr int NW = BK_THREADS / 32;
-    for (int j = j0 + warp * 4; j < j1; j += NW * 4) {
-        long long r[4];
-        float acc[4];
+    constexpr int NW = BK_THREADS / 32, U = 8;        // rows in flight per warp
+    long long rn[U];                                  // indices of the NEXT iteration: their load overlaps this one's row reads
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { r[u] = (j + u < j1) ? __ldg(irow + j + u) : -1; acc[u] = 0.f; }
+    for (int u = 0; u < U; ++u) { const int jj = j0 + warp * U + u; rn[u] = (jj < j1) ? __ldg(irow + jj) : -1; }
+    for (int j = j0 + warp * U; j < j1; j += NW * U) {
+        long long r[U];
+        float acc[U];
 #pragma unroll
-        for (int c = 0; c < BK_MAX_CH; ++c) {
+        for (int u = 0; u < U; ++u) { r[u] = rn[u]; acc[u] = 0.f; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int jj = j + NW * U + u; rn[u] = (jj < j1) ? __ldg(irow + jj) : -1; }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
             const int i = lane + 32 * c;
             if (i < d4) {
-                float4 v[4];
+                float4 v[U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < U; ++u)
                     v[u] = (r[u] >= 0 && r[u] < n_data) ? __ldg(reinterpret_cast<const float4*>(bank + (size_t)r[u] * d) + i)
                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) acc[u] = dot4(v[u], xr[c], acc[u]);
+                for (int u = 0; u < U; ++u) acc[u] = dot4(v[u], xr[c], acc[u]);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const float s = warp_sum(acc[u]);
             if (lane == 0 && j + u < j1)
                 lrow[j + u] = (r[u] >= 0 && r[u] < n_data) ? s * inv_T : __int_as_float(0x7fc00000);   // index out of range: NaN
@@ -70,6 +76,7 @@ bank_logits_kernel(const float* __restrict__ x, const float* __restrict__ bank, 
 
 // grid (S, B): CTA (s, b) sums the rows j = s * 8 + warp, + S * 8, ... of feature row b (fixed order per warp), the eight
 // warps are added in order, the S partials of a row by bank_dx_reduce_kernel in order
+template <int NCH>
 __global__ void __launch_bounds__(BK_THREADS)
 bank_dx_kernel(const float* __restrict__ g, const float* __restrict__ bank, const long long* __restrict__ idx, int K1, int d,
                long long n_data, float* __restrict__ part /* [S, B, d] */)
@@ -78,32 +85,43 @@ bank_dx_kernel(const float* __restrict__ g, const float* __restrict__ bank, cons
     const int b = blockIdx.y, S = gridDim.x, B = gridDim.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d4 = d >> 2;
     constexpr int NW = BK_THREADS / 32;
-    float4 acc[BK_MAX_CH];
+    float4 acc[NCH];
 #pragma unroll
-    for (int c = 0; c < BK_MAX_CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < NCH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     const long long* irow = idx + (size_t)b * K1;
     const float* grow = g + (size_t)b * K1;
     const int stride = S * NW;
-    for (int j = blockIdx.x * NW + warp; j < K1; j += 4 * stride) {
-        long long r[4];
-        float w[4];
+    constexpr int U = 8;                              // rows in flight per warp
+    long long rn[U];
+    float wn[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int jj = j + u * stride;
-            r[u] = (jj < K1) ? __ldg(irow + jj) : -1;
-            w[u] = (jj < K1) ? __ldg(grow + jj) : 0.f;
+    for (int u = 0; u < U; ++u) {
+        const int jj = blockIdx.x * NW + warp + u * stride;
+        rn[u] = (jj < K1) ? __ldg(irow + jj) : -1;
+        wn[u] = (jj < K1) ? __ldg(grow + jj) : 0.f;
+    }
+    for (int j = blockIdx.x * NW + warp; j < K1; j += U * stride) {
+        long long r[U];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { r[u] = rn[u]; w[u] = wn[u]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {                  // indices / weights of the next iteration: overlap this one's row reads
+            const int jj = j + (U + u) * stride;
+            rn[u] = (jj < K1) ? __ldg(irow + jj) : -1;
+            wn[u] = (jj < K1) ? __ldg(grow + jj) : 0.f;
         }
 #pragma unroll
-        for (int c = 0; c < BK_MAX_CH; ++c) {
+        for (int c = 0; c < NCH; ++c) {
             const int i = lane + 32 * c;
             if (i < d4) {
-                float4 v[4];
+                float4 v[U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < U; ++u)
                     v[u] = (r[u] >= 0 && r[u] < n_data) ? __ldg(reinterpret_cast<const float4*>(bank + (size_t)r[u] * d) + i)
                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     acc[c].x = fmaf(w[u], v[u].x, acc[c].x); acc[c].y = fmaf(w[u], v[u].y, acc[c].y);
                     acc[c].z = fmaf(w[u], v[u].z, acc[c].z); acc[c].w = fmaf(w[u], v[u].w, acc[c].w);
                 }
@@ -111,7 +129,7 @@ bank_dx_kernel(const float* __restrict__ g, const float* __restrict__ bank, cons
         }
     }
 #pragma unroll
-    for (int c = 0; c < BK_MAX_CH; ++c) { const int i = lane + 32 * c; if (i < d4) sm[warp * d4 + i] = acc[c]; }
+    for (int c = 0; c < NCH; ++c) { const int i = lane + 32 * c; if (i < d4) sm[warp * d4 + i] = acc[c]; }
     __syncthreads();
     for (int i = threadIdx.x; i < d4; i += BK_THREADS) {
         float4 t = sm[i];
@@ -187,7 +205,7 @@ static int bank_dx_splits(int B)
 {
     int sms = sm_count_cached();
     if (sms < 1) sms = 148;
-    int S = (2 * sms + B - 1) / B;                    // about two CTAs per SM in all
+    int S = (4 * sms + B - 1) / B;                    // about four CTAs per SM in all
     if (S < 1) S = 1;
     if (S > 16) S = 16;
     return S;
@@ -213,14 +231,17 @@ extern "C" int gca_bank_logits(const float* x, const float* bank, const long lon
     int rc = bank_check("gca_bank_logits", B, K1, d, n_data);
     if (rc != GCA_OK) return rc;
     GCA_CHECK_ARG(B <= 65535, "gca_bank_logits: B <= 65535");
-    // rows per CTA: a multiple of 32 (8 warps x 4 rows), enough CTAs to fill the GPU a few times over
+    // rows per CTA: a multiple of 64 (8 warps x 8 rows), enough CTAs to fill the GPU a few times over
     int sms = sm_count_cached();
     long long want = ((long long)B * K1 + 8ll * sms - 1) / (8ll * sms);
-    int rows = (int)((want + 31) / 32 * 32);
-    if (rows < 32) rows = 32;
+    int rows = (int)((want + 63) / 64 * 64);
+    if (rows < 64) rows = 64;
     if (rows > 1024) rows = 1024;
     dim3 grid((K1 + rows - 1) / rows, B);
-    bank_logits_kernel<<<grid, BK_THREADS, 0, (cudaStream_t)stream>>>(x, bank, idx, K1, d, n_data, inv_T, rows, logits);
+    const int nch = (d / 4 + 31) / 32;
+#define GCA_BANK_LOGITS(N) bank_logits_kernel<N><<<grid, BK_THREADS, 0, (cudaStream_t)stream>>>(x, bank, idx, K1, d, n_data, inv_T, rows, logits)
+    if (nch <= 1) GCA_BANK_LOGITS(1); else if (nch <= 2) GCA_BANK_LOGITS(2); else if (nch <= 4) GCA_BANK_LOGITS(4); else GCA_BANK_LOGITS(8);
+#undef GCA_BANK_LOGITS
     GCA_LAUNCH_CHECK("bank_logits_kernel");
     count_launch(1);
     return GCA_OK;
@@ -246,7 +267,10 @@ extern "C" int gca_bank_dx(const float* g_logits, const float* bank, const long 
     const int S = bank_dx_splits(B);
     float* part = (float*)workspace;
     const size_t smem = (size_t)(BK_THREADS / 32) * (d / 4) * sizeof(float4);
-    bank_dx_kernel<<<dim3(S, B), BK_THREADS, smem, (cudaStream_t)stream>>>(g_logits, bank, idx, K1, d, n_data, part);
+    const int nch = (d / 4 + 31) / 32;
+#define GCA_BANK_DX(N) bank_dx_kernel<N><<<dim3(S, B), BK_THREADS, smem, (cudaStream_t)stream>>>(g_logits, bank, idx, K1, d, n_data, part)
+    if (nch <= 1) GCA_BANK_DX(1); else if (nch <= 2) GCA_BANK_DX(2); else if (nch <= 4) GCA_BANK_DX(4); else GCA_BANK_DX(8);
+#undef GCA_BANK_DX
     GCA_LAUNCH_CHECK("bank_dx_kernel");
     const long long n = (long long)B * d;
     bank_dx_reduce_kernel<<<(unsigned)((n + BK_THREADS - 1) / BK_THREADS), BK_THREADS, 0, (cudaStream_t)stream>>>(part, S, n, inv_T, dx);
