@@ -166,7 +166,6 @@ infonce_finalize_kernel(const FinalizeParams F)
     int ns = F.nsplit;
     const int grp = tid / FIN_COLS, col = tid % FIN_COLS;
     size_t stride = (size_t)F.Bpad * F.d;                      // floats between two splits of the accumulator partials
-    size_t sstride = (size_t)F.Bpad;                           // ... of the statistics
     const float* p_max = F.part_max; const float* p_sum = F.part_sum; const int* p_cnt = F.part_cnt; const float* p_acc = F.part_acc;
     float* out_row = (kMode == FIN_SHARD) ? (F.out_acc ? F.out_acc + (size_t)b * F.d : nullptr) : (F.dq ? F.dq + (size_t)b * F.d : nullptr);
     float* o_max = F.out_max ? F.out_max + b : nullptr; float* o_sum = F.out_sum ? F.out_sum + b : nullptr;
@@ -200,9 +199,11 @@ infonce_finalize_kernel(const FinalizeParams F)
     auto acc_of = [&](int sp) -> const float* {
         return peer_merge ? pm_rows(F.merge.mailboxes[sp], F.merge, mpar) : p_acc + (size_t)sp * stride;
     };
+    // statistics of split sp for this row: part_* [Bpad, nsplit] (gca_common.cuh), or -- cross-rank merge -- the max / sum / count
+    // arrays behind rank sp's rows block
     auto max_of = [&](int sp) -> const float* {
-        return peer_merge ? pm_rows(F.merge.mailboxes[sp], F.merge, mpar) + (size_t)F.merge.W * F.merge.Bl * F.merge.d
-                          : p_max + (size_t)sp * sstride;
+        return peer_merge ? pm_rows(F.merge.mailboxes[sp], F.merge, mpar) + (size_t)F.merge.W * F.merge.Bl * F.merge.d + brow
+                          : p_max + part_stat_index(sp, brow, F.nsplit);
     };
     const size_t stat_gap = peer_merge ? (size_t)F.merge.W * F.merge.Bl : 0;     // merge: max -> sum -> count arrays of a block
     if (peer_merge) p_acc = F.dq ? reinterpret_cast<const float*>(F.merge.mailboxes) : nullptr;      // (non-null marker only)
@@ -221,9 +222,10 @@ infonce_finalize_kernel(const FinalizeParams F)
 #pragma unroll
         for (int i = 0; i < FIN_STAT; ++i) {
             const int sp = lane + 32 * i;
-            const float* pm_ = max_of(sp < ns ? sp : 0) + brow;
-            const float* ps_ = peer_merge ? pm_ + stat_gap : p_sum + (size_t)(sp < ns ? sp : 0) * sstride + brow;
-            const int* pc_ = peer_merge ? reinterpret_cast<const int*>(ps_ + stat_gap) : p_cnt + (size_t)(sp < ns ? sp : 0) * sstride + brow;
+            const int spc = sp < ns ? sp : 0;
+            const float* pm_ = max_of(spc);
+            const float* ps_ = peer_merge ? pm_ + stat_gap : p_sum + part_stat_index(spc, brow, F.nsplit);
+            const int* pc_ = peer_merge ? reinterpret_cast<const int*>(ps_ + stat_gap) : p_cnt + part_stat_index(spc, brow, F.nsplit);
             st_m[i] = (sp < ns) ? ld_part(pm_, peer_merge) : -INFINITY;
             st_s[i] = (sp < ns) ? ld_part(ps_, peer_merge) : 0.f;
             st_c[i] = (sp < ns) ? ld_part(pc_, peer_merge) : 0;
@@ -273,13 +275,13 @@ infonce_finalize_kernel(const FinalizeParams F)
                     cnt += st_c[i];
                 }
             } else {                                           // many splits: two dependent passes over the statistics
-                for (int sp = lane; sp < ns; sp += 32) m = fmaxf(m, ld_part(max_of(sp) + brow, peer_merge));
+                for (int sp = lane; sp < ns; sp += 32) m = fmaxf(m, ld_part(max_of(sp), peer_merge));
                 m = warp_max(m);
                 if (kMode == FIN_FULL) m = fmaxf(m, pos);
                 for (int sp = lane; sp < ns; sp += 32) {
-                    const float* pm_ = max_of(sp) + brow;
-                    const float* ps_ = peer_merge ? pm_ + stat_gap : p_sum + (size_t)sp * sstride + brow;
-                    const int* pc_ = peer_merge ? reinterpret_cast<const int*>(ps_ + stat_gap) : p_cnt + (size_t)sp * sstride + brow;
+                    const float* pm_ = max_of(sp);
+                    const float* ps_ = peer_merge ? pm_ + stat_gap : p_sum + part_stat_index(sp, brow, F.nsplit);
+                    const int* pc_ = peer_merge ? reinterpret_cast<const int*>(ps_ + stat_gap) : p_cnt + part_stat_index(sp, brow, F.nsplit);
                     const float pm = ld_part(pm_, peer_merge);
                     const float e = (pm == -INFINITY) ? 0.f : __expf(pm - m);
                     w_s[sp] = e;

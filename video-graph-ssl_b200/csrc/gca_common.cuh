@@ -24,15 +24,21 @@ int sm_count_cached();          // SMs of the current device (cached per device)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// element of the split statistics part_max / part_sum / part_cnt (layout below)
+__host__ __device__ __forceinline__ size_t part_stat_index(int split, int row, int nsplit) { return (size_t)row * nsplit + split; }
+
 // ---------------------------------------------------------------------------------------------
 // Workspace layout shared by the InfoNCE stream kernels and the finalize kernels.
 //   [0, 256)                 : control block, 64 words: [0] ticket, [2..3] packed loss / hit word, [4] top-1, [5] top-5 hits,
 //                              [6] out-of-range-logit flag (all self-resetting); [12..13] device-addressable pointer to a
 //                              32-bit host completion word (gca_workspace_set_done_flag; 0 = off), [14] CTAs of the finalize
 //                              launch that are done, [15] number of completed steps (what is written to the completion word)
-//   part_max [nsplit, Bpad]  : natural-log max logit of the split        (-inf when the split is empty)
-//   part_sum [nsplit, Bpad]  : sum exp(logit - part_max)
-//   part_cnt [nsplit, Bpad]  : #negatives > positive in the split
+//   part_max [Bpad, nsplit]  : natural-log max logit of the split        (-inf when the split is empty)
+//   part_sum [Bpad, nsplit]  : sum exp(logit - part_max)
+//   part_cnt [Bpad, nsplit]  : #negatives > positive in the split
+//                              (row-major over the ROW: the finalize CTA of a row reads its nsplit statistics with three
+//                              coalesced loads -- split-major they were 32 different cache lines per load, ~480 L1 wavefronts
+//                              per CTA queued in front of the gradient partials; part_stat_index() below)
 //   part_acc [nsplit, Bpad, d] : sum exp(logit - part_max) * queue_row
 //   pos_tmp  [Bpad]          : positive logits (backward-recompute entry point)
 // Bpad = B rounded up to 128 so both kernel families index it the same way.

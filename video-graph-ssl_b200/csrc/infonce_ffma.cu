@@ -198,7 +198,7 @@ infonce_ffma_kernel(const InfoNceStreamParams P)
         for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         const int r = row0 + ty * MR + i;
         if (tx == 0 && r < P.Bpad) {
-            const size_t o = (size_t)split * P.Bpad + r;
+            const size_t o = part_stat_index(split, r, P.nsplit);
             P.part_max[o] = m_run[i];
             P.part_sum[o] = s_run[i];
             P.part_cnt[o] = c;

@@ -276,7 +276,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             w_ot = 1.f;
         }
         if (g == 0) {
-            const size_t po = (size_t)split * P.Bpad + row;
+            const size_t po = part_stat_index(split, row, P.nsplit);
             P.part_max[po] = kFixedMax ? 0.f : m_all * 0.6931471805599453f;  // back to natural-log units
             // logits beyond the unit-row range (un-normalised inputs): the finalize kernel must not use its packed
             // fixed-point loss word (control word 6, cleared by the finalize kernel)

@@ -404,7 +404,7 @@ infonce_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         // =============================================================================================== epilogue
         if (cg == 0) {
             // one thread per row: the split statistics
-            const size_t po = (size_t)split * P.Bpad + row;
+            const size_t po = part_stat_index(split, row, P.nsplit);
             const float m_nat = m_ref * 0.6931471805599453f;
             P.part_max[po] = (n > 0) ? m_nat : -INFINITY;
             P.part_sum[po] = (n > 0) ? s_run : 0.f;
