@@ -337,7 +337,7 @@ def run_single(args):
     sampler.mark_end()
     clocks = sampler.stop()
     ms_per_step = ev0.elapsed_time(ev1) / args.steps
-    launches = steps_g[0].launches_per_step * args.steps
+    launches = (steps_g[0].plan.launches if steps_g[0].plan is not None else steps_g[0].launches_per_step) * args.steps
     loss_last = float(steps_g[(args.warmup + args.steps - 1) % QPOOL].loss)
     # round 1's figure for continuity: one step between its own event pair, L2 flushed before it
     iso = []
@@ -625,7 +625,10 @@ def run_multi(args, rank, world, local_rank):
     if sampler:
         sampler.mark_end()
     clocks = sampler.stop() if sampler else None
-    launches = (steps_g[0].launches_per_step * args.steps) if graphed else int(lib.gca_launch_count() - n0)
+    if graphed and steps_g[0].plan is not None and not steps_g[0].prefer_graph:
+        launches = steps_g[0].plan.launches * args.steps     # the timed steps were re-issued from the launch plan
+    else:
+        launches = (steps_g[0].launches_per_step * args.steps) if graphed else int(lib.gca_launch_count() - n0)
     tot = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(tot, op=dist.ReduceOp.MAX)              # max over ranks of the device-timed total
     ms_per_step = float(tot) / args.steps
