@@ -1046,6 +1046,49 @@ def test_launch_plan_equals_graph_replay(lib, B, N, K):
     assert torch.equal(mocos[0].memory, mocos[1].memory)
 
 
+def test_launch_plan_of_the_projection_step(lib, GF):
+    """gca_moco_step_proj is recordable too (same launches as the plain step): a plan over static buffers with the
+    device-resident ring pointer, run three times, equals three direct calls -- loss, dz, normalised keys, queue, pointer."""
+    import ctypes
+    from gca_b200 import _lib
+    from gca_b200._lib import ptr
+    gen = torch.Generator().manual_seed(19)
+    B, K, T = 96, 2048, 0.07
+    mem0 = cu(unit_rows(K, 128, gen)).to(torch.bfloat16)
+    zs = [(cu(torch.randn(B, 128, generator=gen) * 2.0), cu(torch.randn(B, 128, generator=gen) * 0.3)) for _ in range(3)]
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    res = []
+    for planned in (False, True):
+        mem = mem0.clone()
+        zq, zk = torch.empty(B, 128, device="cuda"), torch.empty(B, 128, device="cuda")
+        state = torch.tensor([K - B - 7, 0], dtype=torch.int64, device="cuda")          # the second step wraps
+        loss = torch.zeros(1, device="cuda"); rows = torch.zeros(B, device="cuda"); lse = torch.zeros(B, device="cuda")
+        pos = torch.zeros(B, device="cuda"); rank = torch.zeros(B, dtype=torch.int32, device="cuda")
+        hits = torch.zeros(2, dtype=torch.int32, device="cuda"); dz = torch.zeros(B, 128, device="cuda"); kh = torch.zeros(B, 128, device="cuda")
+        ws = torch.zeros(GF.infonce_workspace_bytes(B, K, 128, 1, "tcgen05"), dtype=torch.uint8, device="cuda")
+
+        def issue(stream):
+            _lib.call("gca_moco_step_proj", ptr(zq), ptr(zk), ptr(mem), 1, B, K, 128, 1.0 / T, 2, None, B, 0, ptr(state),
+                      ptr(loss), ptr(rows), ptr(lse), ptr(pos), ptr(rank), ptr(hits), ptr(dz), ptr(kh), ptr(ws), ws.numel(), stream)
+        plan = _lib.LaunchPlan.record(lambda: issue(None), mem.device) if planned else None
+        outs = []
+        for a, b in zs:
+            zq.copy_(a); zk.copy_(b)
+            if planned:
+                plan.run(st)
+            else:
+                issue(st)
+            outs.append((loss.clone(), dz.clone(), kh.clone(), rank.clone()))
+        torch.cuda.synchronize()
+        res.append((outs, mem, state.clone()))
+        if planned:
+            assert plan.launches == 3
+    for (l0, d0, k0, r0), (l1, d1, k1, r1) in zip(res[0][0], res[1][0]):
+        assert torch.equal(l0, l1) and torch.equal(d0, d1) and torch.equal(k0, k1) and torch.equal(r0, r1)
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert int(res[1][2][0]) == (K - B - 7 + 3 * B) % K
+
+
 def test_launch_plan_rejects_unrecordable_calls(lib, GF):
     """Only the tcgen05-family step entry points are recordable: a plan around an fp32-queue step is refused (the call
     itself has then run normally), and begin / end / run misuse returns error codes."""

@@ -222,6 +222,7 @@ extern "C" int gca_sm_count(void)
 
 // ---- launch plans (launch_plan.cuh) ----------------------------------------------------------------------------------
 struct gca_plan { gca::LaunchPlan plan; };
+static thread_local gca_plan* t_plan_owner = nullptr;      // the object whose .plan this thread records into
 
 extern "C" int gca_plan_begin(void)
 {
@@ -230,6 +231,7 @@ extern "C" int gca_plan_begin(void)
     if (sm_count_cached() < 1) return set_err(GCA_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
     gca_plan* p = new gca_plan();
     cudaGetDevice(&p->plan.device);
+    t_plan_owner = p;
     t_plan = &p->plan;
     return GCA_OK;
 }
@@ -238,8 +240,9 @@ extern "C" int gca_plan_end(gca_plan** out)
 {
     using namespace gca;
     if (!t_plan) return set_err(GCA_ERR_BAD_ARG, "gca_plan_end: this thread is not recording");
-    gca_plan* p = reinterpret_cast<gca_plan*>(t_plan);   // (the plan is the first member)
+    gca_plan* p = t_plan_owner;
     t_plan = nullptr;
+    t_plan_owner = nullptr;
     if (out) *out = nullptr;
     if (!out) { delete p; return set_err(GCA_ERR_BAD_ARG, "gca_plan_end: null output pointer"); }
     if (p->plan.recorded == 0 || p->plan.recorded != p->plan.counted) {
@@ -257,6 +260,9 @@ extern "C" int gca_plan_run(gca_plan* p, void* stream)
     using namespace gca;
     GCA_CHECK_ARG(p != nullptr, "gca_plan_run: null plan");
     if (t_plan) return set_err(GCA_ERR_BAD_ARG, "gca_plan_run: called while recording");
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != p->plan.device)
+        return set_err(GCA_ERR_BAD_ARG, "gca_plan_run: the plan was recorded on device %d, the current device is %d", p->plan.device, dev);
     cudaStream_t st = (cudaStream_t)stream, side = nullptr;
     for (PlanOp& op : p->plan.ops) {
         switch (op.kind) {
@@ -282,7 +288,7 @@ extern "C" int gca_plan_launches(const gca_plan* p) { return p ? p->plan.recorde
 
 extern "C" void gca_plan_destroy(gca_plan* p)
 {
-    if (p && gca::t_plan == &p->plan) gca::t_plan = nullptr;
+    if (p && gca::t_plan == &p->plan) { gca::t_plan = nullptr; t_plan_owner = nullptr; }
     delete p;
 }
 

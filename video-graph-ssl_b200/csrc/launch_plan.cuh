@@ -63,7 +63,8 @@ inline cudaError_t launch_ex(const cudaLaunchConfig_t* cfg, void (*kern)(KArgs..
     op.lane = plan_is_side_stream(cfg->stream) ? 1 : 0;
     op.func = reinterpret_cast<const void*>(kern);
     op.cfg = *cfg;
-    op.nattrs = (int)cfg->numAttrs < 4 ? (int)cfg->numAttrs : 4;
+    if (cfg->numAttrs > 4) return cudaErrorInvalidValue;         // (no launch site of this library sets more than three)
+    op.nattrs = (int)cfg->numAttrs;
     for (int i = 0; i < op.nattrs; ++i) op.attrs[i] = cfg->attrs[i];
     op.cfg.attrs = nullptr;                    // re-pointed at op.attrs when the plan runs (ops move inside the vector)
     op.cfg.stream = nullptr;
