@@ -91,24 +91,42 @@ __device__ __forceinline__ void enqueue_rows(const FinalizeParams& F, int blk, i
         timed_out = (__syncthreads_and(ok) == 0);
         keys = xchg_slot(F.xchg.mailboxes[F.xchg.rank], F.xchg, (int)(xstep & 1ull), 0);
     }
-    for (long long i = (long long)blk * FIN_THREADS + threadIdx.x; !timed_out && i < total; i += (long long)nblk * FIN_THREADS) {
-        const int row = (int)(i / d4), c4 = (int)(i - (long long)row * d4);
-        long long slot = index + row;
-        if (slot >= F.enq_K) slot -= F.enq_K;
-        if (F.enq_kend > 0) {                                 // K-sharded queue: this rank stores only the slots it owns
-            if (slot < F.enq_kbegin || slot >= F.enq_kend) continue;
-            slot -= F.enq_kbegin;
+    // four rows' worth of loads in flight per thread before the first store (W ranks' keys: W * B * d / 4 items over <= 64 CTAs)
+    const long long step_i = (long long)nblk * FIN_THREADS;
+    for (long long i0 = (long long)blk * FIN_THREADS + threadIdx.x; !timed_out && i0 < total; i0 += 4 * step_i) {
+        float4 v[4];
+        long long off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * step_i;
+            off[u] = -1;
+            if (i < total) {
+                const int row = (int)(i / d4), c4 = (int)(i - (long long)row * d4);
+                long long slot = index + row;
+                if (slot >= F.enq_K) slot -= F.enq_K;
+                bool mine = true;
+                if (F.enq_kend > 0) {                         // K-sharded queue: this rank stores only the slots it owns
+                    mine = (slot >= F.enq_kbegin && slot < F.enq_kend);
+                    slot -= F.enq_kbegin;
+                }
+                if (mine) {
+                    v[u] = peer ? ld_cg_f4(keys + i) : __ldg(keys + i);
+                    off[u] = slot * d4 + c4;
+                }
+            }
         }
-        const float4 v = peer ? ld_cg_f4(keys + i) : __ldg(keys + i);
-        const long long off = slot * d4 + c4;
-        if constexpr (sizeof(QT) == 4) {
-            reinterpret_cast<float4*>(queue)[off] = v;
-        } else {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            reinterpret_cast<uint2*>(queue)[off] = pk;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (off[u] < 0) continue;
+            if constexpr (sizeof(QT) == 4) {
+                reinterpret_cast<float4*>(queue)[off[u]] = v[u];
+            } else {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y), hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                reinterpret_cast<uint2*>(queue)[off[u]] = pk;
+            }
         }
     }
     if (F.enq_state) {                                        // device-resident pointer: the last enqueue CTA advances it
