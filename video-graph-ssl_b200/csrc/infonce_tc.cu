@@ -628,8 +628,7 @@ int infonce_tc_launch(const InfoNceStreamParams& P_, bool fixed_max, cudaStream_
     // loss + gradient in one sweep (the product path): second-generation stream kernel (infonce_tcx.cu)
     const bool use_tcx = P.part_acc != nullptr && !fixed_max && P.logits_out == nullptr && infonce_tcx_enabled();
     if (!P.skip_prep) {
-        int prep_rows = 8;                                   // rows (warps) per CTA of the prep launch
-        { const char* e = getenv("GCA_PREP_ROWS"); if (e && P.xchg.mailboxes == nullptr) { const int r = atoi(e); if (r == 1 || r == 2 || r == 4) prep_rows = r; } }
+        constexpr int prep_rows = 8;                         // rows (warps) per CTA of the prep launch (1 / 2 / 4 measured: no difference)
         const int nprep = (P.Bpad + prep_rows - 1) / prep_rows;
         // peer exchange: the q|k gather of the K-sharded step rides in this launch (its rows are needed by this very launch);
         // the key push of the replica step goes out as its own small launch on a side stream (joined by the caller after the
