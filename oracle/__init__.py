@@ -23,3 +23,4 @@ from .infonce import (logits_full, infonce_loss, infonce_grad_q, infonce_step,  
 from .graph import hop_distance, hop_weights, graph_forward, graph_forward_backward  # noqa: F401
 from .negcos import neg_cosine, neg_cosine_grad                               # noqa: F401
 from .retrieval import cosine_topk, recall_hits                               # noqa: F401
+from . import bank                                                            # noqa: F401  (NPID instance bank: mem_bank.py)
