@@ -1,11 +1,17 @@
 #!/bin/bash
+# where do finalize's partial reads come from?  one-pass ncu (no cache flush, no replay): DRAM bytes of the step's kernels
 cd ${GRAFT_REPO_ROOT:-.}; mkdir -p gpurun_out
-N=2
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_n$N.log 2>&1; grep -E "^FAILED|passed|failed" gpurun_out/pytest_gpu_n$N.log | head; grep -E "^E  " gpurun_out/pytest_gpu_n$N.log | head -20
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus $N --steps 1000 --warmup 20 --no-sharded > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
-echo "bench exit $?"; grep -v "OMP_NUM\|^\*\*\*" gpurun_out/bench_n$N.err | tail -2
-python - $N <<'PY'
-import json, sys
-d = json.loads(open("gpurun_out/bench_n%s.json" % sys.argv[1]).read().strip().splitlines()[-1])
-print({k: d.get(k) for k in ("value", "ms_per_step", "ms_per_step_isolated", "replicas_consistent", "gpu_launches")}, "e2e", d["e2e"]["ms_per_step"])
+timeout 200 ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
+  -k regex:"infonce_tcx|infonce_finalize|infonce_prep" -s 90 -c 9 --csv --log-file gpurun_out/r02_step_dram_nocachectl.csv \
+  python bench.py --steps 40 --warmup 3 --no-cpu --no-secondary > gpurun_out/ncu_nocc.log 2>&1
+echo "exit $?"
+python - <<'PY'
+import csv
+rows = [r for r in csv.reader(open("gpurun_out/r02_step_dram_nocachectl.csv")) if len(r) > 10]
+h = rows[0]; ki, mi, vi, ii = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("ID")
+d = {}
+for r in rows[1:]:
+    d.setdefault((int(r[ii]), r[ki].split("(")[0][-40:]), {})[r[mi]] = r[vi]
+for k, v in sorted(d.items()):
+    print(k, v)
 PY
