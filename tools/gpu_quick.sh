@@ -1,17 +1,10 @@
 #!/bin/bash
-# where do finalize's partial reads come from?  one-pass ncu (no cache flush, no replay): DRAM bytes of the step's kernels
+# smallest end-to-end sanity on one GPU: smoke() and one short bench line
 cd ${GRAFT_REPO_ROOT:-.}; mkdir -p gpurun_out
-timeout 200 ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
-  -k regex:"infonce_tcx|infonce_finalize|infonce_prep" -s 90 -c 9 --csv --log-file gpurun_out/r02_step_dram_nocachectl.csv \
-  python bench.py --steps 40 --warmup 3 --no-cpu --no-secondary > gpurun_out/ncu_nocc.log 2>&1
-echo "exit $?"
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
+timeout 300 python bench.py --steps 500 --warmup 20 --no-cpu > gpurun_out/bench_short.json 2> gpurun_out/bench_short.err; echo "bench exit $?"; tail -2 gpurun_out/bench_short.err
 python - <<'PY'
-import csv
-rows = [r for r in csv.reader(open("gpurun_out/r02_step_dram_nocachectl.csv")) if len(r) > 10]
-h = rows[0]; ki, mi, vi, ii = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("ID")
-d = {}
-for r in rows[1:]:
-    d.setdefault((int(r[ii]), r[ki].split("(")[0][-40:]), {})[r[mi]] = r[vi]
-for k, v in sorted(d.items()):
-    print(k, v)
+import json
+d = json.loads(open("gpurun_out/bench_short.json").read().strip().splitlines()[-1])
+print({k: d[k] for k in ("value", "ms_per_step", "gpu_launches")}, "e2e", d["e2e"]["ms_per_step"], "pretrain", (d.get("pretrain_clips_per_s") or {}).get("clips_per_s"), list((d.get("secondary") or {}).keys()))
 PY
