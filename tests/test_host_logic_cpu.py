@@ -238,3 +238,21 @@ def test_pretrain_encoder_has_the_reference_r3d18_layer_shapes():
     with torch.no_grad():
         f = enc.layers(enc.stem(torch.randn(1, 3, 16, 112, 112)))
     assert list(f.shape) == g["feature_map_shape_for_1x3x16x112x112"]
+
+
+def test_cpu_placement_helper_is_best_effort():
+    """gca_b200.affinity: without a CUDA device (or NVML / sysfs information) nothing is bound and nothing raises; restore() of
+    an unbound record is a no-op; the sysfs parser understands cpulist ranges."""
+    import os
+    from gca_b200 import affinity
+    before = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    rec = affinity.bind_cpu_to_device(0)
+    assert isinstance(rec, dict) and set(rec) >= {"bound", "source", "cpus", "previous"}
+    if not torch.cuda.is_available():
+        assert rec["bound"] is False
+    affinity.restore(rec)
+    affinity.restore(None)
+    if before is not None:
+        assert os.sched_getaffinity(0) == before
+    cpus, src = affinity._local_cpus("0000ffff:ff:1f.0")                # no such device: unknown, empty
+    assert cpus == set() and src == "unknown"
