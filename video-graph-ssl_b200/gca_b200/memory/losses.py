@@ -30,15 +30,12 @@ class NCECriterion(nn.Module):
         self.n_data = n_data
 
     def forward(self, x):
-        eps = 1e-7
-        bsz = x.shape[0]
-        m = x.size(1) - 1
-        Pn = 1 / float(self.n_data)                                   # noise distribution
-        P_pos = x.select(1, 0)
-        log_D1 = torch.div(P_pos, P_pos.add(m * Pn + eps)).log_()
-        P_neg = x.narrow(1, 1, m)
-        log_D0 = torch.div(P_neg.clone().fill_(m * Pn), P_neg.add(m * Pn + eps)).log_()
-        return - (log_D1.sum(0) + log_D0.view(-1, 1).sum(0)) / bsz
+        rows, negatives = x.shape[0], x.shape[1] - 1
+        noise = negatives / float(self.n_data)                        # m * Pn: expected noise mass against one data sample
+        shift = noise + 1e-7                                          # (eps of the reference, added in double like upstream)
+        log_d1 = (x[:, 0] / (x[:, 0] + shift)).log()                  # positives: P(data | x)
+        log_d0 = (noise / (x[:, 1:] + shift)).log()                   # negatives: P(noise | x)
+        return -(log_d1.sum() + log_d0.sum()).reshape(1) / rows       # shape [1], as upstream returns it
 
 
 class D(nn.Module):
